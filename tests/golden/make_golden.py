@@ -1,0 +1,235 @@
+"""Generate golden vectors by running the UNMODIFIED reference on CPU.
+
+Run in the authoring container only (needs /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Writes ``tests/golden/*.npz`` (inputs + reference outputs, all small).  The GPU
+box never runs this script; tests read the committed ``.npz`` files.
+
+Reference entry points exercised (mesnico/ALADIN @ d1bd7bf):
+  alad/loss.py:70-159   AlignmentContrastiveLoss  (all tensor pooling modes)
+  alad/loss.py:162-186  ContrastiveLoss           (dot / cosine, max_violation on/off)
+  alad/loss.py:359-447  DistillationLoss          (listnet)
+  alad/evaluation.py:158-327  i2t / t2i           (alignment callback and slot-0 path)
+  alad/recall_auxiliary.py:133-149  compute_recall
+"""
+import contextlib
+import io
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+REF = os.environ.get("ALAD_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+warnings.filterwarnings("ignore")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+# the reference calls .cuda() unconditionally in i2t/t2i (evaluation.py:179,202,267,291)
+torch.Tensor.cuda = lambda self, *a, **k: self
+
+import alad.loss as rloss  # noqa: E402
+import alad.evaluation as reval  # noqa: E402
+import alad.recall_auxiliary as rrec  # noqa: E402
+
+torch.manual_seed(0)
+torch.set_num_threads(4)
+
+
+def rs(seed):
+    return np.random.RandomState(seed)
+
+
+def t(x, grad=False):
+    return torch.tensor(np.asarray(x, dtype=np.float32), requires_grad=grad)
+
+
+def save(name, **kw):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **kw)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+# ---------------------------------------------------------------------------------------
+# 1. alignment scores, rectangular, ragged, every tensor pooling mode
+# ---------------------------------------------------------------------------------------
+def golden_alignment_scores():
+    r = rs(11)
+    Bi, Bc, S_im, S_s, d = 5, 7, 9, 12, 32
+    im = r.standard_normal((Bi, S_im, d)).astype(np.float32) * 1.7
+    s = r.standard_normal((Bc, S_s, d)).astype(np.float32) * 0.6
+    im[2, 4] = 0.0                        # an all-zero token (normalize eps path)
+    im_len = [9, 4, 1, 6, 9]              # full, ragged, zero scored regions (len-1 == 0)
+    s_len = [12, 3, 7, 5, 12, 4, 9]       # full container, zero scored words (len-3 == 0), ragged
+    out = {}
+    for agg in ("sum", "mean", "MrSw", "MrAVGw", "symm", "MwSr"):
+        crit = rloss.AlignmentContrastiveLoss(aggregation=agg)
+        with torch.no_grad():
+            S = crit(t(im), t(s), im_len, s_len, return_loss=False, return_similarity_mat=True)
+        out["S_" + agg] = S.numpy()
+    save("alignment_scores", im=im, s=s, im_len=np.array(im_len), s_len=np.array(s_len), **out)
+
+
+# ---------------------------------------------------------------------------------------
+# 2. alignment loss + gradients (square), max_violation on/off, permuted [S,B,d] inputs
+# ---------------------------------------------------------------------------------------
+def golden_alignment_loss():
+    r = rs(12)
+    B, S_im, S_s, d = 6, 8, 11, 48
+    im_sbd = r.standard_normal((S_im, B, d)).astype(np.float32)
+    s_sbd = r.standard_normal((S_s, B, d)).astype(np.float32)
+    # make the diagonal pairs related so that the hinge has both active and inactive rows
+    for b in range(B):
+        s_sbd[1:6, b] += 1.5 * im_sbd[1:6, b]
+    im_len = [8, 5, 8, 3, 6, 7]
+    s_len = [11, 6, 9, 11, 5, 8]
+    out = {}
+    for mv in (True, False):
+        im_t = t(im_sbd, True)
+        s_t = t(s_sbd, True)
+        crit = rloss.AlignmentContrastiveLoss(margin=0.2, measure="dot", max_violation=mv, aggregation="MrSw")
+        loss, S = crit(im_t.permute(1, 0, 2), s_t.permute(1, 0, 2), im_len, s_len, return_similarity_mat=True)
+        loss.backward()
+        k = "mv" if mv else "sum"
+        out[f"loss_{k}"] = loss.detach().numpy()
+        out[f"S_{k}"] = S.detach().numpy()
+        out[f"dim_{k}"] = im_t.grad.numpy()
+        out[f"ds_{k}"] = s_t.grad.numpy()
+    # dense upstream gradient on S (exercises the dense backward): L = sum(Gup * S)
+    Gup = r.standard_normal((B, B)).astype(np.float32)
+    im_t = t(im_sbd, True)
+    s_t = t(s_sbd, True)
+    crit = rloss.AlignmentContrastiveLoss(aggregation="MrSw")
+    S = crit(im_t.permute(1, 0, 2), s_t.permute(1, 0, 2), im_len, s_len, return_loss=False, return_similarity_mat=True)
+    (S * t(Gup)).sum().backward()
+    out["Gup"] = Gup
+    out["dim_dense"] = im_t.grad.numpy()
+    out["ds_dense"] = s_t.grad.numpy()
+    save("alignment_loss", im_sbd=im_sbd, s_sbd=s_sbd, im_len=np.array(im_len), s_len=np.array(s_len), **out)
+
+
+# ---------------------------------------------------------------------------------------
+# 3. matching head: ContrastiveLoss (dot, cosine) + gradients
+# ---------------------------------------------------------------------------------------
+def golden_matching():
+    r = rs(13)
+    B, d = 9, 40
+    im = r.standard_normal((B, d)).astype(np.float32)
+    s = (0.8 * im + r.standard_normal((B, d))).astype(np.float32)
+    im /= np.linalg.norm(im, axis=1, keepdims=True)
+    s /= np.linalg.norm(s, axis=1, keepdims=True)
+    out = {}
+    for measure in ("dot", "cosine"):
+        for mv in (True, False):
+            im_t, s_t = t(im * (1.0 if measure == "dot" else 2.5), True), t(s, True)
+            crit = rloss.ContrastiveLoss(margin=0.2, measure=measure, max_violation=mv)
+            loss, S = crit(im_t, s_t, return_similarity_mat=True)
+            loss.backward()
+            k = f"{measure}_{'mv' if mv else 'sum'}"
+            out[f"loss_{k}"] = loss.detach().numpy()
+            out[f"S_{k}"] = S.detach().numpy()
+            out[f"dim_{k}"] = im_t.grad.numpy()
+            out[f"ds_{k}"] = s_t.grad.numpy()
+    save("matching", im=im, s=s, **out)
+
+
+# ---------------------------------------------------------------------------------------
+# 4. triplet on raw matrices incl. ties / zero-violation rows; listnet distillation
+# ---------------------------------------------------------------------------------------
+def golden_triplet_listnet():
+    r = rs(14)
+    B = 10
+    S = r.standard_normal((B, B)).astype(np.float32)
+    S[np.arange(B), np.arange(B)] += 1.0
+    S[3, :] = -5.0
+    S[3, 3] = 5.0                         # row with no violation
+    S[:, 7] = np.minimum(S[:, 7], -4.0)
+    S[7, 7] = 4.0                         # column with no violation
+    S[5, 1] = S[5, 2] = 3.0               # tie for the hardest negative of row 5
+    out = {"S": S}
+    crit = rloss.Contrastive(margin=0.2, measure="dot", max_violation=True)
+    for mv in (True, False):
+        crit.max_violation = mv
+        S_t = t(S, True)
+        loss = crit.compute_contrastive_loss(S_t)
+        loss.backward()
+        k = "mv" if mv else "sum"
+        out[f"loss_{k}"] = loss.detach().numpy()
+        out[f"G_{k}"] = S_t.grad.numpy()
+    # listnet: teacher = alignment-like magnitudes (O(#words)), student = cosines
+    T = (r.standard_normal((B, B)) * 1.5 + 4.0).astype(np.float32)
+    M = np.clip(r.standard_normal((B, B)) * 0.3, -1, 1).astype(np.float32)
+    T_t, M_t = t(T, True), t(M, True)
+    dl = rloss.DistillationLoss(mode="listnet")
+    loss = dl(T_t, M_t)
+    loss.backward()
+    out.update(T=T, M=M, listnet_loss=loss.detach().numpy(), listnet_dM=M_t.grad.numpy(),
+               listnet_dT_is_none=np.array(T_t.grad is None))
+    save("triplet_listnet", **out)
+
+
+# ---------------------------------------------------------------------------------------
+# 5. retrieval: i2t / t2i (alignment callback + slot-0 path) and compute_recall
+# ---------------------------------------------------------------------------------------
+def make_eval_containers(seed, Ni, S, d, max_regions, max_words):
+    """[N,S,d] containers laid out like encode_data (evaluation.py:98-130): slot 0 =
+    global vector, tokens from slot 1, zero padding, every image row repeated 5x."""
+    r = rs(seed)
+    N = 5 * Ni
+    img_feat_len = r.randint(3, max_regions + 1, size=Ni)            # raw feat_len (incl. slot 0)
+    cap_len = r.randint(4, max_words + 1, size=N)                    # [CLS] w.. [SEP]
+    images = np.zeros((N, S, d), np.float32)
+    captions = np.zeros((N, S, d), np.float32)
+    base = r.standard_normal((Ni, S, d)).astype(np.float32)
+    for i in range(Ni):
+        L = img_feat_len[i]
+        base[i, L:] = 0
+        images[5 * i:5 * i + 5] = base[i]
+    for c in range(N):
+        L = cap_len[c]
+        noise = r.standard_normal((L, d)).astype(np.float32)
+        src = base[c // 5, 1 + r.randint(0, max(img_feat_len[c // 5] - 1, 1), size=L)]
+        captions[c, :L] = noise + 0.55 * src
+    img_lens = [int(img_feat_len[i // 5]) for i in range(N)]
+    return images, captions, img_lens, [int(x) for x in cap_len]
+
+
+def golden_retrieval():
+    Ni, S, d = 60, 20, 24
+    images, captions, img_lens, cap_lens = make_eval_containers(15, Ni, S, d, max_regions=12, max_words=15)
+    crit = rloss.AlignmentContrastiveLoss(aggregation="MrSw")
+
+    def sim_fn(img, cap, img_len, cap_len):
+        with torch.no_grad():
+            return crit(img, cap, img_len, cap_len, return_loss=False, return_similarity_mat=True)
+
+    ti, tc = torch.from_numpy(images), torch.from_numpy(captions)
+    sink = io.StringIO()
+    with contextlib.redirect_stderr(sink), contextlib.redirect_stdout(sink):
+        m_i2t, (ranks_i2t, top1) = reval.i2t(ti, tc, img_lens, cap_lens, return_ranks=True,
+                                              sim_function=sim_fn, cap_batches=5)
+        m_t2i, (ranks_t2i, top50) = reval.t2i(ti, tc, img_lens, cap_lens, return_ranks=True,
+                                               sim_function=sim_fn, im_batches=5)
+        g_i2t, (granks_i2t, gtop1) = reval.i2t(ti, tc, img_lens, cap_lens, return_ranks=True, sim_function=None)
+        g_t2i, (granks_t2i, gtop50) = reval.t2i(ti, tc, img_lens, cap_lens, return_ranks=True, sim_function=None)
+        rec = rrec.compute_recall(ti[:, 0, :], tc[:, 0, :])
+        S_full = sim_fn(ti[0::5], tc, img_lens[0::5], cap_lens).numpy()
+    save("retrieval", images=images[0::5], captions=captions,        # image rows are 5x duplicates: store one each
+         img_lens=np.array(img_lens), cap_lens=np.array(cap_lens),
+         m_i2t=np.array(m_i2t, dtype=np.float64), ranks_i2t=ranks_i2t, top1=top1,
+         m_t2i=np.array(m_t2i, dtype=np.float64), ranks_t2i=ranks_t2i, top50=top50,
+         g_i2t=np.array(g_i2t, dtype=np.float64), granks_i2t=granks_i2t, gtop1=gtop1,
+         g_t2i=np.array(g_t2i, dtype=np.float64), granks_t2i=granks_t2i, gtop50=gtop50,
+         compute_recall=np.array(rec, dtype=np.float64), S_full=S_full)
+
+
+if __name__ == "__main__":
+    golden_alignment_scores()
+    golden_alignment_loss()
+    golden_matching()
+    golden_triplet_listnet()
+    golden_retrieval()

@@ -1,0 +1,127 @@
+"""The oracle is only trusted once it reproduces the reference's own outputs.
+
+Golden vectors: tests/golden/*.npz, produced by tests/golden/make_golden.py from the
+unmodified reference (alad/loss.py, alad/evaluation.py, alad/recall_auxiliary.py)."""
+import numpy as np
+import pytest
+
+from oracle import alad_oracle as O
+from conftest import load_golden
+
+
+def test_alignment_scores_all_modes_match_reference():
+    g = load_golden("alignment_scores")
+    im_len, s_len = g["im_len"].tolist(), g["s_len"].tolist()
+    for agg in O.AGGREGATIONS:
+        S = O.alignment_scores_small(g["im"], g["s"], im_len, s_len, agg)
+        ref = g["S_" + agg]
+        # MrAVGw divides by nw == 0 for one caption -> nan/inf in the reference too
+        np.testing.assert_allclose(S, ref, rtol=2e-5, atol=2e-6, equal_nan=True, err_msg=agg)
+
+
+def test_mrsw_fast_and_scalar_match_reference():
+    g = load_golden("alignment_scores")
+    im_len, s_len = g["im_len"].tolist(), g["s_len"].tolist()
+    ref = g["S_MrSw"]
+    np.testing.assert_allclose(O.mrsw_scores(g["im"], g["s"], im_len, s_len, chunk=2), ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(O.mrsw_scores(g["im"], g["s"], im_len, s_len, acc64=True), ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(O.mrsw_scores_scalar(g["im"], g["s"], im_len, s_len), ref, rtol=2e-5, atol=2e-6)
+    # reference edge cases: im_len==1 -> zero row, s_len==3 -> zero column (SURVEY A.5 iv)
+    assert np.all(ref[2] == 0) and np.all(ref[:, 1] == 0)
+
+
+def test_valid_count_python_slice_semantics():
+    assert O.valid_count(5, 8) == 5
+    assert O.valid_count(9, 8) == 8
+    assert O.valid_count(0, 8) == 0
+    assert O.valid_count(-1, 8) == 7        # mask[-1:] masks only the last slot
+    assert O.valid_count(-9, 8) == 0
+
+
+@pytest.mark.parametrize("key,mv", [("mv", True), ("sum", False)])
+def test_alignment_loss_and_grads_match_reference(key, mv):
+    g = load_golden("alignment_loss")
+    im = np.transpose(g["im_sbd"], (1, 0, 2))
+    s = np.transpose(g["s_sbd"], (1, 0, 2))
+    im_len, s_len = g["im_len"].tolist(), g["s_len"].tolist()
+    S = O.mrsw_scores(im, s, im_len, s_len)
+    np.testing.assert_allclose(S, g[f"S_{key}"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(O.triplet_loss(S, 0.2, mv), g[f"loss_{key}"], rtol=1e-5)
+    G = O.triplet_grad(g[f"S_{key}"], 0.2, mv)
+    d_im, d_s = O.mrsw_backward(im, s, im_len, s_len, G)
+    np.testing.assert_allclose(np.transpose(d_im, (1, 0, 2)), g[f"dim_{key}"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(np.transpose(d_s, (1, 0, 2)), g[f"ds_{key}"], rtol=1e-4, atol=2e-6)
+
+
+def test_alignment_dense_backward_matches_reference():
+    g = load_golden("alignment_loss")
+    im = np.transpose(g["im_sbd"], (1, 0, 2))
+    s = np.transpose(g["s_sbd"], (1, 0, 2))
+    d_im, d_s = O.mrsw_backward(im, s, g["im_len"].tolist(), g["s_len"].tolist(), g["Gup"])
+    np.testing.assert_allclose(np.transpose(d_im, (1, 0, 2)), g["dim_dense"], rtol=1e-4, atol=3e-6)
+    np.testing.assert_allclose(np.transpose(d_s, (1, 0, 2)), g["ds_dense"], rtol=1e-4, atol=3e-6)
+    # dropped slots (image slot 0, caption slot 0 and the last two) never receive gradient
+    assert np.all(d_im[:, 0] == 0) and np.all(d_s[:, 0] == 0) and np.all(d_s[:, -2:] == 0)
+
+
+def test_matching_scores_and_loss_match_reference():
+    g = load_golden("matching")
+    for measure in ("dot", "cosine"):
+        im = g["im"] * (1.0 if measure == "dot" else 2.5)
+        S = O.dot_scores(im, g["s"]) if measure == "dot" else O.cosine_scores(im, g["s"])
+        for key, mv in (("mv", True), ("sum", False)):
+            k = f"{measure}_{key}"
+            np.testing.assert_allclose(S, g[f"S_{k}"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(O.triplet_loss(S, 0.2, mv), g[f"loss_{k}"], rtol=1e-5)
+            if measure == "dot":
+                G = O.triplet_grad(g[f"S_{k}"], 0.2, mv)
+                np.testing.assert_allclose(G @ g["s"], g[f"dim_{k}"], rtol=1e-5, atol=1e-6)
+                np.testing.assert_allclose(G.T @ im, g[f"ds_{k}"], rtol=1e-5, atol=1e-6)
+
+
+def test_triplet_and_listnet_match_reference():
+    g = load_golden("triplet_listnet")
+    for key, mv in (("mv", True), ("sum", False)):
+        np.testing.assert_allclose(O.triplet_loss(g["S"], 0.2, mv), g[f"loss_{key}"], rtol=1e-6)
+        np.testing.assert_array_equal(O.triplet_grad(g["S"], 0.2, mv), g[f"G_{key}"])
+    np.testing.assert_allclose(O.listnet_loss(g["T"], g["M"]), g["listnet_loss"], rtol=1e-5)
+    np.testing.assert_allclose(O.listnet_grad(g["T"], g["M"]), g["listnet_dM"], rtol=2e-4, atol=1e-7)
+    assert bool(g["listnet_dT_is_none"])   # teacher is detached (loss.py:370)
+
+
+def _containers(g):
+    return np.repeat(g["images"], 5, axis=0), g["captions"], g["img_lens"].tolist(), g["cap_lens"].tolist()
+
+
+def test_retrieval_alignment_matches_reference():
+    g = load_golden("retrieval")
+    images, captions, il, cl = _containers(g)
+    S = O.mrsw_scores(images[0::5], captions, il[0::5], cl)
+    np.testing.assert_allclose(S, g["S_full"], rtol=2e-5, atol=2e-6)
+    ri, top1 = O.i2t_ranks(S)
+    rt, top50 = O.t2i_ranks(S)
+    np.testing.assert_array_equal(ri, g["ranks_i2t"])
+    np.testing.assert_array_equal(top1, g["top1"])
+    np.testing.assert_array_equal(rt, g["ranks_t2i"])
+    np.testing.assert_array_equal(top50, g["top50"])
+    np.testing.assert_allclose(O.recall_metrics(ri), g["m_i2t"][:5])
+    np.testing.assert_allclose(O.recall_metrics(rt), g["m_t2i"][:5])
+
+
+def test_retrieval_loops_match_reference():
+    g = load_golden("retrieval")
+    images, captions, il, cl = _containers(g)
+    m, (ranks, top1) = O.i2t(images, captions, il, cl, cap_batches=5)
+    np.testing.assert_allclose(m, g["m_i2t"])
+    np.testing.assert_array_equal(ranks, g["ranks_i2t"])
+    m, (ranks, top50) = O.t2i(images, captions, il, cl, im_batches=5)
+    np.testing.assert_allclose(m, g["m_t2i"])
+    np.testing.assert_array_equal(top50, g["top50"])
+    # slot-0 (global vector) path, sim_function=None
+    m, (ranks, top1) = O.i2t(images, captions, il, cl, use_alignment=False)
+    np.testing.assert_allclose(m, g["g_i2t"])
+    np.testing.assert_array_equal(top1, g["gtop1"])
+    m, (ranks, top50) = O.t2i(images, captions, il, cl, use_alignment=False)
+    np.testing.assert_allclose(m, g["g_t2i"])
+    np.testing.assert_array_equal(ranks, g["granks_t2i"])
+    np.testing.assert_allclose(O.compute_recall(images[:, 0, :], captions[:, 0, :]), g["compute_recall"])
