@@ -1,0 +1,363 @@
+// alad_mrsw_scores_fwd: all-pairs region x word cosine GEMM on tcgen05/TMEM with the
+// TERAN-style MrSw pooling (max over regions, sum over words) fused in the epilogue.
+// Replaces alad/loss.py:97-125 of the reference (expand + batched matmul + masked_fill +
+// max(2)[0].sum(2)); the B x B x R x W tensor never exists.
+//
+// Mapping
+//   M (TMEM lanes, 128 / tile)   = densely packed valid WORD rows of all captions
+//   N (TMEM columns, 240 / tile) = densely packed valid REGION rows, whole images per tile
+//   K                            = feature dim (bf16, or 3x for the split-precision mode)
+// One persistent CTA per SM, 6 warps:
+//   warps 0-3  epilogue: tcgen05.ld -> per-thread max over each image's columns ->
+//              smem -> ordered per-caption row sums -> <= 2 atomic addends per S entry
+//   warp 4     TMA producer (4-stage smem ring, 128B swizzle)
+//   warp 5     tcgen05.mma issuer (one lane), 2 accumulator stages in TMEM
+#include <math.h>
+
+#include "common.h"
+#include "sm100_ptx.cuh"
+
+namespace alad {
+
+constexpr int BM = ALAD_TILE_M;
+constexpr int BN = ALAD_TILE_N;
+constexpr int BK = ALAD_TILE_K;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KiB
+constexpr int B_BYTES = BN * BK * 2;          // 30 KiB
+constexpr int V_STRIDE = ALAD_MAX_SEG + 1;    // 33 floats: conflict-free row-major scratch
+constexpr int V_BYTES = BM * V_STRIDE * 4;
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_THREADS + 64;
+constexpr int ACC_STAGES = 2;
+constexpr int ACC_COLS = 256;                 // column stride between accumulator stages
+constexpr int TMEM_COLS = 512;
+constexpr int NTILE_WORDS = sizeof(alad_ntile) / 4;   // 12
+constexpr int N_BLOCK = 32;                   // N tiles swept per M pass (keeps B tiles hot in L2)
+
+// dynamic shared memory carve-up (offsets from a 1024-aligned base)
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
+constexpr int OFF_V = OFF_B + STAGES * B_BYTES;
+constexpr int OFF_CAP = OFF_V + 2 * V_BYTES;                  // int capS[2][128]
+constexpr int OFF_TAB = OFF_CAP + 2 * BM * 4;                 // uint32 tab[4 warps][16]
+constexpr int OFF_BAR = OFF_TAB + EPI_WARPS * 16 * 4;         // mbarriers
+constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
+constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_USED = OFF_TMEMPTR + 16;
+constexpr int SMEM_BYTES = SMEM_USED + 1024;                  // slack for manual 1024 B alignment
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
+static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "SWIZZLE_128B tiles must stay 1024 B aligned");
+
+struct MrswParams {
+  const int32_t* row_cap;
+  const alad_ntile* ntiles;
+  float* S;
+  long long ldS;
+  long long n_word_rows;
+  long long n_region_rows;
+  int n_mtiles;
+  int n_ntiles;
+  int num_kb;
+  int epilogue;
+};
+
+__device__ __forceinline__ void tile_coord(int t, int n_mtiles, int n_ntiles, int& mt, int& nt) {
+  const int per_block = n_mtiles * N_BLOCK;
+  const int nb = t / per_block;
+  const int rem = t - nb * per_block;
+  const int nb_size = min(N_BLOCK, n_ntiles - nb * N_BLOCK);
+  mt = rem / nb_size;
+  nt = nb * N_BLOCK + (rem - mt * nb_size);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_regions,
+                const MrswParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_TMEMPTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.n_mtiles * p.n_ntiles;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_words);
+    tma_prefetch_desc(&map_regions);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 4) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mt, nt;
+        tile_coord(t, p.n_mtiles, p.n_ntiles, mt, nt);
+        const int n_row0 = __ldg(&p.ntiles[nt].row_start);
+        const int m_row0 = mt * BM;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          tma_load_2d(smem + OFF_A + stage * A_BYTES, &map_words, &full_bar[stage], kb * BK, m_row0);
+          tma_load_2d(smem + OFF_B + stage * B_BYTES, &map_regions, &full_bar[stage], kb * BK, n_row0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ============================== MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem + OFF_A + stage * A_BYTES));
+          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem + OFF_B + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // +32 B per K step inside the 128 B swizzle row: start-address field is in 16 B units
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue (warps 0-3) ======================
+    const int row = warp * 32 + lane;                       // TMEM lane == row of the M tile
+    float* V = reinterpret_cast<float*>(smem + OFF_V);
+    int* capS = reinterpret_cast<int*>(smem + OFF_CAP);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + OFF_TAB) + warp * 16;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int mt, nt;
+      tile_coord(t, p.n_mtiles, p.n_ntiles, mt, nt);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int buf = it & 1;
+      // tile metadata, fetched before waiting on the accumulator
+      if (lane < NTILE_WORDS) tab[lane] = __ldg(reinterpret_cast<const uint32_t*>(&p.ntiles[nt]) + lane);
+      const long long mrow = static_cast<long long>(mt) * BM + row;
+      const int mycap = (p.epilogue == 0) ? __ldg(&p.row_cap[mrow]) : 0;
+      __syncwarp();
+      const int n_row0 = static_cast<int>(tab[0]);
+      const int img0 = static_cast<int>(tab[1]);
+      const int nseg = static_cast<int>(tab[2]);
+      const uint32_t clamp = tab[3];
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * ACC_COLS;
+
+      if (p.epilogue == 0) {
+        // ---- phase 1: per-row max over each image's columns -> V[row][seg]
+        float* Vrow = V + buf * (BM * V_STRIDE) + row * V_STRIDE;
+        capS[buf * BM + row] = mycap;
+        int seg = -1;
+        float cur = 0.f;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 8; ++chunk) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + chunk * 32, v);
+          const uint32_t mk = tab[4 + chunk];
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if ((mk >> c) & 1u) {                          // warp-uniform: column starts a new image
+              if (seg >= 0) Vrow[seg] = cur;
+              ++seg;
+              cur = ((clamp >> (seg & 31)) & 1u) ? 0.f : -INFINITY;
+            }
+            cur = fmaxf(cur, __uint_as_float(v[c]));
+          }
+          if (seg >= nseg) break;                          // sentinel passed: remaining columns are not ours
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);                     // accumulator stage may be overwritten
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        // ---- phase 2: ordered row sums per caption; warp w owns caption ordinals w, w+4, ...
+        const int* caps = capS + buf * BM;
+        const float* Vb = V + buf * (BM * V_STRIDE);
+        const bool active = lane < nseg;
+        float* Sout = p.S + static_cast<long long>(img0 + lane) * p.ldS;
+        int prev = caps[0];
+        int ord = 0;
+        float sum = 0.f;
+        for (int r = 0; r < BM; ++r) {
+          const int c = caps[r];
+          if (c != prev) {
+            if ((ord & 3) == warp && active && prev >= 0) atomicAdd(Sout + prev, sum);
+            sum = 0.f;
+            prev = c;
+            ++ord;
+            if (c < 0) break;                              // padding rows follow
+          }
+          if ((ord & 3) == warp && active) sum += Vb[r * V_STRIDE + lane];
+        }
+        if ((ord & 3) == warp && active && prev >= 0) atomicAdd(Sout + prev, sum);
+      } else {
+        // ---- plain GEMM epilogue: S[region row, word row] = accumulator (coalesced over lanes)
+        const int ncols = static_cast<int>(min(static_cast<long long>(BN), p.n_region_rows - n_row0));
+        const bool row_ok = mrow < p.n_word_rows;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 8; ++chunk) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + chunk * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int col = chunk * 32 + c;
+            if (row_ok && col < ncols) p.S[static_cast<long long>(n_row0 + col) * p.ldS + mrow] = __uint_as_float(v[c]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// [rows, Kp] bf16 row-major; box = 64 elements (128 B, one swizzle row) x box_rows.
+static int make_map(CUtensorMap* m, const void* ptr, long long rows, int Kp, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(ALAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kp) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ALAD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+}  // namespace alad
+
+extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
+  using namespace alad;
+  ALAD_REQUIRE(a != nullptr, "alad_mrsw_scores_fwd: NULL args");
+  ALAD_REQUIRE(a->S != nullptr && a->Ni >= 0 && a->Nc >= 0 && a->ldS >= a->Nc, "alad_mrsw_scores_fwd: bad output");
+  ALAD_REQUIRE(a->Kp > 0 && a->Kp % BK == 0, "alad_mrsw_scores_fwd: Kp=%d must be a positive multiple of %d", a->Kp, BK);
+  ALAD_REQUIRE(a->n_word_rows >= 0 && a->n_region_rows >= 0 && a->n_word_rows < (1ll << 31) &&
+                   a->n_region_rows < (1ll << 31),
+               "alad_mrsw_scores_fwd: bad row counts");
+  ALAD_REQUIRE(a->epilogue == 0 || a->epilogue == 1, "alad_mrsw_scores_fwd: unknown epilogue %d", a->epilogue);
+  cudaStream_t st = as_stream(stream);
+  if (a->Ni > 0 && a->Nc > 0) {
+    if (a->ldS == a->Nc) {
+      ALAD_CUDA(cudaMemsetAsync(a->S, 0, sizeof(float) * (size_t)a->Ni * (size_t)a->Nc, st));
+    } else {
+      ALAD_CUDA(cudaMemset2DAsync(a->S, sizeof(float) * (size_t)a->ldS, 0, sizeof(float) * (size_t)a->Nc,
+                                  (size_t)a->Ni, st));
+    }
+  }
+  if (a->n_word_rows == 0 || a->n_region_rows == 0 || a->n_ntiles == 0 || a->Ni == 0 || a->Nc == 0) return ALAD_OK;
+  ALAD_REQUIRE(a->words && a->regions && a->ntiles, "alad_mrsw_scores_fwd: NULL operand");
+  ALAD_REQUIRE(a->epilogue == 1 || a->row_cap, "alad_mrsw_scores_fwd: NULL row_cap");
+  ALAD_REQUIRE((reinterpret_cast<uintptr_t>(a->words) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->regions) & 15) == 0,
+               "alad_mrsw_scores_fwd: operands must be 16-byte aligned");
+
+  MrswParams p;
+  p.row_cap = a->row_cap;
+  p.ntiles = a->ntiles;
+  p.S = a->S;
+  p.ldS = a->ldS;
+  p.n_word_rows = a->n_word_rows;
+  p.n_region_rows = a->n_region_rows;
+  p.n_mtiles = (int)((a->n_word_rows + BM - 1) / BM);
+  p.n_ntiles = a->n_ntiles;
+  p.num_kb = a->Kp / BK;
+  p.epilogue = a->epilogue;
+  const long long total = (long long)p.n_mtiles * p.n_ntiles;
+  ALAD_REQUIRE(total < (1ll << 31), "alad_mrsw_scores_fwd: too many tiles (%lld)", total);
+
+  CUtensorMap map_w, map_r;
+  int rc = make_map(&map_w, a->words, a->n_word_rows, a->Kp, BM);
+  if (rc) return rc;
+  rc = make_map(&map_r, a->regions, a->n_region_rows, a->Kp, BN);
+  if (rc) return rc;
+
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int ctas = a->num_ctas > 0 ? a->num_ctas : sm_count();
+  if (ctas > total) ctas = (int)total;
+  mrsw_fwd_kernel<<<ctas, THREADS, SMEM_BYTES, st>>>(map_w, map_r, p);
+  ALAD_CUDA(cudaGetLastError());
+  return ALAD_OK;
+}

@@ -1,0 +1,117 @@
+// alad_pack_tokens: L2-normalise (F.normalize semantics, alad/loss.py:80-81), drop the
+// unscored slots (loss.py:87-90), compact the valid tokens of every item into dense
+// K-major bf16 rows (the layout the TMA descriptors of the scoring kernel read) and
+// optionally split fp32 into bf16 hi/lo parts for the fp32-grade mode.
+// HBM-bound: reads 4 B, writes 2 B (6 B split) per element; one warp per token row,
+// 128-bit loads, 64-bit stores.
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace alad {
+
+constexpr int PACK_WARPS = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
+  __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&lo);
+  r.y = *reinterpret_cast<uint32_t*>(&hi);
+  return r;
+}
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <bool kVec>
+__global__ void __launch_bounds__(PACK_WARPS * 32) pack_tokens_kernel(const alad_pack_args a) {
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cnt = a.count[b];
+  const long long row0 = a.row_off[b];
+  const int d = a.d;
+  const int Kp = a.Kp;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.dst);
+  // offsets of the three output segments inside a packed row
+  const int off_hi2 = (a.mode == 1) ? d : 2 * d;   // second copy of hi
+  const int off_lo = (a.mode == 1) ? 2 * d : d;    // lo part
+  const int used = (a.mode == 0) ? d : 3 * d;
+
+  for (int t = warp; t < cnt; t += PACK_WARPS) {
+    const float* x = a.src + (long long)b * a.stride_b + (long long)(a.slot0 + t) * a.stride_s;
+    __nv_bfloat16* y = dst + (row0 + t) * (long long)Kp;
+    float ss = 0.f;
+    if (a.normalize) {
+      if (kVec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        for (int i = lane; i < d / 4; i += 32) {
+          const float4 v = __ldg(x4 + i);
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+      } else {
+        for (int i = lane; i < d; i += 32) {
+          const float v = __ldg(x + i);
+          ss += v * v;
+        }
+      }
+      ss = warp_sum(ss);
+    }
+    const float denom = a.normalize ? fmaxf(sqrtf(ss), a.eps) : 1.f;
+    if (kVec) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      for (int i = lane; i < d / 4; i += 32) {
+        float4 v = __ldg(x4 + i);
+        v.x /= denom; v.y /= denom; v.z /= denom; v.w /= denom;
+        const uint2 hi = pack_bf16x4(v.x, v.y, v.z, v.w);
+        *reinterpret_cast<uint2*>(y + 4 * i) = hi;
+        if (a.mode != 0) {
+          *reinterpret_cast<uint2*>(y + off_hi2 + 4 * i) = hi;
+          const uint2 lo = pack_bf16x4(v.x - bf16_round(v.x), v.y - bf16_round(v.y), v.z - bf16_round(v.z),
+                                       v.w - bf16_round(v.w));
+          *reinterpret_cast<uint2*>(y + off_lo + 4 * i) = lo;
+        }
+      }
+    } else {
+      for (int i = lane; i < d; i += 32) {
+        const float v = __ldg(x + i) / denom;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        y[i] = hi;
+        if (a.mode != 0) {
+          y[off_hi2 + i] = hi;
+          y[off_lo + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
+      }
+    }
+    for (int i = used + lane; i < Kp; i += 32) y[i] = __float2bfloat16_rn(0.f);   // K padding
+    if (a.row_item != nullptr && lane == 0) a.row_item[row0 + t] = b;
+  }
+}
+
+}  // namespace alad
+
+extern "C" int alad_pack_tokens(const alad_pack_args* a, void* stream) {
+  using namespace alad;
+  ALAD_REQUIRE(a != nullptr, "alad_pack_tokens: NULL args");
+  ALAD_REQUIRE(a->B >= 0 && a->S >= 0 && a->d > 0, "alad_pack_tokens: bad shape");
+  ALAD_REQUIRE(a->mode >= 0 && a->mode <= 2, "alad_pack_tokens: unknown mode %d", a->mode);
+  ALAD_REQUIRE(a->Kp % ALAD_TILE_K == 0 && a->Kp >= (a->mode == 0 ? a->d : 3 * a->d),
+               "alad_pack_tokens: Kp=%d too small or not a multiple of %d", a->Kp, ALAD_TILE_K);
+  if (a->B == 0) return ALAD_OK;
+  ALAD_REQUIRE(a->src && a->dst && a->count && a->row_off, "alad_pack_tokens: NULL pointer");
+  const bool vec = (a->d % 4 == 0) && (a->stride_b % 4 == 0) && (a->stride_s % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(a->src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a->dst) & 7) == 0);
+  cudaStream_t st = as_stream(stream);
+  if (vec)
+    pack_tokens_kernel<true><<<a->B, PACK_WARPS * 32, 0, st>>>(*a);
+  else
+    pack_tokens_kernel<false><<<a->B, PACK_WARPS * 32, 0, st>>>(*a);
+  ALAD_CUDA(cudaGetLastError());
+  return ALAD_OK;
+}

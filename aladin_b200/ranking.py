@@ -1,0 +1,72 @@
+"""Device-side ranking ops over an image-major score matrix S[Ni,Nc] (thin wrappers over
+the C ABI).  Replace numpy.argsort/where of alad/evaluation.py:213-223,303-308 and
+alad/recall_auxiliary.py:34-56."""
+import torch
+
+from . import _cabi
+
+
+def _check_S(S):
+    assert S.is_cuda and S.dtype == torch.float32 and S.dim() == 2 and S.stride(1) == 1
+    return S.shape[0], S.shape[1], max(S.stride(0), S.shape[1])
+
+
+def rank_rows(S, group=5, img_off=0):
+    """i2t: (rank[Ni] int32, top1[Ni] int32) -- evaluation.py:213-223."""
+    Ni, Nc, ld = _check_S(S)
+    rank = torch.empty(Ni, dtype=torch.int32, device=S.device)
+    top1 = torch.empty(Ni, dtype=torch.int32, device=S.device)
+    _cabi.check(_cabi.lib().alad_rank_rows(S.data_ptr(), ld, Ni, Nc, group, img_off, rank.data_ptr(), top1.data_ptr(),
+                                            _cabi.stream_ptr()), "alad_rank_rows")
+    return rank, top1
+
+
+def col_gt(S, gt, group=5, img_off=0):
+    """t2i: write the ground-truth score of every caption whose image this shard owns into gt[Nc]."""
+    Ni, Nc, ld = _check_S(S)
+    assert gt.is_cuda and gt.dtype == torch.float32 and gt.numel() == Nc and gt.is_contiguous()
+    _cabi.check(_cabi.lib().alad_col_gt(S.data_ptr(), ld, Ni, Nc, group, img_off, gt.data_ptr(), _cabi.stream_ptr()),
+                "alad_col_gt")
+    return gt
+
+
+def col_count(S, gt, group=5, img_off=0):
+    """t2i: count[Nc] int32 = local images ordered ahead of each caption's ground truth."""
+    Ni, Nc, ld = _check_S(S)
+    count = torch.empty(Nc, dtype=torch.int32, device=S.device)
+    _cabi.check(_cabi.lib().alad_col_count(S.data_ptr(), ld, Ni, Nc, group, img_off, gt.data_ptr(), count.data_ptr(),
+                                            _cabi.stream_ptr()), "alad_col_count")
+    return count
+
+
+def col_topk(S, k, img_off=0, splits=8):
+    """t2i: sorted per-caption candidates (score[splits,Nc,k], global image idx[splits,Nc,k])."""
+    Ni, Nc, ld = _check_S(S)
+    splits = max(1, min(splits, (Ni + 63) // 64))
+    cs = torch.empty((splits, Nc, k), dtype=torch.float32, device=S.device)
+    ci = torch.empty((splits, Nc, k), dtype=torch.int32, device=S.device)
+    _cabi.check(_cabi.lib().alad_col_topk(S.data_ptr(), ld, Ni, Nc, k, img_off, splits, cs.data_ptr(), ci.data_ptr(),
+                                           _cabi.stream_ptr()), "alad_col_topk")
+    return cs, ci
+
+
+def topk_merge(cand_score, cand_idx):
+    """Merge P sorted candidate lists per caption: [P,Nc,k] -> ([Nc,k], [Nc,k])."""
+    P, Nc, k = cand_score.shape
+    assert cand_score.is_contiguous() and cand_idx.is_contiguous() and cand_idx.shape == cand_score.shape
+    os_ = torch.empty((Nc, k), dtype=torch.float32, device=cand_score.device)
+    oi = torch.empty((Nc, k), dtype=torch.int32, device=cand_score.device)
+    _cabi.check(_cabi.lib().alad_topk_merge(cand_score.data_ptr(), cand_idx.data_ptr(), P, Nc, k, os_.data_ptr(),
+                                             oi.data_ptr(), _cabi.stream_ptr()), "alad_topk_merge")
+    return os_, oi
+
+
+def t2i_rank_topk(S, k, group=5):
+    """Single-shard t2i: (rank[Nc] int32, topk[Nc,k] int32)."""
+    Ni, Nc, _ = _check_S(S)
+    gt = torch.zeros(Nc, dtype=torch.float32, device=S.device)
+    col_gt(S, gt, group, 0)
+    count = col_count(S, gt, group, 0)
+    cs, ci = col_topk(S, k, 0)
+    _, idx = topk_merge(cs, ci)
+    return count, idx

@@ -1,0 +1,130 @@
+/* alad_b200 -- C ABI of the B200 (sm_100a) implementation of ALADIN's all-pairs
+ * cross-modal scoring path.
+ *
+ * The reference (mesnico/ALADIN) is pure Python/PyTorch and has no FFI; its "plugin
+ * boundary" for this path is the Python call sites listed next to each entry point.
+ * The host side (aladin_b200/*.py) mirrors those call sites and reaches the kernels
+ * only through the functions below (ctypes).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no allocation inside: the caller owns inputs, outputs and workspaces;
+ *   - return 0 on success, negative alad_status otherwise; alad_last_error() gives the
+ *     text of the last failure on the calling thread;
+ *   - re-entrant across streams; the device is the current CUDA device of the caller.
+ */
+#ifndef ALAD_B200_H_
+#define ALAD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum alad_status {
+  ALAD_OK = 0,
+  ALAD_ERR_INVALID = -1,   /* bad argument (shape, alignment, NULL) */
+  ALAD_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed    */
+  ALAD_ERR_UNSUPPORTED = -3
+} alad_status;
+
+/* geometry of the scoring kernel, exposed so the host can build tile tables */
+#define ALAD_TILE_M 128      /* packed word rows per tile (TMEM lanes)            */
+#define ALAD_TILE_N 240      /* packed region rows per tile (TMEM columns)        */
+#define ALAD_TILE_K 64       /* bf16 elements per pipeline stage (128 B rows)     */
+#define ALAD_MAX_SEG 32      /* images per N tile                                 */
+
+int alad_abi_version(void);
+const char* alad_last_error(void);
+
+/* ---------------------------------------------------------------------------------
+ * alad_pack_tokens  -- replaces F.normalize + slot slicing at alad/loss.py:80-90 and the
+ * per-query `.cuda()` uploads of alad/evaluation.py:179,202,267,291.
+ * For item b and scored token t < count[b] reads src[b, slot0 + t, :], scales it by
+ * 1/max(||x||_2, eps) when `normalize`, converts to bf16 and writes packed row
+ * row_off[b] + t of dst ([rows, Kp] bf16, K-major, Kp % 64 == 0, zero padded).
+ *   mode 0: plain bf16 (Kp >= d)
+ *   mode 1: split-precision "word side"   [hi | hi | lo] (Kp >= 3d)
+ *   mode 2: split-precision "region side" [hi | lo | hi] (Kp >= 3d)
+ * so that <mode1 row, mode2 row> = hi*hi + hi*lo + lo*hi (fp32-grade dot product on the
+ * bf16 tensor pipe).  row_item (optional) receives b for every packed row.
+ * ------------------------------------------------------------------------------- */
+typedef struct alad_pack_args {
+  const float* src;          /* [B, S, d] fp32, innermost stride 1                   */
+  int64_t stride_b;          /* element strides of src                               */
+  int64_t stride_s;
+  int32_t B, S, d;
+  int32_t slot0;             /* first scored slot (1: loss.py:87-88)                 */
+  const int32_t* count;      /* [B] scored tokens per item (<= S - slot0)            */
+  const int64_t* row_off;    /* [B] first packed row of item b                       */
+  void* dst;                 /* [rows, Kp] bf16                                      */
+  int32_t Kp;
+  int32_t mode;
+  int32_t normalize;         /* 1: F.normalize semantics; 0: copy                    */
+  float eps;                 /* 1e-12 (F.normalize) or 0 (alad.utils.l2norm)         */
+  int32_t* row_item;         /* optional [rows]                                      */
+} alad_pack_args;
+int alad_pack_tokens(const alad_pack_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * alad_mrsw_scores_fwd -- replaces alad/loss.py:97-125 (expand + batched matmul + masks +
+ * `alignments.max(2)[0].sum(2)`), i.e. the body of AlignmentContrastiveLoss.forward for
+ * aggregation 'MrSw'.  S[i, j] = sum_w max_r <region(i,r), word(j,w)> over packed valid
+ * tokens; the max starts from 0 when the image has masked slots inside its container
+ * (clamp bit) and from -inf otherwise.  TMA + tcgen05/TMEM; the 4-D tensor is never
+ * written.  S is zeroed by the call and accumulated with <= 2 addends per entry.
+ * ------------------------------------------------------------------------------- */
+typedef struct alad_ntile {      /* one 240-column tile of packed region rows (device table) */
+  int32_t row_start;             /* first packed region row of the tile                      */
+  int32_t img0;                  /* first image (row of S) of the tile; images are consecutive */
+  int32_t nseg;                  /* images in the tile (<= ALAD_MAX_SEG)                     */
+  uint32_t clamp_bits;           /* bit s: image img0+s has masked slots -> max starts at 0  */
+  uint32_t start_mask[8];        /* bit c: column c starts a segment; bit ncols = sentinel   */
+} alad_ntile;
+
+typedef struct alad_mrsw_fwd_args {
+  const void* words;             /* [n_word_rows, Kp] bf16 packed (mode 0 or 1)              */
+  int64_t n_word_rows;
+  const void* regions;           /* [n_region_rows, Kp] bf16 packed (mode 0 or 2)            */
+  int64_t n_region_rows;
+  int32_t Kp;
+  const int32_t* row_cap;        /* [ceil(n_word_rows/128)*128] caption of each row, -1 pad  */
+  const alad_ntile* ntiles;
+  int32_t n_ntiles;
+  float* S;                      /* [Ni, ldS] fp32                                           */
+  int64_t ldS;
+  int32_t Ni, Nc;
+  int32_t epilogue;              /* 0 = MrSw pooling; 1 = plain GEMM: S[n, m] = <region n, word m> */
+  int32_t num_ctas;              /* 0 = one persistent CTA per SM                            */
+} alad_mrsw_fwd_args;
+int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Ranking -- replaces numpy.argsort + numpy.where of alad/evaluation.py:213-223,303-308
+ * and alad/recall_auxiliary.py:34-56.  Order = score descending, index descending on
+ * exact ties (= stable argsort reversed).  S is image-major [Ni, ldS]; ground truth of
+ * image i (global index img_off + i) are captions 5*(img_off+i) .. +4 (group = 5).
+ * ------------------------------------------------------------------------------- */
+/* i2t: rank[i] = position of the best ground-truth caption; top1[i] = arg-max caption. */
+int alad_rank_rows(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t group, int32_t img_off,
+                   int32_t* rank, int32_t* top1, void* stream);
+/* t2i step 1: gt[c] = S[c/group - img_off, c] where this shard owns that image, else untouched. */
+int alad_col_gt(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t group, int32_t img_off,
+                float* gt, void* stream);
+/* t2i step 2: count[c] = #{ local images ahead of the ground truth of caption c }. */
+int alad_col_count(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t group, int32_t img_off,
+                   const float* gt, int32_t* count, void* stream);
+/* t2i step 3: per-caption top-k candidates of this shard, `splits` row slices each:
+ * cand_score/cand_idx are [splits, Nc, k], sorted, idx = global image index (-1 = empty). */
+int alad_col_topk(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t k, int32_t img_off, int32_t splits,
+                  float* cand_score, int32_t* cand_idx, void* stream);
+/* merge P sorted candidate lists per caption (after the all-gather across shards). */
+int alad_topk_merge(const float* cand_score, const int32_t* cand_idx, int32_t P, int32_t Nc, int32_t k,
+                    float* out_score, int32_t* out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALAD_B200_H_ */
