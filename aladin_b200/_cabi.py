@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libalad_b200.so")
 
 TILE_M, TILE_N, TILE_K, MAX_SEG = 128, 240, 64, 32
-NTILE_WORDS = 12
+NTILE_WORDS = 20
 
 
 class PackArgs(C.Structure):

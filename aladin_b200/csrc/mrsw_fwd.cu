@@ -34,7 +34,8 @@ constexpr int THREADS = EPI_THREADS + 64;
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 256;                 // column stride between accumulator stages
 constexpr int TMEM_COLS = 512;
-constexpr int NTILE_WORDS = sizeof(alad_ntile) / 4;   // 12
+constexpr int NTILE_WORDS = sizeof(alad_ntile) / 4;   // 20
+static_assert(NTILE_WORDS <= 32, "one lane per table word");
 constexpr int N_BLOCK = 32;                   // N tiles swept per M pass (keeps B tiles hot in L2)
 
 // dynamic shared memory carve-up (offsets from a 1024-aligned base)
@@ -42,8 +43,9 @@ constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
 constexpr int OFF_V = OFF_B + STAGES * B_BYTES;
 constexpr int OFF_CAP = OFF_V + 2 * V_BYTES;                  // int capS[2][128]
-constexpr int OFF_TAB = OFF_CAP + 2 * BM * 4;                 // uint32 tab[4 warps][16]
-constexpr int OFF_BAR = OFF_TAB + EPI_WARPS * 16 * 4;         // mbarriers
+constexpr int OFF_TAB = OFF_CAP + 2 * BM * 4;                 // uint32 tab[4 warps][32]
+constexpr int OFF_RUN = OFF_TAB + EPI_WARPS * 32 * 4;         // uint32 run_start_mask[2][4]
+constexpr int OFF_BAR = OFF_RUN + 2 * EPI_WARPS * 4;          // mbarriers
 constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
 constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_USED = OFF_TMEMPTR + 16;
@@ -77,7 +79,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_regions,
                 const MrswParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // manual 1024 B alignment by OFFSET (keeps the pointer in the shared address space -> LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* full_bar = bars;
@@ -173,7 +176,25 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
     const int row = warp * 32 + lane;                       // TMEM lane == row of the M tile
     float* V = reinterpret_cast<float*>(smem + OFF_V);
     int* capS = reinterpret_cast<int*>(smem + OFF_CAP);
-    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + OFF_TAB) + warp * 16;
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + OFF_TAB) + warp * 32;
+    uint32_t* runS = reinterpret_cast<uint32_t*>(smem + OFF_RUN);
+    const bool mrsw = p.epilogue == 0;
+
+    // metadata of a tile: N-tile record word (lanes 0..11), caption of my row and of the row above
+    uint32_t nx_tab = 0;
+    int nx_cap = 0, nx_above = 0;
+    auto fetch_meta = [&](int t) {
+      int mt, nt;
+      tile_coord(t, p.n_mtiles, p.n_ntiles, mt, nt);
+      if (lane < NTILE_WORDS) nx_tab = __ldg(reinterpret_cast<const uint32_t*>(&p.ntiles[nt]) + lane);
+      if (mrsw) {
+        const long long mrow = static_cast<long long>(mt) * BM + row;
+        nx_cap = __ldg(&p.row_cap[mrow]);
+        nx_above = (row > 0 && lane == 0) ? __ldg(&p.row_cap[mrow - 1]) : 0;
+      }
+    };
+    if (blockIdx.x < total_tiles) fetch_meta(blockIdx.x);
+
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int mt, nt;
@@ -181,66 +202,132 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int buf = it & 1;
-      // tile metadata, fetched before waiting on the accumulator
-      if (lane < NTILE_WORDS) tab[lane] = __ldg(reinterpret_cast<const uint32_t*>(&p.ntiles[nt]) + lane);
       const long long mrow = static_cast<long long>(mt) * BM + row;
-      const int mycap = (p.epilogue == 0) ? __ldg(&p.row_cap[mrow]) : 0;
+      const int mycap = nx_cap;
+      if (lane < NTILE_WORDS) tab[lane] = nx_tab;
+      if (mrsw) {
+        // caption runs of this M tile: a row starts a run when its caption differs from the row above
+        int above = __shfl_up_sync(0xffffffffu, mycap, 1);
+        if (lane == 0) above = nx_above;
+        const bool is_start = (row == 0) || (mycap != above);
+        const uint32_t smask = __ballot_sync(0xffffffffu, is_start);
+        if (lane == 0) runS[buf * EPI_WARPS + warp] = smask;
+        capS[buf * BM + row] = mycap;
+      }
       __syncwarp();
       const int n_row0 = static_cast<int>(tab[0]);
       const int img0 = static_cast<int>(tab[1]);
-      const int nseg = static_cast<int>(tab[2]);
+      const int nseg = __shfl_sync(0xffffffffu, static_cast<int>(tab[2]), 0);      // shfl => provably warp-uniform
       const uint32_t clamp = tab[3];
+      const uint32_t mydesc = (tab[4 + (lane >> 1)] >> ((lane & 1) * 16)) & 0xffffu;  // descriptor of image `lane`
+      // prefetch the next tile's metadata while this one is processed
+      if (t + static_cast<int>(gridDim.x) < total_tiles) fetch_meta(t + gridDim.x);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * ACC_COLS;
 
-      if (p.epilogue == 0) {
-        // ---- phase 1: per-row max over each image's columns -> V[row][seg]
+      if (mrsw) {
+        // ---- phase 1: per-row max over each image's columns -> V[row][seg].
+        // Every image is covered by windows of P consecutive columns that lie entirely inside
+        // it (P = 32, or the largest power of two <= width; the last window overlaps the
+        // previous one), so no masking is needed and each window is a FMNMX3 tree.
         float* Vrow = V + buf * (BM * V_STRIDE) + row * V_STRIDE;
-        capS[buf * BM + row] = mycap;
-        int seg = -1;
-        float cur = 0.f;
-#pragma unroll 1
-        for (int chunk = 0; chunk < 8; ++chunk) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + chunk * 32, v);
-          const uint32_t mk = tab[4 + chunk];
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if ((mk >> c) & 1u) {                          // warp-uniform: column starts a new image
-              if (seg >= 0) Vrow[seg] = cur;
-              ++seg;
-              cur = ((clamp >> (seg & 31)) & 1u) ? 0.f : -INFINITY;
+        for (int s_i = 0; s_i < nseg; ++s_i) {
+          const uint32_t dsc = __shfl_sync(0xffffffffu, mydesc, s_i);   // warp-uniform (start | width << 8)
+          const uint32_t c0 = taddr + (dsc & 0xffu);
+          const int w = static_cast<int>(dsc >> 8);
+          float m;
+          if (w >= 32) {
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32(c0, va);
+            tmem_ld_32x32(c0 + (w > 64 ? 32 : w - 32), vb);
+            tmem_ld_wait();
+            m = fmaxf(tree_max_bits(va), tree_max_bits(vb));
+            for (int off = 64; off < w; off += 32) {                    // images wider than 64 columns
+              tmem_ld_32x32(c0 + min(off, w - 32), va);
+              tmem_ld_wait();
+              m = fmaxf(m, tree_max_bits(va));
             }
-            cur = fmaxf(cur, __uint_as_float(v[c]));
+          } else if (w >= 16) {
+            uint32_t va[16], vb[16];
+            tmem_ld_32x16(c0, va);
+            tmem_ld_32x16(c0 + w - 16, vb);
+            tmem_ld_wait();
+            m = fmaxf(tree_max_bits(va), tree_max_bits(vb));
+          } else if (w >= 8) {
+            uint32_t va[8], vb[8];
+            tmem_ld_32x8(c0, va);
+            tmem_ld_32x8(c0 + w - 8, vb);
+            tmem_ld_wait();
+            m = fmaxf(tree_max_bits(va), tree_max_bits(vb));
+          } else if (w >= 4) {
+            uint32_t va[4], vb[4];
+            tmem_ld_32x4(c0, va);
+            tmem_ld_32x4(c0 + w - 4, vb);
+            tmem_ld_wait();
+            m = fmaxf(tree_max_bits(va), tree_max_bits(vb));
+          } else if (w >= 2) {
+            uint32_t va[2], vb[2];
+            tmem_ld_32x2(c0, va);
+            tmem_ld_32x2(c0 + w - 2, vb);
+            tmem_ld_wait();
+            m = fmaxf(tree_max_bits(va), tree_max_bits(vb));
+          } else {
+            uint32_t va[1];
+            tmem_ld_32x1(c0, va);
+            tmem_ld_wait();
+            m = __uint_as_float(va[0]);
           }
-          if (seg >= nseg) break;                          // sentinel passed: remaining columns are not ours
+          Vrow[s_i] = m;
         }
+        tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);                     // accumulator stage may be overwritten
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-        // ---- phase 2: ordered row sums per caption; warp w owns caption ordinals w, w+4, ...
+        // ---- phase 2: per-caption row sums in a fixed order; warp w owns caption runs w, w+4, ...
         const int* caps = capS + buf * BM;
-        const float* Vb = V + buf * (BM * V_STRIDE);
+        const float* Vcol = V + buf * (BM * V_STRIDE) + lane;
         const bool active = lane < nseg;
+        const float floor_v = ((clamp >> lane) & 1u) ? 0.f : -INFINITY;   // masked slots take part in the max as 0
         float* Sout = p.S + static_cast<long long>(img0 + lane) * p.ldS;
-        int prev = caps[0];
-        int ord = 0;
-        float sum = 0.f;
-        for (int r = 0; r < BM; ++r) {
-          const int c = caps[r];
-          if (c != prev) {
-            if ((ord & 3) == warp && active && prev >= 0) atomicAdd(Sout + prev, sum);
-            sum = 0.f;
-            prev = c;
-            ++ord;
-            if (c < 0) break;                              // padding rows follow
+        unsigned long long lo = runS[buf * EPI_WARPS + 0] | (static_cast<unsigned long long>(runS[buf * EPI_WARPS + 1]) << 32);
+        unsigned long long hi = runS[buf * EPI_WARPS + 2] | (static_cast<unsigned long long>(runS[buf * EPI_WARPS + 3]) << 32);
+        auto pop_start = [&]() -> int {                    // next run start (128 when exhausted)
+          if (lo) {
+            const int b = __ffsll(static_cast<long long>(lo)) - 1;
+            lo &= lo - 1;
+            return b;
           }
-          if ((ord & 3) == warp && active) sum += Vb[r * V_STRIDE + lane];
+          if (hi) {
+            const int b = __ffsll(static_cast<long long>(hi)) - 1;
+            hi &= hi - 1;
+            return 64 + b;
+          }
+          return BM;
+        };
+        int start = pop_start();                           // row 0 always starts a run
+        int ord = 0;
+        while (start < BM) {
+          const int end = pop_start();
+          if ((ord & 3) == warp) {
+            const int cap = caps[start];
+            if (cap >= 0 && active) {
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              int r = start;
+              for (; r + 4 <= end; r += 4) {
+                s0 += fmaxf(Vcol[(r + 0) * V_STRIDE], floor_v);
+                s1 += fmaxf(Vcol[(r + 1) * V_STRIDE], floor_v);
+                s2 += fmaxf(Vcol[(r + 2) * V_STRIDE], floor_v);
+                s3 += fmaxf(Vcol[(r + 3) * V_STRIDE], floor_v);
+              }
+              for (; r < end; ++r) s0 += fmaxf(Vcol[r * V_STRIDE], floor_v);
+              atomicAdd(Sout + cap, (s0 + s1) + (s2 + s3));
+            }
+          }
+          start = end;
+          ++ord;
         }
-        if ((ord & 3) == warp && active && prev >= 0) atomicAdd(Sout + prev, sum);
       } else {
         // ---- plain GEMM epilogue: S[region row, word row] = accumulator (coalesced over lanes)
         const int ncols = static_cast<int>(min(static_cast<long long>(BN), p.n_region_rows - n_row0));
@@ -350,11 +437,7 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   rc = make_map(&map_r, a->regions, a->n_region_rows, a->Kp, BN);
   if (rc) return rc;
 
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int ctas = a->num_ctas > 0 ? a->num_ctas : sm_count();
   if (ctas > total) ctas = (int)total;
   mrsw_fwd_kernel<<<ctas, THREADS, SMEM_BYTES, st>>>(map_w, map_r, p);

@@ -102,6 +102,66 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "memory");
 }
 
+// Narrower variants (N consecutive columns, N = 16 / 8 / 4 / 2 / 1).
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t (&v)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t (&v)[1]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(taddr) : "memory");
+}
+
+// 3-input fp32 max (FMNMX3 on sm_100) and a compile-time max tree over N register values.
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+template <int N>
+__device__ __forceinline__ float tree_max(const float (&x)[N]) {
+  if constexpr (N == 1) {
+    return x[0];
+  } else if constexpr (N == 2) {
+    return fmaxf(x[0], x[1]);
+  } else {
+    constexpr int M = (N + 2) / 3;
+    float y[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      const int i0 = 3 * i, i1 = 3 * i + 1 < N ? 3 * i + 1 : N - 1, i2 = 3 * i + 2 < N ? 3 * i + 2 : N - 1;
+      y[i] = (3 * i + 2 < N) ? max3(x[i0], x[i1], x[i2]) : ((3 * i + 1 < N) ? fmaxf(x[i0], x[i1]) : x[i0]);
+    }
+    return tree_max<M>(y);
+  }
+}
+template <int N>
+__device__ __forceinline__ float tree_max_bits(const uint32_t (&v)[N]) {
+  float x[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = __uint_as_float(v[i]);
+  return tree_max<N>(x);
+}
+
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 128 B
 // (64 bf16), 8-row groups 1024 B apart.  Field layout (cute::UMMA::SmemDescriptor):

@@ -24,62 +24,57 @@ def build_region_tiles(nr, clamp):
     """Greedy tiling of consecutive images into tiles of <= TILE_N packed region rows and
     <= MAX_SEG images.  Images with no valid region own no column (their score row stays 0).
 
-    Returns (row_off[int64 Ni], table[uint32 T, 12], n_rows).  Table row layout = struct
-    alad_ntile: row_start, img0, nseg, clamp_bits, start_mask[8] (bit ncols = sentinel)."""
+    Returns (row_off[int64 Ni], table[uint32 T, 20], n_rows).  Table row layout = struct
+    alad_ntile: row_start, img0, nseg, clamp_bits, seg[32] (uint16: first column | width << 8)."""
     nr = np.asarray(nr, dtype=np.int64)
     clamp = np.asarray(clamp, dtype=bool)
     if nr.size and int(nr.max()) > TILE_N:
         raise ValueError(f"an image has {int(nr.max())} scored regions; the kernel supports at most {TILE_N}")
     row_off, n_rows = exclusive_cumsum(nr)
-    tiles = []
     Ni = len(nr)
+    # tile id of every image (greedy, sequential): images without regions close the current tile
+    tile_of = np.full(Ni, -1, dtype=np.int64)
+    col_of = np.zeros(Ni, dtype=np.int64)
+    seg_of = np.zeros(Ni, dtype=np.int64)
     uniform = Ni > 0 and int(nr.min()) == int(nr.max()) and nr[0] > 0
     if uniform:
-        # closed form: every tile holds `per` images of `w` columns
         w = int(nr[0])
         per = max(1, min(MAX_SEG, TILE_N // w))
-        n_t = (Ni + per - 1) // per
-        table = np.zeros((n_t, NTILE_WORDS), dtype=np.uint32)
-        img0 = np.arange(n_t, dtype=np.int64) * per
-        nseg = np.minimum(per, Ni - img0)
-        table[:, 0] = (img0 * w).astype(np.uint32)
-        table[:, 1] = img0.astype(np.uint32)
-        table[:, 2] = nseg.astype(np.uint32)
-        cb = np.zeros(n_t, dtype=np.uint64)
-        cl = clamp.astype(np.uint64)
-        for s in range(per):
-            idx = img0 + s
-            ok = idx < Ni
-            cb[ok] |= cl[idx[ok]] << np.uint64(s)
-        table[:, 3] = cb.astype(np.uint32)
-        for t_nseg in np.unique(nseg):
-            mask = np.zeros(8, dtype=np.uint32)
-            for s in range(int(t_nseg) + 1):           # segment starts + sentinel
-                c = s * w
-                mask[c >> 5] |= np.uint32(1 << (c & 31))
-            table[nseg == t_nseg, 4:12] = mask
-        return row_off, table, n_rows
-    i = 0
-    while i < Ni:
-        if nr[i] == 0:
-            i += 1
-            continue
-        rec = np.zeros(NTILE_WORDS, dtype=np.uint32)
-        rec[0] = row_off[i]
-        rec[1] = i
-        cols = 0
-        seg = 0
-        while i < Ni and nr[i] > 0 and seg < MAX_SEG and cols + nr[i] <= TILE_N:
-            rec[4 + (cols >> 5)] |= np.uint32(1 << (cols & 31))
-            if clamp[i]:
-                rec[3] |= np.uint32(1 << seg)
-            cols += int(nr[i])
+        idx = np.arange(Ni, dtype=np.int64)
+        tile_of = idx // per
+        seg_of = idx % per
+        col_of = seg_of * w
+        n_t = int(tile_of[-1]) + 1
+    else:
+        t = -1
+        cols = seg = 0
+        open_tile = False
+        for i in range(Ni):
+            n = int(nr[i])
+            if n == 0:
+                open_tile = False
+                continue
+            if not open_tile or seg >= MAX_SEG or cols + n > TILE_N:
+                t += 1
+                cols = seg = 0
+                open_tile = True
+            tile_of[i], col_of[i], seg_of[i] = t, cols, seg
+            cols += n
             seg += 1
-            i += 1
-        rec[4 + (cols >> 5)] |= np.uint32(1 << (cols & 31))      # sentinel at column `cols`
-        rec[2] = seg
-        tiles.append(rec)
-    table = np.stack(tiles) if tiles else np.zeros((0, NTILE_WORDS), dtype=np.uint32)
+        n_t = t + 1
+    table = np.zeros((n_t, NTILE_WORDS), dtype=np.uint32)
+    if n_t == 0:
+        return row_off, table, n_rows
+    has = tile_of >= 0
+    ii = np.nonzero(has)[0]
+    tt, ss = tile_of[ii], seg_of[ii]
+    first = ss == 0
+    table[tt[first], 0] = row_off[ii[first]].astype(np.uint32)
+    table[tt[first], 1] = ii[first].astype(np.uint32)
+    np.add.at(table[:, 2], tt, 1)
+    np.bitwise_or.at(table[:, 3], tt, (clamp[ii].astype(np.uint32) << ss.astype(np.uint32)))
+    seg16 = (col_of[ii] | (nr[ii] << 8)).astype(np.uint32)
+    np.bitwise_or.at(table, (tt, 4 + ss // 2), seg16 << (16 * (ss % 2)).astype(np.uint32))
     return row_off, table, n_rows
 
 

@@ -81,7 +81,7 @@ typedef struct alad_ntile {      /* one 240-column tile of packed region rows (d
   int32_t img0;                  /* first image (row of S) of the tile; images are consecutive */
   int32_t nseg;                  /* images in the tile (<= ALAD_MAX_SEG)                     */
   uint32_t clamp_bits;           /* bit s: image img0+s has masked slots -> max starts at 0  */
-  uint32_t start_mask[8];        /* bit c: column c starts a segment; bit ncols = sentinel   */
+  uint16_t seg[ALAD_MAX_SEG];    /* image s: low byte = first column, high byte = #columns   */
 } alad_ntile;
 
 typedef struct alad_mrsw_fwd_args {
