@@ -30,13 +30,31 @@ class MrswFwdArgs(C.Structure):
     ]
 
 
+class MrswBwdArgs(C.Structure):
+    _fields_ = [
+        ("im", C.c_void_p), ("im_stride_b", C.c_int64), ("im_stride_s", C.c_int64),
+        ("s", C.c_void_p), ("s_stride_b", C.c_int64), ("s_stride_s", C.c_int64),
+        ("Bi", C.c_int32), ("S_im", C.c_int32), ("Bc", C.c_int32), ("S_s", C.c_int32), ("d", C.c_int32),
+        ("nr", C.c_void_p), ("nw", C.c_void_p),
+        ("G0", C.c_void_p), ("ldG0", C.c_int64), ("g0_scale", C.c_void_p), ("G1", C.c_void_p), ("ldG1", C.c_int64),
+        ("d_im", C.c_void_p), ("d_s", C.c_void_p), ("eps", C.c_float), ("max_pairs", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/alad_b200.h one to one
 _I32, _I64, _P = C.c_int32, C.c_int64, C.c_void_p
 PROTOTYPES = {
     "alad_abi_version": (C.c_int, []),
     "alad_last_error": (C.c_char_p, []),
+    "alad_h2d_2d": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P]),
     "alad_pack_tokens": (C.c_int, [C.POINTER(PackArgs), _P]),
     "alad_mrsw_scores_fwd": (C.c_int, [C.POINTER(MrswFwdArgs), _P]),
+    "alad_mrsw_bwd_workspace_bytes": (C.c_int64, [_I32, _I32, _I32, _I32, _I64]),
+    "alad_mrsw_scores_bwd": (C.c_int, [C.POINTER(MrswBwdArgs), _P]),
+    "alad_loss_workspace_bytes": (C.c_int64, [_I32]),
+    "alad_triplet_fwd_bwd": (C.c_int, [_P, _I64, _I32, C.c_float, _I32, _P, _P, _I64, _P, _P, _P, _P]),
+    "alad_listnet_fwd_bwd": (C.c_int, [_P, _I64, _P, _I64, _I32, C.c_float, C.c_float, _P, _P, _I64, _P, _P]),
     "alad_rank_rows": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "alad_col_gt": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "alad_col_count": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
@@ -68,7 +86,17 @@ def lib():
     return _lib
 
 
+# kernels launched per successful entry-point call (bench.py reports the total as gpu_launches)
+KERNELS_PER_CALL = {
+    "alad_h2d_2d": 0, "alad_pack_tokens": 1, "alad_mrsw_scores_fwd": 1, "alad_mrsw_scores_bwd": 6,
+    "alad_triplet_fwd_bwd": 2, "alad_listnet_fwd_bwd": 2, "alad_rank_rows": 1, "alad_col_gt": 1,
+    "alad_col_count": 1, "alad_col_topk": 1, "alad_topk_merge": 1,
+}
+launch_count = {"kernels": 0}
+
+
 def check(rc, what):
+    launch_count["kernels"] += KERNELS_PER_CALL.get(what, 0)
     if rc != 0:
         msg = lib().alad_last_error()
         raise AladError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")

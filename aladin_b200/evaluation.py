@@ -1,0 +1,150 @@
+"""Drop-ins for ``alad.evaluation.i2t`` / ``t2i`` (alad/evaluation.py:158-327).
+
+Same signatures, same return tuples (7 metrics, optionally (ranks, top1) / (ranks, top50) as
+float64 numpy arrays).  When ``sim_function`` is (or closes over) an
+``aladin_b200.loss.AlignmentContrastiveLoss`` with aggregation 'MrSw' -- which is exactly
+what alad/test.py:258-264 and alad/train.py:493-500 build -- the whole Ni x Nc score block is
+computed once on the GPU and both directions are ranked from it; ``sim_function=None`` is the
+global-vector path on slot 0 (evaluation.py:195-197,284-286); any other callable is invoked
+per query like the reference does, and only the ranking runs in our kernels."""
+import numpy as np
+import torch
+
+from . import ranking, retrieval, scoring
+
+_cache = {}
+
+
+def _find_scorer(fn):
+    from .loss import AlignmentContrastiveLoss
+    if fn is None:
+        return None
+    cands = [fn, getattr(fn, "alad_scorer", None), getattr(fn, "__self__", None)]
+    for cell in getattr(fn, "__closure__", None) or ():
+        try:
+            cands.append(cell.cell_contents)
+        except ValueError:
+            pass
+    for c in cands:
+        if isinstance(c, AlignmentContrastiveLoss) and c.aggregation == "MrSw":
+            return c
+    return None
+
+
+def _key(images, captions, img_lens, cap_lens, mode, precision):
+    return (images.data_ptr(), captions.data_ptr(), tuple(images.shape), tuple(captions.shape), images._version,
+            captions._version, hash(tuple(img_lens)), hash(tuple(cap_lens)), mode, precision)
+
+
+def _callback_scores(images, captions, img_lens, cap_lens, sim_function, cap_batches):
+    """Reference behaviour for arbitrary callables: one sim_function call per query image and
+    gallery chunk (evaluation.py:199-210); results land in a device matrix for our ranking."""
+    N = images.shape[0]
+    Ni = N // 5
+    per = captions.shape[0] // cap_batches
+    S = torch.empty((Ni, per * cap_batches), dtype=torch.float32, device="cuda")
+    caps_dev = [captions[b * per:(b + 1) * per].cuda() for b in range(cap_batches)]
+    for i in range(Ni):
+        im = images[5 * i].reshape(1, images.shape[1], images.shape[2]).cuda()
+        for b in range(cap_batches):
+            d = sim_function(im, caps_dev[b], [img_lens[5 * i]], cap_lens[b * per:(b + 1) * per])
+            S[i, b * per:(b + 1) * per] = d.reshape(-1).float().cuda()
+    return S
+
+
+def clear_cache():
+    """Forget the score block kept from the previous i2t/t2i call."""
+    _cache.clear()
+
+
+def _dist_state():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_world_size(), dist.get_rank(), dist.group.WORLD
+    return 1, 0, None
+
+
+def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
+    """Scores + both directions' ranks for the whole gallery, computed once per distinct input.
+
+    Returns dict(S, img_off, ranks_i2t, top1, ranks_t2i, top50).  Under torch.distributed
+    (world > 1) the fused path shards the gallery images across ranks (retrieval.py)."""
+    scorer = _find_scorer(sim_function)
+    mode = "global" if sim_function is None else ("fused" if scorer is not None else "callback")
+    precision = getattr(scorer, "precision", None) or scoring.get_precision()
+    key = _key(images, captions, img_lens, cap_lens, mode, precision) if mode != "callback" else None
+    if key is not None and _cache.get("key") == key:
+        return _cache["res"]
+    Ni = images.shape[0] // 5
+    world, rank, group = (1, 0, None)
+    img_off = 0
+    if mode == "global":
+        S = scoring.dot_scores(images[0::5][:, 0, :], captions[:, 0, :], precision=precision)
+    elif mode == "fused":
+        world, rank, group = _dist_state()
+        gal = retrieval.AlignmentGallery(images, captions, img_lens, cap_lens, n_images=Ni, img_start=0, img_step=5,
+                                         precision=precision, world=world, rank=rank)
+        S = gal.scores()
+        img_off = gal.lo
+    else:
+        S = _callback_scores(images, captions, img_lens, cap_lens, sim_function, batches)
+    k = min(50, Ni)
+    ri, t1, rt, tk = retrieval.rank_both_directions(S, Ni, img_off=img_off, n_images_total=Ni, k=k, group=group)
+    res = dict(S=S, img_off=img_off, world=world, ranks_i2t=ri, top1=t1, ranks_t2i=rt, top50=tk)
+    if key is not None:
+        _cache.clear()
+        _cache.update(key=key, res=res)
+    return res
+
+
+def _ndcg(ndcg_scorer, res, npts, fold_index, retrieval_kind):
+    """NDCG hooks (evaluation.py:225-228,310-313): need the full order per query."""
+    if res["world"] > 1:
+        raise NotImplementedError("NDCG scoring needs the whole score block on one device")
+    S = res["S"]
+    n = npts if retrieval_kind == "sentence" else 5 * npts
+    rougel, spice = np.zeros(n), np.zeros(n)
+    for q in range(n):
+        d = S[q] if retrieval_kind == "sentence" else S[:, q]
+        inds = torch.argsort(d, descending=True, stable=True).cpu().numpy()
+        rougel[q], spice[q] = ndcg_scorer.compute_ndcg(npts, q, inds.astype(int), fold_index=fold_index,
+                                                       retrieval=retrieval_kind).values()
+    return rougel, spice
+
+
+def _check_measure(measure):
+    if measure == "order":
+        raise NotImplementedError("measure='order' (order embeddings) is outside the ported path: no shipped "
+                                  "ALADIN config selects it (configs/*.yaml: measure: 'dot')")
+
+
+def i2t(images, captions, img_lenghts, cap_lenghts, npts=None, return_ranks=False, ndcg_scorer=None, fold_index=0,
+        measure='dot', sim_function=None, cap_batches=1):
+    """Images->Text (image annotation).  Mirrors alad/evaluation.py:158-241."""
+    _check_measure(measure)
+    if npts is None:
+        npts = images.shape[0] // 5
+    res = _retrieve(images, captions, img_lenghts, cap_lenghts, sim_function, cap_batches)
+    ranks = res["ranks_i2t"][:npts].copy()
+    top1 = res["top1"][:npts].copy()
+    if ndcg_scorer is not None:
+        _ndcg(ndcg_scorer, res, npts, fold_index, "sentence")
+    metrics = retrieval.recall_tuple(ranks) + (0, 0)
+    return (metrics, (ranks, top1)) if return_ranks else metrics
+
+
+def t2i(images, captions, img_lenghts, cap_lenghts, npts=None, return_ranks=False, ndcg_scorer=None, fold_index=0,
+        measure='dot', sim_function=None, im_batches=1):
+    """Text->Images (image search).  Mirrors alad/evaluation.py:244-327."""
+    _check_measure(measure)
+    if npts is None:
+        npts = images.shape[0] // 5
+    if images.shape[0] // 5 < 50:
+        raise ValueError("t2i keeps the 50 best images per caption (evaluation.py:257,308): need >= 50 gallery images")
+    res = _retrieve(images, captions, img_lenghts, cap_lenghts, sim_function, im_batches)
+    ranks = res["ranks_t2i"][:5 * npts].copy()
+    top50 = res["top50"][:5 * npts].copy()
+    if ndcg_scorer is not None:
+        _ndcg(ndcg_scorer, res, npts, fold_index, "image")
+    metrics = retrieval.recall_tuple(ranks) + (0, 0)
+    return (metrics, (ranks, top50)) if return_ranks else metrics

@@ -1,0 +1,280 @@
+"""Drop-ins for the criteria of ``alad/loss.py`` used by ``ALADModel`` (alad/alad_model.py:275-292,
+380, 386, 405): ``Contrastive``, ``AlignmentContrastiveLoss``, ``ContrastiveLoss``,
+``DistillationLoss`` -- same constructor arguments, same ``forward`` signatures and return
+conventions, no parameters (except ``DistillationLoss(mode='mse').wb``, kept so that
+state_dict keys stay identical).  All math runs in the CUDA kernels behind the C ABI;
+autograd is wired with ``torch.autograd.Function``."""
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _cabi, scoring
+
+
+def _ws(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------
+# kernels as functions
+# --------------------------------------------------------------------------------------
+def triplet_fwd_bwd(scores, margin, max_violation, want_grad=True):
+    """(loss 0-d, G [B,B] or None, row_arg, col_arg) -- alad/loss.py:42-67 + SURVEY A.1."""
+    lib = _cabi.lib()
+    if scores.dim() != 2 or scores.shape[0] != scores.shape[1]:
+        raise RuntimeError("compute_contrastive_loss needs a square score matrix (torch.eye at alad/loss.py:55)")
+    S = scores.detach()
+    if S.stride(1) != 1:
+        S = S.contiguous()
+    B = S.shape[0]
+    dev = S.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    G = torch.empty((B, B), dtype=torch.float32, device=dev) if want_grad else None
+    ra = torch.empty(B, dtype=torch.int32, device=dev)
+    ca = torch.empty(B, dtype=torch.int32, device=dev)
+    ws = _ws(lib.alad_loss_workspace_bytes(B), dev)
+    _cabi.check(lib.alad_triplet_fwd_bwd(S.data_ptr(), max(S.stride(0), B), B, float(margin), 1 if max_violation else 0,
+                                         loss.data_ptr(), G.data_ptr() if G is not None else None, B, ra.data_ptr(),
+                                         ca.data_ptr(), ws.data_ptr(), _cabi.stream_ptr()), "alad_triplet_fwd_bwd")
+    return loss, G, ra, ca
+
+
+def listnet_fwd_bwd(teacher, student, temperature=6.0, eps=1e-10, want_grad=True):
+    """(loss 0-d, dM or None) -- alad/loss.py:427-445 + SURVEY A.2."""
+    lib = _cabi.lib()
+    T = teacher.detach().float()
+    M = student.detach().float()
+    if T.shape != M.shape or T.dim() != 2 or T.shape[0] != T.shape[1]:
+        raise RuntimeError("listnet distillation expects two square matrices of equal shape")
+    T = T if T.stride(1) == 1 else T.contiguous()
+    M = M if M.stride(1) == 1 else M.contiguous()
+    B = T.shape[0]
+    dev = M.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dM = torch.empty((B, B), dtype=torch.float32, device=dev) if want_grad else None
+    ws = _ws(lib.alad_loss_workspace_bytes(B), dev)
+    _cabi.check(lib.alad_listnet_fwd_bwd(T.data_ptr(), max(T.stride(0), B), M.data_ptr(), max(M.stride(0), B), B,
+                                         float(temperature), float(eps), loss.data_ptr(),
+                                         dM.data_ptr() if dM is not None else None, B, ws.data_ptr(),
+                                         _cabi.stream_ptr()), "alad_listnet_fwd_bwd")
+    return loss, dM
+
+
+def mrsw_backward(im_set, s_seq, nr, nw, G0=None, g0_scale=None, G1=None, eps=1e-12):
+    """(d im_set, d s_seq) for dL/dS = g0_scale*G0 + G1 (alad_mrsw_scores_bwd)."""
+    lib = _cabi.lib()
+    Bi, S_im, d = im_set.shape
+    Bc, S_s, _ = s_seq.shape
+    dev = im_set.device
+    d_im = torch.empty((Bi, S_im, d), dtype=torch.float32, device=dev)
+    d_s = torch.empty((Bc, S_s, d), dtype=torch.float32, device=dev)
+    max_pairs = max(Bi * Bc, 1)
+    nbytes = lib.alad_mrsw_bwd_workspace_bytes(Bi, S_im, Bc, S_s, max_pairs)
+    ws = _ws(nbytes, dev)
+    nr_d = scoring._to_dev(np.asarray(nr, np.int32), dev)
+    nw_d = scoring._to_dev(np.asarray(nw, np.int32), dev)
+
+    def ptr(t):
+        return t.data_ptr() if t is not None else None
+
+    for g in (G0, G1):
+        assert g is None or (g.dtype == torch.float32 and g.stride(1) == 1 and g.shape == (Bi, Bc))
+    a = _cabi.MrswBwdArgs(
+        im=im_set.data_ptr(), im_stride_b=im_set.stride(0), im_stride_s=im_set.stride(1),
+        s=s_seq.data_ptr(), s_stride_b=s_seq.stride(0), s_stride_s=s_seq.stride(1),
+        Bi=Bi, S_im=S_im, Bc=Bc, S_s=S_s, d=d, nr=nr_d.data_ptr(), nw=nw_d.data_ptr(),
+        G0=ptr(G0), ldG0=max(G0.stride(0), Bc) if G0 is not None else 0, g0_scale=ptr(g0_scale),
+        G1=ptr(G1), ldG1=max(G1.stride(0), Bc) if G1 is not None else 0,
+        d_im=d_im.data_ptr(), d_s=d_s.data_ptr(), eps=eps, max_pairs=max_pairs,
+        workspace=ws.data_ptr(), workspace_bytes=nbytes)
+    _cabi.check(lib.alad_mrsw_scores_bwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_bwd")
+    return d_im, d_s
+
+
+# --------------------------------------------------------------------------------------
+# autograd wiring
+# --------------------------------------------------------------------------------------
+class _TripletFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, margin, max_violation):
+        loss, G, _, _ = triplet_fwd_bwd(scores, margin, max_violation, want_grad=scores.requires_grad)
+        ctx.save_for_backward(G)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (G,) = ctx.saved_tensors
+        return G * g, None, None
+
+
+class _ListnetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, teacher, student):
+        loss, dM = listnet_fwd_bwd(teacher, student, want_grad=student.requires_grad)
+        ctx.save_for_backward(dM)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dM,) = ctx.saved_tensors
+        return None, dM * g                     # teacher is detached (alad/loss.py:370)
+
+
+class _DotScoresFn(torch.autograd.Function):
+    """scores = im @ s.T on the tcgen05 GEMM; backward = two more GEMMs on the same kernel."""
+
+    @staticmethod
+    def forward(ctx, im, s, precision, normalize):
+        ctx.save_for_backward(im, s)
+        ctx.precision = precision
+        ctx.normalize = normalize
+        return scoring.dot_scores(im, s, precision=precision, normalize=normalize, eps=0.0)
+
+    @staticmethod
+    def backward(ctx, G):
+        im, s = ctx.saved_tensors
+        if ctx.normalize:
+            raise NotImplementedError("gradient of cosine_sim is not ported (no shipped config trains with it)")
+        G = G.contiguous().float()
+        d_im = d_s = None
+        if ctx.needs_input_grad[0]:
+            d_im = scoring.dot_scores(G, s.detach().float().t().contiguous(), precision="fp32")       # G @ s
+        if ctx.needs_input_grad[1]:
+            d_s = scoring.dot_scores(G.t().contiguous(), im.detach().float().t().contiguous(), precision="fp32")  # G.T @ im
+        return d_im, d_s, None, None
+
+
+class _AlignmentFn(torch.autograd.Function):
+    """(loss, S) = alignment scores + hinge; backward recomputes only the pairs whose dL/dS != 0."""
+
+    @staticmethod
+    def forward(ctx, im_set, s_seq, im_len, s_len, margin, max_violation, want_loss, precision):
+        ctx.set_materialize_grads(False)
+        im_c = scoring._require_cuda(im_set.detach(), "im_set")
+        s_c = scoring._require_cuda(s_seq.detach(), "s_seq")
+        S = scoring.alignment_scores(im_c, s_c, im_len, s_len, precision=precision)
+        _, _, nr, nw, _ = scoring.scored_counts(im_c.shape, s_c.shape, im_len, s_len)
+        needs_grad = im_set.requires_grad or s_seq.requires_grad
+        G0 = None
+        if want_loss:
+            loss, G0, _, _ = triplet_fwd_bwd(S, margin, max_violation, want_grad=needs_grad)
+        else:
+            loss = torch.zeros((), dtype=torch.float32, device=S.device)
+        ctx.nr, ctx.nw = nr, nw
+        ctx.devices = (im_set.device, s_seq.device)
+        ctx.save_for_backward(im_c, s_c, G0)
+        return loss, S
+
+    @staticmethod
+    def backward(ctx, g_loss, g_S):
+        im_c, s_c, G0 = ctx.saved_tensors
+        use_G0 = G0 is not None and g_loss is not None
+        if not use_G0 and g_S is None:
+            return (None,) * 8
+        g_scale = g_loss.detach().float().reshape(1).contiguous() if use_G0 else None
+        G1 = g_S.detach().float().contiguous() if g_S is not None else None
+        d_im, d_s = mrsw_backward(im_c, s_c, ctx.nr, ctx.nw, G0=G0 if use_G0 else None, g0_scale=g_scale, G1=G1)
+        return (d_im.to(ctx.devices[0]) if ctx.needs_input_grad[0] else None,
+                d_s.to(ctx.devices[1]) if ctx.needs_input_grad[1] else None, None, None, None, None, None, None)
+
+
+# --------------------------------------------------------------------------------------
+# nn.Module drop-ins
+# --------------------------------------------------------------------------------------
+def dot_sim(im, s):
+    """alad/loss.py:8-11."""
+    return _DotScoresFn.apply(im, s, None, False)
+
+
+def cosine_sim(im, s):
+    """alad/loss.py:13-18 (l2norm without eps, then mm); forward only."""
+    return _DotScoresFn.apply(im, s, None, True)
+
+
+def order_sim(im, s):
+    raise NotImplementedError("order_sim (alad/loss.py:20-26) is outside the ported path: unused by every config")
+
+
+class Contrastive(nn.Module):
+    """alad/loss.py:29-67."""
+
+    def __init__(self, margin=0, measure=False, max_violation=False):
+        super().__init__()
+        self.margin = margin
+        if measure == 'order':
+            self.sim = order_sim
+        elif measure == 'cosine':
+            self.sim = cosine_sim
+        elif measure == 'dot':
+            self.sim = dot_sim
+        self.max_violation = max_violation
+
+    def compute_contrastive_loss(self, scores):
+        if not scores.is_cuda:
+            scores = scores.cuda()
+        return _TripletFn.apply(scores.float(), self.margin, self.max_violation)
+
+
+class AlignmentContrastiveLoss(Contrastive):
+    """alad/loss.py:70-159.  aggregation 'MrSw' (every shipped config) runs the fused kernel."""
+
+    SUPPORTED = ("MrSw",)
+
+    def __init__(self, margin=0, measure=False, max_violation=False, aggregation='sum-max-sentences'):
+        super().__init__(margin, measure, max_violation)
+        self.aggregation = aggregation
+        self.precision = None          # None -> aladin_b200.get_precision()
+
+    def forward(self, im_set, s_seq, im_len, s_len, return_loss=True, return_similarity_mat=False):
+        if self.aggregation not in self.SUPPORTED:
+            raise NotImplementedError(
+                f"aggregation {self.aggregation!r} is not ported yet (SURVEY §8(f) rank 1); 'MrSw' is what "
+                "configs/*.yaml select")
+        out_dev = im_set.device
+        loss, S = _AlignmentFn.apply(im_set, s_seq, list(im_len), list(s_len), self.margin, self.max_violation,
+                                     bool(return_loss), self.precision)
+        if out_dev.type != "cuda":
+            loss, S = loss.to(out_dev), S.to(out_dev)
+        if return_loss and return_similarity_mat:
+            return loss, S
+        elif return_loss:
+            return loss
+        elif return_similarity_mat:
+            return S
+
+
+class ContrastiveLoss(Contrastive):
+    """alad/loss.py:162-186."""
+
+    def __init__(self, margin=0, measure=False, max_violation=False):
+        super().__init__(margin, measure, max_violation)
+
+    def forward(self, im, s, return_similarity_mat=False):
+        scores = self.sim(im, s)
+        loss = self.compute_contrastive_loss(scores)
+        if return_similarity_mat:
+            return loss, scores
+        return loss
+
+
+class DistillationLoss(nn.Module):
+    """alad/loss.py:359-447; mode 'listnet' (every shipped config) is ported."""
+
+    def __init__(self, mode='mse', margin=0.2, threshold=0.1, stride=3):
+        super().__init__()
+        self.mode = mode
+        self.margin = margin
+        self.threshold = threshold
+        self.stride = stride
+        if mode == 'mse':
+            self.wb = nn.Parameter(torch.FloatTensor([0.5, 0.5]), requires_grad=True)
+
+    def forward(self, teacher_scores, student_scores):
+        if self.mode != 'listnet':
+            raise NotImplementedError(f"distillation mode {self.mode!r} is not ported yet (SURVEY §8(f) rank 3); "
+                                      "configs/*.yaml select 'listnet'")
+        if not student_scores.is_cuda:
+            student_scores = student_scores.cuda()
+        return _ListnetFn.apply(teacher_scores.detach().to(student_scores.device), student_scores)

@@ -1,0 +1,178 @@
+"""All-pairs retrieval engine: upload -> pack -> fused MrSw scores -> exact ranks + top-k.
+
+This is the fused replacement for the per-query Python loops of alad/evaluation.py:175-223
+(i2t) and :263-313 (t2i): the gallery goes to the device once, one pass over the
+Ni x Nc score block serves both directions, ranks come from "count ahead of the ground
+truth" kernels instead of per-query numpy argsorts.
+
+Multi-GPU: gallery images are split into contiguous image blocks, captions are
+replicated.  i2t needs no exchange; t2i exchanges the ground-truth scores (all-reduce of
+Nc floats), the per-shard counts (all-reduce of Nc ints) and the per-shard top-k candidates
+(all-gather of k (score, index) pairs per caption) through torch.distributed / NCCL.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi, ranking, scoring
+from .tiling import build_region_tiles
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous image block of `rank`: [lo, hi)."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def _upload_rows(x, row_start, row_step, n_rows, n_slots, out=None):
+    """Rows row_start + i*row_step (i < n_rows), slots [0, n_slots) of a [N,S,d] fp32 tensor ->
+    device tensor [n_rows, n_slots, d].  CPU sources go through one pitched H2D copy."""
+    N, S, d = x.shape
+    if x.is_cuda:
+        return x[row_start:row_start + (n_rows - 1) * row_step + 1:row_step, :n_slots] if n_rows else x[:0, :n_slots]
+    if x.dtype != torch.float32 or x.stride(2) != 1 or x.stride(1) != d:
+        x = x.float().contiguous()
+    if out is None:
+        out = torch.empty((n_rows, n_slots, d), dtype=torch.float32, device="cuda")
+    dst = out[:n_rows, :n_slots]
+    assert out.shape[1] == n_slots and out.shape[2] == d and out.is_contiguous()
+    if n_rows and n_slots:
+        src = x.data_ptr() + row_start * x.stride(0) * 4
+        _cabi.check(_cabi.lib().alad_h2d_2d(out.data_ptr(), n_slots * d * 4, src, row_step * x.stride(0) * 4,
+                                            n_slots * d * 4, n_rows, _cabi.stream_ptr()), "alad_h2d_2d")
+    return dst
+
+
+class AlignmentGallery:
+    """Scores a block of gallery images against all captions.
+
+    images   [N_img_rows, S_im, d]  fp32, CPU (pinned or pageable) or CUDA
+    captions [Nc, S_s, d]
+    image i of the gallery is row img_start + i*img_step (the reference stores every image 5x:
+    i2t reads row 5i, t2i rows 0::5 -- alad/evaluation.py:178,252)."""
+
+    def __init__(self, images, captions, img_lens, cap_lens, n_images, img_start=0, img_step=1,
+                 precision=None, world=1, rank=0, caption_chunk=4096):
+        if not torch.cuda.is_available():
+            raise _cabi.AladError("aladin_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.precision = precision or scoring.get_precision()
+        self.images, self.captions = images, captions
+        self.Ni, self.Nc = int(n_images), int(captions.shape[0])
+        self.img_start, self.img_step = img_start, img_step
+        self.world, self.rank = world, rank
+        self.lo, self.hi = shard_bounds(self.Ni, world, rank)
+        self.caption_chunk = caption_chunk
+        img_lens_g = [img_lens[img_start + i * img_step] for i in range(self.Ni)]
+        self.R, self.W, self.nr, self.nw, self.clamp = scoring.scored_counts(
+            (self.Ni, images.shape[1]), captions.shape, img_lens_g, cap_lens)
+
+    def scores(self):
+        """S[hi-lo, Nc] fp32 on the device for this shard's image block."""
+        split = self.precision == "fp32"
+        lo, hi = self.lo, self.hi
+        n_loc = hi - lo
+        dev = torch.device("cuda", torch.cuda.current_device())
+        S = torch.empty((n_loc, self.Nc), dtype=torch.float32, device=dev)
+        if n_loc == 0 or self.Nc == 0:
+            return S
+        nr, nw = self.nr[lo:hi], self.nw
+        # ---- regions of this image block
+        Lr = 1 + (int(nr.max()) if n_loc else 0)
+        im_dev = _upload_rows(self.images, self.img_start + lo * self.img_step, self.img_step, n_loc, Lr)
+        regions = scoring.pack_tokens(im_dev, nr, slot0=1, mode=2 if split else 0)
+        _, table, _ = build_region_tiles(nr, self.clamp[lo:hi])
+        n_tiles = len(table)
+        tiles_dev = scoring._to_dev(table.view(np.int32).reshape(-1), dev) if n_tiles else None
+        # ---- captions, in chunks; CPU sources are double-buffered so that the upload of chunk
+        #      k+1 overlaps the scoring of chunk k
+        on_cpu = not self.captions.is_cuda
+        chunk = self.caption_chunk if on_cpu else self.Nc
+        bounds = [(c0, min(self.Nc, c0 + chunk)) for c0 in range(0, self.Nc, chunk)]
+        main = torch.cuda.current_stream()
+        if on_cpu:
+            Lw_max = 1 + int(nw.max())
+            stage = [torch.empty((chunk, Lw_max, self.captions.shape[2]), dtype=torch.float32, device=dev) for _ in range(2)]
+            copy_stream = torch.cuda.Stream()
+            copy_stream.wait_stream(main)
+            ready = [torch.cuda.Event() for _ in bounds]
+            freed = [None, None]
+        for k, (c0, c1) in enumerate(bounds):
+            nw_k = nw[c0:c1]
+            if on_cpu:
+                b = k & 1
+                with torch.cuda.stream(copy_stream):
+                    if freed[b] is not None:
+                        copy_stream.wait_event(freed[b])
+                    cap_dev = _upload_rows(self.captions, c0, 1, c1 - c0, Lw_max, out=stage[b])
+                    ready[k].record(copy_stream)
+                main.wait_event(ready[k])
+            else:
+                cap_dev = self.captions[c0:c1]
+            words = scoring.pack_tokens(cap_dev, nw_k, slot0=1, mode=1 if split else 0, want_row_item=True)
+            scoring.mrsw_scores_packed(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, out=S[:, c0:c1])
+            if on_cpu:
+                freed[b] = torch.cuda.Event()
+                freed[b].record(main)
+        return S
+
+
+def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=None, gather_i2t=True):
+    """Exact i2t / t2i ranks and top-k from a shard's score block S[n_loc, Nc].
+
+    Returns numpy arrays shaped like the reference's (alad/evaluation.py:166-167,255-256):
+    ranks_i2t[npts], top1[npts], ranks_t2i[5*npts], topk[5*npts, k] (float64)."""
+    import torch.distributed as dist
+    n_loc, Nc = S.shape
+    dist_on = group is not None and dist.is_initialized() and dist.get_world_size(group) > 1
+    Ni_total = n_images_total if n_images_total is not None else n_loc
+    npts = min(npts, Ni_total)
+    # ---------------- i2t: rows (queries = images < npts), gallery = all captions
+    q_loc = max(0, min(n_loc, npts - img_off))
+    rank_i, top1_i = ranking.rank_rows(S[:q_loc], 5, img_off)
+    # ---------------- t2i: columns (queries = captions < 5*npts), gallery = all images
+    ncq = min(Nc, 5 * npts)
+    Sq = S[:, :ncq]
+    gt = torch.zeros(ncq, dtype=torch.float32, device=S.device)
+    ranking.col_gt(Sq, gt, 5, img_off)
+    if dist_on:
+        dist.all_reduce(gt, group=group)                       # every entry is owned by exactly one shard
+    count = ranking.col_count(Sq, gt, 5, img_off)
+    k_eff = k
+    cs, ci = ranking.col_topk(Sq, k_eff, img_off)
+    ts, ti = ranking.topk_merge(cs, ci)
+    if dist_on:
+        world = dist.get_world_size(group)
+        dist.all_reduce(count, group=group)
+        gs = [torch.empty_like(ts) for _ in range(world)]
+        gi = [torch.empty_like(ti) for _ in range(world)]
+        dist.all_gather(gs, ts, group=group)
+        dist.all_gather(gi, ti, group=group)
+        ts, ti = ranking.topk_merge(torch.stack(gs).contiguous(), torch.stack(gi).contiguous())
+        if gather_i2t:
+            per = (Ni_total + world - 1) // world
+            pad_r = torch.full((per,), -1, dtype=torch.int32, device=S.device)
+            pad_t = torch.full((per,), -1, dtype=torch.int32, device=S.device)
+            pad_r[:q_loc] = rank_i
+            pad_t[:q_loc] = top1_i
+            gr = [torch.empty_like(pad_r) for _ in range(world)]
+            gt1 = [torch.empty_like(pad_t) for _ in range(world)]
+            dist.all_gather(gr, pad_r, group=group)
+            dist.all_gather(gt1, pad_t, group=group)
+            rank_i = torch.cat(gr)[:npts]
+            top1_i = torch.cat(gt1)[:npts]
+    out = (rank_i.cpu().numpy().astype(np.float64), top1_i.cpu().numpy().astype(np.float64),
+           count.cpu().numpy().astype(np.float64), ti.cpu().numpy().astype(np.float64))
+    return out
+
+
+def recall_tuple(ranks):
+    """(r1, r5, r10, medr, meanr) exactly as alad/evaluation.py:231-235."""
+    n = ranks.size
+    r1 = 100.0 * np.count_nonzero(ranks < 1) / n
+    r5 = 100.0 * np.count_nonzero(ranks < 5) / n
+    r10 = 100.0 * np.count_nonzero(ranks < 10) / n
+    medr = np.floor(np.median(ranks)) + 1
+    meanr = ranks.mean() + 1
+    return r1, r5, r10, medr, meanr

@@ -14,6 +14,8 @@ from . import _cabi
 from .tiling import (build_region_tiles, exclusive_cumsum, gemm_tiles, padded_rows, round_up, valid_counts)
 
 PRECISIONS = ("bf16", "fp32")
+# bench.py sets this to a list to collect (start_event, end_event, pairs, Kp) of every scoring launch
+kernel_timeline = None
 _precision = "bf16"
 
 
@@ -97,7 +99,13 @@ def mrsw_scores_packed(words, regions, tiles_dev, n_tiles, Ni, Nc, out=None, num
         n_region_rows=regions.n_rows, Kp=words.Kp, row_cap=words.row_item.data_ptr(),
         ntiles=tiles_dev.data_ptr() if n_tiles else None, n_ntiles=n_tiles, S=out.data_ptr(),
         ldS=out.stride(0) if Ni > 1 else max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=0, num_ctas=num_ctas)
+    if kernel_timeline is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _cabi.check(lib.alad_mrsw_scores_fwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_fwd")
+    if kernel_timeline is not None:
+        e1.record()
+        kernel_timeline.append((e0, e1, Ni, Nc, words.Kp))
     return out
 
 

@@ -51,7 +51,7 @@ def eval_containers(seed, Ni, S, d, max_regions, max_words, alpha=0.55, dense=Fa
     return images, captions, img_lens, [int(x) for x in cap_len]
 
 
-def dense_gallery_device(Ni, Nc, regions=34, words=50, d=1024, device="cuda", alpha=0.3, seeds=(1234, 5678)):
+def dense_gallery_device(Ni, Nc, regions=34, words=50, d=1024, device="cuda", alpha=0.05, seeds=(1234, 5678)):
     """Full-size dense roofline set generated on the device: every image has `regions`
     scored regions, every caption `words` scored words -> raw containers S_im = regions+1,
     S_s = words+3 (SURVEY §8(d)).  Returns (images[Ni,S_im,d], captions[Nc,S_s,d], im_len, s_len);

@@ -40,6 +40,15 @@ int alad_abi_version(void);
 const char* alad_last_error(void);
 
 /* ---------------------------------------------------------------------------------
+ * alad_h2d_2d -- pitched host->device upload (cudaMemcpy2DAsync): only the scored slots of
+ * the [N, 71, d] evaluation containers (alad/evaluation.py:98-99) cross PCIe, and the 5x
+ * duplicated image rows are read with a 5-row pitch.  Replaces the per-query `.cuda()` of
+ * the whole gallery (evaluation.py:179,202,267,291).  src_host may be pinned or pageable.
+ * ------------------------------------------------------------------------------- */
+int alad_h2d_2d(void* dst, int64_t dst_pitch, const void* src_host, int64_t src_pitch, int64_t width_bytes,
+                int64_t height, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * alad_pack_tokens  -- replaces F.normalize + slot slicing at alad/loss.py:80-90 and the
  * per-query `.cuda()` uploads of alad/evaluation.py:179,202,267,291.
  * For item b and scored token t < count[b] reads src[b, slot0 + t, :], scales it by
@@ -100,6 +109,52 @@ typedef struct alad_mrsw_fwd_args {
   int32_t num_ctas;              /* 0 = one persistent CTA per SM                            */
 } alad_mrsw_fwd_args;
 int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * alad_mrsw_scores_bwd -- autograd of alad/loss.py:80-125 for aggregation 'MrSw': given
+ * dL/dS = g0_scale * G0 + G1 (either may be NULL; g0_scale is a DEVICE scalar or NULL = 1)
+ * writes dL/d im_set [Bi,S_im,d] and dL/d s_seq [Bc,S_s,d] (contiguous fp32, zeroed inside).
+ * Non-zero entries of dL/dS are compacted into a pair list and only those (image, caption)
+ * tiles are recomputed (<= 3B pairs with hardest-negative mining).
+ * ------------------------------------------------------------------------------- */
+typedef struct alad_mrsw_bwd_args {
+  const float* im;               /* raw image tokens [Bi, S_im, d], innermost stride 1       */
+  int64_t im_stride_b, im_stride_s;
+  const float* s;                /* raw caption tokens [Bc, S_s, d]                          */
+  int64_t s_stride_b, s_stride_s;
+  int32_t Bi, S_im, Bc, S_s, d;
+  const int32_t* nr;             /* [Bi] valid scored regions (slots 1 .. nr)                */
+  const int32_t* nw;             /* [Bc] valid scored words                                  */
+  const float* G0;               /* optional [Bi, ldG0]                                      */
+  int64_t ldG0;
+  const float* g0_scale;         /* optional device scalar multiplying G0                    */
+  const float* G1;               /* optional [Bi, ldG1]                                      */
+  int64_t ldG1;
+  float* d_im;
+  float* d_s;
+  float eps;                     /* F.normalize eps (1e-12)                                  */
+  int64_t max_pairs;             /* capacity of the pair list (Bi*Bc is always enough)       */
+  void* workspace;
+  int64_t workspace_bytes;       /* >= alad_mrsw_bwd_workspace_bytes(...)                    */
+} alad_mrsw_bwd_args;
+int64_t alad_mrsw_bwd_workspace_bytes(int32_t Bi, int32_t S_im, int32_t Bc, int32_t S_s, int64_t max_pairs);
+int alad_mrsw_scores_bwd(const alad_mrsw_bwd_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * B x B losses, forward + gradient in one call (workspace: alad_loss_workspace_bytes(B)).
+ * alad_triplet_fwd_bwd -- Contrastive.compute_contrastive_loss, alad/loss.py:42-67:
+ *   loss = sum_i max_j [m + S_ij - S_ii]_+ + sum_j max_i [m + S_ij - S_jj]_+   (max_violation)
+ *   or the plain sums; G (optional) = dloss/dS dense; row_arg/col_arg = hardest negative of
+ *   every row / column (-1 when nothing violates; violation counts in sum mode).
+ * alad_listnet_fwd_bwd -- DistillationLoss(mode='listnet'), alad/loss.py:427-445: teacher is
+ *   detached (loss.py:370); dM (optional) = dloss/dstudent.
+ * ------------------------------------------------------------------------------- */
+int64_t alad_loss_workspace_bytes(int32_t B);
+int alad_triplet_fwd_bwd(const float* S, int64_t ldS, int32_t B, float margin, int32_t max_violation, float* loss,
+                         float* G, int64_t ldG, int32_t* row_arg, int32_t* col_arg, void* workspace, void* stream);
+int alad_listnet_fwd_bwd(const float* teacher, int64_t ldT, const float* student, int64_t ldM, int32_t B,
+                         float temperature, float eps, float* loss, float* dM, int64_t ldG, void* workspace,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Ranking -- replaces numpy.argsort + numpy.where of alad/evaluation.py:213-223,303-308

@@ -39,3 +39,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def assert_scores_close(got, ref, rtol, what=""):
+    """Score-matrix tolerance: |got - ref| <= rtol * max(|ref|, 10% of the matrix's largest
+    magnitude).  Entry-wise relative error is meaningless for cosines that happen to be ~0;
+    the floor ties the tolerance to the scale of the matrix."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    floor = 0.1 * np.abs(ref).max() if ref.size else 0.0
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), max(floor, 1e-30))
+    assert err.max() <= rtol, f"{what}: max scaled error {err.max():.3e} > {rtol:.1e}"

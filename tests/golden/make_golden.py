@@ -227,9 +227,49 @@ def golden_retrieval():
          compute_recall=np.array(rec, dtype=np.float64), S_full=S_full)
 
 
+# ---------------------------------------------------------------------------------------
+# 6. training step composite: the three criterion calls of ALADModel.forward_loss
+#    (alad/alad_model.py:377-405) and the weighting of ALADModel.forward (:445-453) for
+#    loss-type 'alignment-distillation-matching', loss-weights [1, 1, 0.1]
+#    (configs/alad-alignment-and-matching-triplet0.1-plus-distill.yaml:23-24)
+# ---------------------------------------------------------------------------------------
+def golden_train_step():
+    r = rs(16)
+    B, S_im, S_s, d = 12, 10, 13, 64
+    img_set = r.standard_normal((S_im, B, d)).astype(np.float32)       # S x B x dim (alad_model.py:439)
+    cap_seq = r.standard_normal((S_s, B, d)).astype(np.float32)
+    for b in range(B):
+        cap_seq[1:7, b] += 1.2 * img_set[1:7, b]
+    img_cls = r.standard_normal((B, d)).astype(np.float32)
+    cap_cls = (0.7 * img_cls + r.standard_normal((B, d))).astype(np.float32)
+    img_cls /= np.linalg.norm(img_cls, axis=1, keepdims=True)
+    cap_cls /= np.linalg.norm(cap_cls, axis=1, keepdims=True)
+    img_len = [10, 7, 10, 4, 8, 9, 10, 5, 6, 10, 3, 8]
+    cap_len = [13, 8, 11, 13, 6, 9, 12, 7, 13, 10, 5, 9]
+    ts = [t(img_cls, True), t(cap_cls, True), t(img_set, True), t(cap_seq, True)]
+    matching_criterion = rloss.ContrastiveLoss(margin=0.2, measure="dot", max_violation=True)
+    alignment_criterion = rloss.AlignmentContrastiveLoss(margin=0.2, measure="dot", max_violation=True, aggregation="MrSw")
+    distillation_loss = rloss.DistillationLoss(mode="listnet")
+    matching_loss, matching_mat = matching_criterion(ts[0], ts[1], return_similarity_mat=True)
+    alignment_loss, teacher_scores = alignment_criterion(ts[2].permute(1, 0, 2), ts[3].permute(1, 0, 2), img_len, cap_len,
+                                                         return_similarity_mat=True)
+    dist = distillation_loss(teacher_scores, matching_mat)
+    weights = {"alignment": 1.0, "distillation": 1.0, "matching": 0.1}
+    loss = alignment_loss * weights["alignment"] + dist * weights["distillation"] + matching_loss * weights["matching"]
+    loss.backward()
+    save("train_step", img_cls=img_cls, cap_cls=cap_cls, img_set=img_set, cap_seq=cap_seq,
+         img_len=np.array(img_len), cap_len=np.array(cap_len),
+         matching_loss=matching_loss.detach().numpy(), alignment_loss=alignment_loss.detach().numpy(),
+         distillation_loss=dist.detach().numpy(), loss=loss.detach().numpy(),
+         matching_mat=matching_mat.detach().numpy(), teacher_scores=teacher_scores.detach().numpy(),
+         d_img_cls=ts[0].grad.numpy(), d_cap_cls=ts[1].grad.numpy(), d_img_set=ts[2].grad.numpy(),
+         d_cap_seq=ts[3].grad.numpy())
+
+
 if __name__ == "__main__":
     golden_alignment_scores()
     golden_alignment_loss()
     golden_matching()
     golden_triplet_listnet()
     golden_retrieval()
+    golden_train_step()

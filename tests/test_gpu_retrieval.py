@@ -1,0 +1,113 @@
+"""GPU parity tests for the retrieval drop-ins (aladin_b200.evaluation / recall_auxiliary):
+Recall@K, medr, meanr, ranks, top1 and top50 identical to the reference's outputs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import alad_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _containers(g):
+    images = torch.from_numpy(np.repeat(g["images"], 5, axis=0))
+    captions = torch.from_numpy(g["captions"])
+    return images, captions, g["img_lens"].tolist(), g["cap_lens"].tolist()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_i2t_t2i_alignment_golden(precision):
+    from aladin_b200 import evaluation as E, loss as L
+    g = load_golden("retrieval")
+    images, captions, il, cl = _containers(g)
+    sim_matrix_class = L.AlignmentContrastiveLoss(aggregation="MrSw")
+    sim_matrix_class.precision = precision
+
+    def alignment_sim_fn(img, cap, img_len, cap_len):             # the closure alad/test.py:259-263 builds
+        with torch.no_grad():
+            return sim_matrix_class(img, cap, img_len, cap_len, return_loss=False, return_similarity_mat=True)
+
+    m, (ranks, top1) = E.i2t(images, captions, il, cl, return_ranks=True, sim_function=alignment_sim_fn, cap_batches=5)
+    mi, (ranks_i, top50) = E.t2i(images, captions, il, cl, return_ranks=True, sim_function=alignment_sim_fn, im_batches=5)
+    np.testing.assert_allclose(m[:3], g["m_i2t"][:3])             # Recall@1/5/10 identical
+    np.testing.assert_allclose(mi[:3], g["m_t2i"][:3])
+    if precision == "fp32":
+        np.testing.assert_allclose(m, g["m_i2t"])
+        np.testing.assert_allclose(mi, g["m_t2i"])
+        np.testing.assert_array_equal(ranks, g["ranks_i2t"])
+        np.testing.assert_array_equal(top1, g["top1"])
+        np.testing.assert_array_equal(ranks_i, g["ranks_t2i"])
+        np.testing.assert_array_equal(top50, g["top50"])
+    assert ranks.dtype == np.float64 and top50.shape == (300, 50)
+
+
+def test_i2t_t2i_global_vector_and_compute_recall_golden(capsys):
+    import aladin_b200
+    from aladin_b200 import evaluation as E, recall_auxiliary as R
+    g = load_golden("retrieval")
+    images, captions, il, cl = _containers(g)
+    aladin_b200.set_precision("fp32")
+    try:
+        m, (ranks, top1) = E.i2t(images, captions, il, cl, return_ranks=True, sim_function=None)
+        mi, (ranks_i, top50) = E.t2i(images, captions, il, cl, return_ranks=True, sim_function=None)
+        np.testing.assert_allclose(m, g["g_i2t"])
+        np.testing.assert_array_equal(top1, g["gtop1"])
+        np.testing.assert_allclose(mi, g["g_t2i"])
+        np.testing.assert_array_equal(ranks_i, g["granks_t2i"])
+        np.testing.assert_array_equal(top50, g["gtop50"])
+        rec = R.compute_recall(images[:, 0, :], captions[:, 0, :])
+        np.testing.assert_allclose(rec, g["compute_recall"])
+        assert "Recall Image to text" in capsys.readouterr().out
+    finally:
+        aladin_b200.set_precision("bf16")
+
+
+def test_arbitrary_callable_sim_function():
+    """A user callable is honoured (called per query like evaluation.py:199-210)."""
+    from aladin_b200 import evaluation as E
+    g = load_golden("retrieval")
+    images, captions, il, cl = _containers(g)
+    calls = []
+
+    def sim(img, cap, img_len, cap_len):
+        calls.append(cap.shape[0])
+        return torch.from_numpy(O.mrsw_scores(img.cpu().numpy(), cap.cpu().numpy(), img_len, cap_len))
+
+    m, (ranks, top1) = E.i2t(images, captions, il, cl, return_ranks=True, sim_function=sim, cap_batches=5)
+    np.testing.assert_array_equal(ranks, g["ranks_i2t"])
+    assert len(calls) == 60 * 5 and set(calls) == {60}
+
+
+def test_coco1k_shape_subset_vs_oracle():
+    """Dense 34x50, d=1024 tokens (BASELINE per-pair shape) at 100 images x 500 captions."""
+    from aladin_b200 import evaluation as E, loss as L, synth
+    images, captions, il, cl = synth.eval_containers(33, 100, 53, 1024, max_regions=35, max_words=53, dense=True, alpha=0.35)
+    scorer = L.AlignmentContrastiveLoss(aggregation="MrSw")
+    scorer.precision = "fp32"
+    ti, tc = torch.from_numpy(images), torch.from_numpy(captions)
+    m, (ranks, top1) = E.i2t(ti, tc, il, cl, return_ranks=True, sim_function=scorer)
+    mi, (ranks_i, top50) = E.t2i(ti, tc, il, cl, return_ranks=True, sim_function=scorer)
+    S = O.mrsw_scores(images[0::5], captions, il[0::5], cl, acc64=True)
+    ri, t1 = O.i2t_ranks(S)
+    rt, t50 = O.t2i_ranks(S)
+    np.testing.assert_array_equal(ranks, ri)
+    np.testing.assert_array_equal(ranks_i, rt)
+    np.testing.assert_allclose(m[:5], O.recall_metrics(ri))
+    np.testing.assert_allclose(mi[:5], O.recall_metrics(rt))
+    assert 5.0 < m[0] < 100.0                                       # non-degenerate recalls
+
+
+def test_pinned_host_gallery_chunked_upload_matches_device_resident():
+    from aladin_b200 import retrieval, synth
+    images, captions, il, cl = synth.eval_containers(34, 64, 71, 256, max_regions=35, max_words=40)
+    ti = torch.from_numpy(images).pin_memory()
+    tc = torch.from_numpy(captions).pin_memory()
+    a = retrieval.AlignmentGallery(ti, tc, il, cl, n_images=64, img_start=0, img_step=5, precision="bf16",
+                                   caption_chunk=50).scores()
+    b = retrieval.AlignmentGallery(ti.cuda(), tc.cuda(), il, cl, n_images=64, img_start=0, img_step=5,
+                                   precision="bf16").scores()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    ref = O.mrsw_scores(images[0::5], captions, il[0::5], cl, acc64=True)
+    assert np.abs(a.cpu().numpy() - ref).max() <= 1e-2

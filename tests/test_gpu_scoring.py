@@ -6,17 +6,13 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden
+from conftest import assert_scores_close, load_golden
 from oracle import alad_oracle as O
 
 pytestmark = pytest.mark.gpu
 
 BF16_ATOL = 1e-2
 FP32_RTOL = 1e-4
-
-
-def rel_err(a, ref, floor=1e-2):
-    return np.abs(a - ref) / np.maximum(np.abs(ref), floor)
 
 
 def test_pack_tokens_matches_normalize():
@@ -99,7 +95,7 @@ def test_alignment_scores_golden(precision):
     if precision == "bf16":
         assert np.abs(got - ref).max() <= BF16_ATOL
     else:
-        assert rel_err(got, ref).max() <= FP32_RTOL
+        assert_scores_close(got, ref, FP32_RTOL)
     assert np.all(got[2] == 0) and np.all(got[:, 1] == 0)        # empty image / empty caption
 
 
@@ -118,7 +114,7 @@ def test_alignment_scores_vs_oracle(precision, shape):
     if precision == "bf16":
         assert np.abs(got - ref).max() <= BF16_ATOL, np.abs(got - ref).max()
     else:
-        assert rel_err(got, ref).max() <= FP32_RTOL, rel_err(got, ref).max()
+        assert_scores_close(got, ref, FP32_RTOL)
 
 
 def test_alignment_scores_dense_uniform_full_width():

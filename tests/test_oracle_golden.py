@@ -125,3 +125,24 @@ def test_retrieval_loops_match_reference():
     np.testing.assert_allclose(m, g["g_t2i"])
     np.testing.assert_array_equal(ranks, g["granks_t2i"])
     np.testing.assert_allclose(O.compute_recall(images[:, 0, :], captions[:, 0, :]), g["compute_recall"])
+
+
+def test_train_step_composite_matches_reference():
+    """alad_model.py:377-405 + :445-453 restated with the oracle pieces."""
+    g = load_golden("train_step")
+    im = np.transpose(g["img_set"], (1, 0, 2))
+    s = np.transpose(g["cap_seq"], (1, 0, 2))
+    il, cl = g["img_len"].tolist(), g["cap_len"].tolist()
+    M = O.dot_scores(g["img_cls"], g["cap_cls"])
+    T = O.mrsw_scores(im, s, il, cl)
+    np.testing.assert_allclose(M, g["matching_mat"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(T, g["teacher_scores"], rtol=2e-5, atol=2e-6)
+    lm, la, ld = O.triplet_loss(M, 0.2, True), O.triplet_loss(T, 0.2, True), O.listnet_loss(T, M)
+    np.testing.assert_allclose([lm, la, ld], [g["matching_loss"], g["alignment_loss"], g["distillation_loss"]], rtol=2e-5)
+    np.testing.assert_allclose(la + ld + 0.1 * lm, g["loss"], rtol=2e-5)
+    GM = 0.1 * O.triplet_grad(M, 0.2, True) + O.listnet_grad(T, M)
+    np.testing.assert_allclose(GM @ g["cap_cls"], g["d_img_cls"], rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(GM.T @ g["img_cls"], g["d_cap_cls"], rtol=2e-4, atol=2e-6)
+    d_im, d_s = O.mrsw_backward(im, s, il, cl, O.triplet_grad(T, 0.2, True))
+    np.testing.assert_allclose(np.transpose(d_im, (1, 0, 2)), g["d_img_set"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(np.transpose(d_s, (1, 0, 2)), g["d_cap_seq"], rtol=1e-4, atol=2e-6)
