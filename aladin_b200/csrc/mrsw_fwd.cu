@@ -13,6 +13,7 @@
 //   warp 4     TMA producer (4-stage smem ring, 128B swizzle)
 //   warp 5     tcgen05.mma issuer (one lane), 2 accumulator stages in TMEM
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "sm100_ptx.cuh"
@@ -36,7 +37,6 @@ constexpr int ACC_COLS = 256;                 // column stride between accumulat
 constexpr int TMEM_COLS = 512;
 constexpr int NTILE_WORDS = sizeof(alad_ntile) / 4;   // 20
 static_assert(NTILE_WORDS <= 32, "one lane per table word");
-constexpr int N_BLOCK = 32;                   // N tiles swept per M pass (keeps B tiles hot in L2)
 
 // dynamic shared memory carve-up (offsets from a 1024-aligned base)
 constexpr int OFF_A = 0;
@@ -64,15 +64,16 @@ struct MrswParams {
   int n_ntiles;
   int num_kb;
   int epilogue;
+  int n_block;      // N tiles swept per pass over the M tiles (their region rows stay hot in L2)
 };
 
-__device__ __forceinline__ void tile_coord(int t, int n_mtiles, int n_ntiles, int& mt, int& nt) {
-  const int per_block = n_mtiles * N_BLOCK;
+__device__ __forceinline__ void tile_coord(int t, int n_mtiles, int n_ntiles, int n_block, int& mt, int& nt) {
+  const int per_block = n_mtiles * n_block;
   const int nb = t / per_block;
   const int rem = t - nb * per_block;
-  const int nb_size = min(N_BLOCK, n_ntiles - nb * N_BLOCK);
+  const int nb_size = min(n_block, n_ntiles - nb * n_block);
   mt = rem / nb_size;
-  nt = nb * N_BLOCK + (rem - mt * nb_size);
+  nt = nb * n_block + (rem - mt * nb_size);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -122,7 +123,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int mt, nt;
-        tile_coord(t, p.n_mtiles, p.n_ntiles, mt, nt);
+        tile_coord(t, p.n_mtiles, p.n_ntiles, p.n_block, mt, nt);
         const int n_row0 = __ldg(&p.ntiles[nt].row_start);
         const int m_row0 = mt * BM;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -185,7 +186,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
     int nx_cap = 0, nx_above = 0;
     auto fetch_meta = [&](int t) {
       int mt, nt;
-      tile_coord(t, p.n_mtiles, p.n_ntiles, mt, nt);
+      tile_coord(t, p.n_mtiles, p.n_ntiles, p.n_block, mt, nt);
       if (lane < NTILE_WORDS) nx_tab = __ldg(reinterpret_cast<const uint32_t*>(&p.ntiles[nt]) + lane);
       if (mrsw) {
         const long long mrow = static_cast<long long>(mt) * BM + row;
@@ -198,7 +199,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int mt, nt;
-      tile_coord(t, p.n_mtiles, p.n_ntiles, mt, nt);
+      tile_coord(t, p.n_mtiles, p.n_ntiles, p.n_block, mt, nt);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int buf = it & 1;
@@ -428,6 +429,20 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   p.n_ntiles = a->n_ntiles;
   p.num_kb = a->Kp / BK;
   p.epilogue = a->epilogue;
+  {
+    // keep one block of region tiles (n_block x 240 rows x Kp bf16) resident in the 126 MB L2 while
+    // all word tiles stream past it; ALAD_L2_BLOCK_MB overrides the budget for experiments
+    static const long long budget_mb = [] {
+      const char* e = getenv("ALAD_L2_BLOCK_MB");
+      const long long v = e ? atoll(e) : 0;
+      return v > 0 ? v : 64;
+    }();
+    const long long tile_bytes = (long long)BN * a->Kp * 2;
+    long long nb = (budget_mb << 20) / tile_bytes;
+    nb = nb < 8 ? 8 : nb;
+    p.n_block = (int)(nb > p.n_ntiles ? p.n_ntiles : nb);
+    if ((long long)p.n_mtiles * p.n_block >= (1ll << 31)) p.n_block = 8;
+  }
   const long long total = (long long)p.n_mtiles * p.n_ntiles;
   ALAD_REQUIRE(total < (1ll << 31), "alad_mrsw_scores_fwd: too many tiles (%lld)", total);
 

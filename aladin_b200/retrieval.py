@@ -118,11 +118,13 @@ class AlignmentGallery:
         return S
 
 
-def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=None, gather_i2t=True):
+def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=None, gather_i2t=True, ops=ranking):
     """Exact i2t / t2i ranks and top-k from a shard's score block S[n_loc, Nc].
 
     Returns numpy arrays shaped like the reference's (alad/evaluation.py:166-167,255-256):
-    ranks_i2t[npts], top1[npts], ranks_t2i[5*npts], topk[5*npts, k] (float64)."""
+    ranks_i2t[npts], top1[npts], ranks_t2i[5*npts], topk[5*npts, k] (float64).
+    `ops` provides rank_rows / col_gt / col_count / col_topk / topk_merge (the CUDA kernels by
+    default; the gloo CPU tests plug the oracle in to exercise the exchange protocol)."""
     import torch.distributed as dist
     n_loc, Nc = S.shape
     dist_on = group is not None and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -130,18 +132,18 @@ def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=No
     npts = min(npts, Ni_total)
     # ---------------- i2t: rows (queries = images < npts), gallery = all captions
     q_loc = max(0, min(n_loc, npts - img_off))
-    rank_i, top1_i = ranking.rank_rows(S[:q_loc], 5, img_off)
+    rank_i, top1_i = ops.rank_rows(S[:q_loc], 5, img_off)
     # ---------------- t2i: columns (queries = captions < 5*npts), gallery = all images
     ncq = min(Nc, 5 * npts)
     Sq = S[:, :ncq]
     gt = torch.zeros(ncq, dtype=torch.float32, device=S.device)
-    ranking.col_gt(Sq, gt, 5, img_off)
+    ops.col_gt(Sq, gt, 5, img_off)
     if dist_on:
         dist.all_reduce(gt, group=group)                       # every entry is owned by exactly one shard
-    count = ranking.col_count(Sq, gt, 5, img_off)
+    count = ops.col_count(Sq, gt, 5, img_off)
     k_eff = k
-    cs, ci = ranking.col_topk(Sq, k_eff, img_off)
-    ts, ti = ranking.topk_merge(cs, ci)
+    cs, ci = ops.col_topk(Sq, k_eff, img_off)
+    ts, ti = ops.topk_merge(cs, ci)
     if dist_on:
         world = dist.get_world_size(group)
         dist.all_reduce(count, group=group)
@@ -149,7 +151,7 @@ def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=No
         gi = [torch.empty_like(ti) for _ in range(world)]
         dist.all_gather(gs, ts, group=group)
         dist.all_gather(gi, ti, group=group)
-        ts, ti = ranking.topk_merge(torch.stack(gs).contiguous(), torch.stack(gi).contiguous())
+        ts, ti = ops.topk_merge(torch.stack(gs).contiguous(), torch.stack(gi).contiguous())
         if gather_i2t:
             per = (Ni_total + world - 1) // world
             pad_r = torch.full((per,), -1, dtype=torch.int32, device=S.device)

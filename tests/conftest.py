@@ -50,3 +50,26 @@ def assert_scores_close(got, ref, rtol, what=""):
     floor = 0.1 * np.abs(ref).max() if ref.size else 0.0
     err = np.abs(got - ref) / np.maximum(np.abs(ref), max(floor, 1e-30))
     assert err.max() <= rtol, f"{what}: max scaled error {err.max():.3e} > {rtol:.1e}"
+
+
+def assert_order_equal_up_to_ties(got, ref, scores, rtol, what=""):
+    """Top-k index lists must be identical except where the two candidates' reference scores
+    differ by less than the score tolerance (BASELINE.json: "top-k indices must be bit-exact
+    except for ties inside that tolerance").  got/ref: [Q,k] indices, scores: [Q,n] reference."""
+    got = np.asarray(got).astype(np.int64)
+    ref = np.asarray(ref).astype(np.int64)
+    scores = np.asarray(scores, dtype=np.float64)
+    assert got.shape == ref.shape, what
+    q, p = np.nonzero(got != ref)
+    if q.size == 0:
+        return
+    floor = 0.1 * np.abs(scores).max()
+    a, b = scores[q, got[q, p]], scores[q, ref[q, p]]
+    err = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
+    assert err.max() <= rtol, f"{what}: {q.size} order differences, worst score gap {err.max():.3e} > {rtol:.1e}"
+    for qq in np.unique(q):                      # and the sets may only differ by near-tied members
+        extra = np.setxor1d(got[qq], ref[qq])
+        if extra.size:
+            kth = scores[qq, ref[qq, -1]]
+            gap = np.abs(scores[qq, extra] - kth) / max(abs(kth), floor)
+            assert gap.max() <= rtol, f"{what}: top-k sets differ beyond ties for query {qq}"
