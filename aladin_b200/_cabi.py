@@ -26,7 +26,7 @@ class MrswFwdArgs(C.Structure):
         ("regions", C.c_void_p), ("n_region_rows", C.c_int64),
         ("Kp", C.c_int32), ("row_cap", C.c_void_p), ("ntiles", C.c_void_p), ("n_ntiles", C.c_int32),
         ("S", C.c_void_p), ("ldS", C.c_int64), ("Ni", C.c_int32), ("Nc", C.c_int32),
-        ("epilogue", C.c_int32), ("num_ctas", C.c_int32),
+        ("epilogue", C.c_int32), ("num_ctas", C.c_int32), ("cta_group", C.c_int32),
     ]
 
 

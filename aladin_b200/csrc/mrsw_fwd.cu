@@ -24,9 +24,7 @@ constexpr int BM = ALAD_TILE_M;
 constexpr int BN = ALAD_TILE_N;
 constexpr int BK = ALAD_TILE_K;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;          // 16 KiB
-constexpr int B_BYTES = BN * BK * 2;          // 30 KiB
+constexpr int A_BYTES = BM * BK * 2;          // 16 KiB: 128 word rows x 64 bf16
 constexpr int V_STRIDE = ALAD_MAX_SEG + 1;    // 33 floats: conflict-free row-major scratch
 constexpr int V_BYTES = BM * V_STRIDE * 4;
 constexpr int EPI_WARPS = 4;
@@ -38,20 +36,29 @@ constexpr int TMEM_COLS = 512;
 constexpr int NTILE_WORDS = sizeof(alad_ntile) / 4;   // 20
 static_assert(NTILE_WORDS <= 32, "one lane per table word");
 
-// dynamic shared memory carve-up (offsets from a 1024-aligned base)
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
-constexpr int OFF_V = OFF_B + STAGES * B_BYTES;
-constexpr int OFF_CAP = OFF_V + 2 * V_BYTES;                  // int capS[2][128]
-constexpr int OFF_TAB = OFF_CAP + 2 * BM * 4;                 // uint32 tab[4 warps][32]
-constexpr int OFF_RUN = OFF_TAB + EPI_WARPS * 32 * 4;         // uint32 run_start_mask[2][4]
-constexpr int OFF_BAR = OFF_RUN + 2 * EPI_WARPS * 4;          // mbarriers
-constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
-constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
-constexpr int SMEM_USED = OFF_TMEMPTR + 16;
-constexpr int SMEM_BYTES = SMEM_USED + 1024;                  // slack for manual 1024 B alignment
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
-static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "SWIZZLE_128B tiles must stay 1024 B aligned");
+// Per-variant geometry.  CG = 1: one CTA per 128 x 240 tile.  CG = 2: a CTA pair (cta_group::2)
+// per 256 x 240 tile -- each CTA stages its own 128 word rows and HALF of the region rows, which
+// cuts the shared-memory fill per SM from 46 KB to 31 KB per K block and leaves room for 6 stages.
+template <int CG>
+struct Cfg {
+  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int B_ROWS = BN / CG;                       // region rows staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
+  static constexpr int OFF_V = OFF_B + STAGES * B_BYTES;
+  static constexpr int OFF_CAP = OFF_V + 2 * V_BYTES;          // int capS[2][128]
+  static constexpr int OFF_TAB = OFF_CAP + 2 * BM * 4;         // uint32 tab[4 warps][32]
+  static constexpr int OFF_RUN = OFF_TAB + EPI_WARPS * 32 * 4; // uint32 run_start_mask[2][4]
+  static constexpr int OFF_BAR = OFF_RUN + 2 * EPI_WARPS * 4;  // mbarriers
+  static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
+  static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
+  static constexpr int SMEM_USED = OFF_TMEMPTR + 16;
+  static constexpr int SMEM_BYTES = SMEM_USED + 1024;          // slack for manual 1024 B alignment
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "SWIZZLE_128B tiles must stay 1024 B aligned");
+};
 
 struct MrswParams {
   const int32_t* row_cap;
@@ -76,23 +83,31 @@ __device__ __forceinline__ void tile_coord(int t, int n_mtiles, int n_ntiles, in
   nt = nb * n_block + (rem - mt * nb_size);
 }
 
+template <int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_regions,
                 const MrswParams p) {
+  using C = Cfg<CG>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // manual 1024 B alignment by OFFSET (keeps the pointer in the shared address space -> LDS/STS)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_TMEMPTR);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEMPTR);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.n_mtiles * p.n_ntiles;
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;   // rank inside the CTA pair
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG;                  // work unit: a CTA (CG=1) or a CTA pair (CG=2)
+  const int n_units = gridDim.x / CG;
+  const int n_munits = (p.n_mtiles + CG - 1) / CG;   // M tiles are consumed CG at a time
+  const int total_tiles = n_munits * p.n_ntiles;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_words);
@@ -103,34 +118,48 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_THREADS);
+      mbar_init(&tempty_bar[a], EPI_THREADS * CG);   // the leader's copy collects both CTAs' epilogues
     }
     fence_mbar_init();
   }
   if (warp == 5) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(tmem_ptr_smem, TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 4) {
-    // ============================== TMA producer ==============================
+    // ============================== TMA producer (every CTA stages its own operands) ==========
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int mt, nt;
-        tile_coord(t, p.n_mtiles, p.n_ntiles, p.n_block, mt, nt);
-        const int n_row0 = __ldg(&p.ntiles[nt].row_start);
-        const int m_row0 = mt * BM;
+      for (int t = unit; t < total_tiles; t += n_units) {
+        int mu, nt;
+        tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt);
+        const int n_row0 = __ldg(&p.ntiles[nt].row_start) + cta_rank * C::B_ROWS;
+        const int m_row0 = (mu * CG + cta_rank) * BM;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-          tma_load_2d(smem + OFF_A + stage * A_BYTES, &map_words, &full_bar[stage], kb * BK, m_row0);
-          tma_load_2d(smem + OFF_B + stage * B_BYTES, &map_regions, &full_bar[stage], kb * BK, n_row0);
+          uint8_t* sa = smem + C::OFF_A + stage * A_BYTES;
+          uint8_t* sb = smem + C::OFF_B + stage * C::B_BYTES;
+          if (CG == 2) {
+            // completion bytes of BOTH CTAs are credited to the leader's barrier
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            tma_load_2d_cg2(sa, &map_words, &full_bar[stage], kb * BK, m_row0);
+            tma_load_2d_cg2(sb, &map_regions, &full_bar[stage], kb * BK, n_row0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_2d(sa, &map_words, &full_bar[stage], kb * BK, m_row0);
+            tma_load_2d(sb, &map_regions, &full_bar[stage], kb * BK, n_row0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -140,13 +169,13 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 5) {
-    // ============================== MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+    // ============================== MMA issuer (leader CTA only) ==============================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = unit; t < total_tiles; t += n_units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -155,38 +184,42 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem + OFF_A + stage * A_BYTES));
-          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem + OFF_B + stage * B_BYTES));
+          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem + C::OFF_A + stage * A_BYTES));
+          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem + C::OFF_B + stage * C::B_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // +32 B per K step inside the 128 B swizzle row: start-address field is in 16 B units
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_bf16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else         umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 2) umma_commit_cg2_both(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CG == 2) umma_commit_cg2_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
       }
     }
     __syncwarp();
   } else {
     // ============================== epilogue (warps 0-3) ======================
     const int row = warp * 32 + lane;                       // TMEM lane == row of the M tile
-    float* V = reinterpret_cast<float*>(smem + OFF_V);
-    int* capS = reinterpret_cast<int*>(smem + OFF_CAP);
-    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + OFF_TAB) + warp * 32;
-    uint32_t* runS = reinterpret_cast<uint32_t*>(smem + OFF_RUN);
+    float* V = reinterpret_cast<float*>(smem + C::OFF_V);
+    int* capS = reinterpret_cast<int*>(smem + C::OFF_CAP);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + C::OFF_TAB) + warp * 32;
+    uint32_t* runS = reinterpret_cast<uint32_t*>(smem + C::OFF_RUN);
     const bool mrsw = p.epilogue == 0;
 
     // metadata of a tile: N-tile record word (lanes 0..11), caption of my row and of the row above
     uint32_t nx_tab = 0;
     int nx_cap = 0, nx_above = 0;
     auto fetch_meta = [&](int t) {
-      int mt, nt;
-      tile_coord(t, p.n_mtiles, p.n_ntiles, p.n_block, mt, nt);
+      int mu, nt;
+      tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt);
+      const int mt = mu * CG + cta_rank;
       if (lane < NTILE_WORDS) nx_tab = __ldg(reinterpret_cast<const uint32_t*>(&p.ntiles[nt]) + lane);
       if (mrsw) {
         const long long mrow = static_cast<long long>(mt) * BM + row;
@@ -194,12 +227,13 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
         nx_above = (row > 0 && lane == 0) ? __ldg(&p.row_cap[mrow - 1]) : 0;
       }
     };
-    if (blockIdx.x < total_tiles) fetch_meta(blockIdx.x);
+    if (unit < total_tiles) fetch_meta(unit);
 
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      int mt, nt;
-      tile_coord(t, p.n_mtiles, p.n_ntiles, p.n_block, mt, nt);
+    for (int t = unit; t < total_tiles; t += n_units, ++it) {
+      int mu, nt;
+      tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt);
+      const int mt = mu * CG + cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int buf = it & 1;
@@ -222,7 +256,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
       const uint32_t clamp = tab[3];
       const uint32_t mydesc = (tab[4 + (lane >> 1)] >> ((lane & 1) * 16)) & 0xffffu;  // descriptor of image `lane`
       // prefetch the next tile's metadata while this one is processed
-      if (t + static_cast<int>(gridDim.x) < total_tiles) fetch_meta(t + gridDim.x);
+      if (t + n_units < total_tiles) fetch_meta(t + n_units);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -284,7 +318,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
         }
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&tempty_bar[acc]);                     // accumulator stage may be overwritten
+        if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);   // stage may be overwritten
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         // ---- phase 2: per-caption row sums in a fixed order; warp w owns caption runs w, w+4, ...
         const int* caps = capS + buf * BM;
@@ -345,16 +379,16 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
           }
         }
         tc_fence_before();
-        mbar_arrive(&tempty_bar[acc]);
+        if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // the pair stays alive until both CTAs are done
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -435,7 +469,7 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
     static const long long budget_mb = [] {
       const char* e = getenv("ALAD_L2_BLOCK_MB");
       const long long v = e ? atoll(e) : 0;
-      return v > 0 ? v : 64;
+      return v > 0 ? v : 30;
     }();
     const long long tile_bytes = (long long)BN * a->Kp * 2;
     long long nb = (budget_mb << 20) / tile_bytes;
@@ -446,16 +480,50 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   const long long total = (long long)p.n_mtiles * p.n_ntiles;
   ALAD_REQUIRE(total < (1ll << 31), "alad_mrsw_scores_fwd: too many tiles (%lld)", total);
 
+  int cg = a->cta_group;
+  if (cg == 0) {
+    static const int env_cg = [] {
+      const char* e = getenv("ALAD_CTA_GROUP");
+      const int v = e ? atoi(e) : 0;
+      return (v == 1 || v == 2) ? v : 2;
+    }();
+    cg = env_cg;
+  }
+  ALAD_REQUIRE(cg == 1 || cg == 2, "alad_mrsw_scores_fwd: cta_group must be 0, 1 or 2");
+  if (sm_count() < 2) cg = 1;
+
   CUtensorMap map_w, map_r;
   int rc = make_map(&map_w, a->words, a->n_word_rows, a->Kp, BM);
   if (rc) return rc;
-  rc = make_map(&map_r, a->regions, a->n_region_rows, a->Kp, BN);
+  rc = make_map(&map_r, a->regions, a->n_region_rows, a->Kp, BN / cg);
   if (rc) return rc;
 
-  ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const long long units = (long long)((p.n_mtiles + cg - 1) / cg) * p.n_ntiles;
   int ctas = a->num_ctas > 0 ? a->num_ctas : sm_count();
-  if (ctas > total) ctas = (int)total;
-  mrsw_fwd_kernel<<<ctas, THREADS, SMEM_BYTES, st>>>(map_w, map_r, p);
+  if ((long long)ctas > units * cg) ctas = (int)(units * cg);
+  ctas = (ctas / cg) * cg;
+  if (ctas < cg) ctas = cg;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cg == 2) {
+    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+    cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+    ALAD_CUDA(cudaLaunchKernelEx(&cfg, mrsw_fwd_kernel<2>, map_w, map_r, p));
+  } else {
+    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+    cfg.dynamicSmemBytes = Cfg<1>::SMEM_BYTES;
+    ALAD_CUDA(cudaLaunchKernelEx(&cfg, mrsw_fwd_kernel<1>, map_w, map_r, p));
+  }
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;
 }

@@ -74,7 +74,7 @@ def pack_tokens(x, counts, *, slot0, mode=0, normalize=True, eps=1e-12, want_row
     data = torch.empty((max(n_rows, 1), Kp), dtype=torch.bfloat16, device=x.device)
     row_item = None
     if want_row_item:
-        row_item = torch.full((max(padded_rows(n_rows), _cabi.TILE_M),), -1, dtype=torch.int32, device=x.device)
+        row_item = torch.full((max(padded_rows(n_rows), 2 * _cabi.TILE_M),), -1, dtype=torch.int32, device=x.device)
     if n_rows:
         cnt_d = _to_dev(counts, x.device)
         off_d = _to_dev(row_off, x.device)
@@ -86,7 +86,7 @@ def pack_tokens(x, counts, *, slot0, mode=0, normalize=True, eps=1e-12, want_row
     return Packed(data, n_rows, Kp, counts, row_off, row_item, mode)
 
 
-def mrsw_scores_packed(words, regions, tiles_dev, n_tiles, Ni, Nc, out=None, num_ctas=0):
+def mrsw_scores_packed(words, regions, tiles_dev, n_tiles, Ni, Nc, out=None, num_ctas=0, cta_group=0):
     """S[Ni,Nc] from packed operands (see alad_mrsw_scores_fwd)."""
     lib = _cabi.lib()
     assert words.Kp == regions.Kp
@@ -98,7 +98,8 @@ def mrsw_scores_packed(words, regions, tiles_dev, n_tiles, Ni, Nc, out=None, num
         words=words.data.data_ptr(), n_word_rows=words.n_rows, regions=regions.data.data_ptr(),
         n_region_rows=regions.n_rows, Kp=words.Kp, row_cap=words.row_item.data_ptr(),
         ntiles=tiles_dev.data_ptr() if n_tiles else None, n_ntiles=n_tiles, S=out.data_ptr(),
-        ldS=out.stride(0) if Ni > 1 else max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=0, num_ctas=num_ctas)
+        ldS=out.stride(0) if Ni > 1 else max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=0, num_ctas=num_ctas,
+        cta_group=cta_group)
     if kernel_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -161,6 +162,6 @@ def dot_scores(im, s, precision=None, normalize=False, eps=0.0, out=None):
     a = _cabi.MrswFwdArgs(
         words=words.data.data_ptr(), n_word_rows=Nc, regions=regions.data.data_ptr(), n_region_rows=Ni,
         Kp=words.Kp, row_cap=None, ntiles=tiles_dev.data_ptr(), n_ntiles=len(table), S=out.data_ptr(),
-        ldS=max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=1, num_ctas=0)
+        ldS=max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=1, num_ctas=0, cta_group=0)
     _cabi.check(lib.alad_mrsw_scores_fwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_fwd")
     return out

@@ -89,7 +89,8 @@ def gemm_tiles(n_rows):
 
 
 def padded_rows(n_rows):
-    return ((n_rows + TILE_M - 1) // TILE_M) * TILE_M
+    """row_cap length: word rows rounded up to a CTA pair's 2 x TILE_M rows."""
+    return ((n_rows + 2 * TILE_M - 1) // (2 * TILE_M)) * (2 * TILE_M)
 
 
 def round_up(x, m):

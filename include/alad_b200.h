@@ -99,7 +99,7 @@ typedef struct alad_mrsw_fwd_args {
   const void* regions;           /* [n_region_rows, Kp] bf16 packed (mode 0 or 2)            */
   int64_t n_region_rows;
   int32_t Kp;
-  const int32_t* row_cap;        /* [ceil(n_word_rows/128)*128] caption of each row, -1 pad  */
+  const int32_t* row_cap;        /* [ceil(n_word_rows/256)*256] caption of each row, -1 pad  */
   const alad_ntile* ntiles;
   int32_t n_ntiles;
   float* S;                      /* [Ni, ldS] fp32                                           */
@@ -107,6 +107,8 @@ typedef struct alad_mrsw_fwd_args {
   int32_t Ni, Nc;
   int32_t epilogue;              /* 0 = MrSw pooling; 1 = plain GEMM: S[n, m] = <region n, word m> */
   int32_t num_ctas;              /* 0 = one persistent CTA per SM                            */
+  int32_t cta_group;             /* 0 = default (2, or $ALAD_CTA_GROUP); 1 = one CTA per 128x240 tile;
+                                    2 = CTA pair (tcgen05 cta_group::2) per 256x240 tile       */
 } alad_mrsw_fwd_args;
 int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream);
 

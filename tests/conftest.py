@@ -73,3 +73,15 @@ def assert_order_equal_up_to_ties(got, ref, scores, rtol, what=""):
             kth = scores[qq, ref[qq, -1]]
             gap = np.abs(scores[qq, extra] - kth) / max(abs(kth), floor)
             assert gap.max() <= rtol, f"{what}: top-k sets differ beyond ties for query {qq}"
+
+
+def assert_ranks_equal_up_to_ties(got, ref, scores, gt_idx, rtol, what=""):
+    """Ranks must be identical except where competitors sit within the score tolerance of the
+    ground truth: |got - ref| may not exceed the number of such near-tied competitors."""
+    got, ref = np.asarray(got, dtype=np.int64), np.asarray(ref, dtype=np.int64)
+    scores = np.asarray(scores, dtype=np.float64)
+    floor = 0.1 * np.abs(scores).max()
+    for q in np.nonzero(got != ref)[0]:
+        g = scores[q, gt_idx[q]]
+        near = np.count_nonzero(np.abs(scores[q] - g) <= rtol * max(abs(g), floor)) - 1
+        assert abs(got[q] - ref[q]) <= near, f"{what}: rank of query {q} is {got[q]}, reference {ref[q]}, {near} near ties"
