@@ -27,6 +27,7 @@ class MrswFwdArgs(C.Structure):
         ("Kp", C.c_int32), ("row_cap", C.c_void_p), ("ntiles", C.c_void_p), ("n_ntiles", C.c_int32),
         ("S", C.c_void_p), ("ldS", C.c_int64), ("Ni", C.c_int32), ("Nc", C.c_int32),
         ("epilogue", C.c_int32), ("num_ctas", C.c_int32), ("cta_group", C.c_int32),
+        ("transpose_out", C.c_int32),
     ]
 
 
@@ -37,7 +38,8 @@ class MrswBwdArgs(C.Structure):
         ("Bi", C.c_int32), ("S_im", C.c_int32), ("Bc", C.c_int32), ("S_s", C.c_int32), ("d", C.c_int32),
         ("nr", C.c_void_p), ("nw", C.c_void_p),
         ("G0", C.c_void_p), ("ldG0", C.c_int64), ("g0_scale", C.c_void_p), ("G1", C.c_void_p), ("ldG1", C.c_int64),
-        ("d_im", C.c_void_p), ("d_s", C.c_void_p), ("eps", C.c_float), ("max_pairs", C.c_int64),
+        ("d_im", C.c_void_p), ("d_s", C.c_void_p), ("eps", C.c_float), ("region_extent", C.c_int32),
+        ("max_pairs", C.c_int64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
@@ -50,6 +52,8 @@ PROTOTYPES = {
     "alad_h2d_2d": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P]),
     "alad_pack_tokens": (C.c_int, [C.POINTER(PackArgs), _P]),
     "alad_mrsw_scores_fwd": (C.c_int, [C.POINTER(MrswFwdArgs), _P]),
+    "alad_pool_tokens": (C.c_int, [_P, _I64, _I64, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P]),
+    "alad_scale_scores": (C.c_int, [_P, _I64, _I32, _I32, _P, C.c_float, _P]),
     "alad_mrsw_bwd_workspace_bytes": (C.c_int64, [_I32, _I32, _I32, _I32, _I64]),
     "alad_mrsw_scores_bwd": (C.c_int, [C.POINTER(MrswBwdArgs), _P]),
     "alad_loss_workspace_bytes": (C.c_int64, [_I32]),
@@ -88,7 +92,7 @@ def lib():
 
 # kernels launched per successful entry-point call (bench.py reports the total as gpu_launches)
 KERNELS_PER_CALL = {
-    "alad_h2d_2d": 0, "alad_pack_tokens": 1, "alad_mrsw_scores_fwd": 1, "alad_mrsw_scores_bwd": 6,
+    "alad_h2d_2d": 0, "alad_pack_tokens": 1, "alad_pool_tokens": 1, "alad_scale_scores": 1, "alad_mrsw_scores_fwd": 1, "alad_mrsw_scores_bwd": 6,
     "alad_triplet_fwd_bwd": 2, "alad_listnet_fwd_bwd": 2, "alad_rank_rows": 1, "alad_col_gt": 1,
     "alad_col_count": 1, "alad_col_topk": 1, "alad_topk_merge": 1,
 }

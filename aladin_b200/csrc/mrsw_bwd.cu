@@ -161,12 +161,12 @@ extern "C" int alad_mrsw_scores_bwd(const alad_mrsw_bwd_args* a, void* stream) {
   const size_t n_im = (size_t)a->Bi * a->S_im, n_s = (size_t)a->Bc * a->S_s;
   if (n_im) ALAD_CUDA(cudaMemsetAsync(a->d_im, 0, n_im * a->d * sizeof(float), st));
   if (n_s) ALAD_CUDA(cudaMemsetAsync(a->d_s, 0, n_s * a->d * sizeof(float), st));
-  if (a->Bi == 0 || a->Bc == 0 || a->S_im < 2 || a->S_s < 4 || (!a->G0 && !a->G1)) return ALAD_OK;
+  if (a->Bi == 0 || a->Bc == 0 || a->S_im < 2 || a->S_s < 2 || (!a->G0 && !a->G1)) return ALAD_OK;
   ALAD_REQUIRE(a->im && a->s && a->nr && a->nw, "alad_mrsw_scores_bwd: NULL input");
   BwdParams p;
   p.im = a->im; p.im_sb = a->im_stride_b; p.im_ss = a->im_stride_s;
   p.s = a->s; p.s_sb = a->s_stride_b; p.s_ss = a->s_stride_s;
-  p.Bi = a->Bi; p.S_im = a->S_im; p.Bc = a->Bc; p.S_s = a->S_s; p.d = a->d; p.R = a->S_im - 1;
+  p.Bi = a->Bi; p.S_im = a->S_im; p.Bc = a->Bc; p.S_s = a->S_s; p.d = a->d; p.R = a->region_extent > 0 ? a->region_extent : a->S_im - 1;
   p.nr = a->nr; p.nw = a->nw;
   p.G0 = a->G0; p.ldG0 = a->ldG0; p.g0_scale = a->g0_scale; p.G1 = a->G1; p.ldG1 = a->ldG1;
   p.d_im = a->d_im; p.d_s = a->d_s;

@@ -64,7 +64,8 @@ struct MrswParams {
   const int32_t* row_cap;
   const alad_ntile* ntiles;
   float* S;
-  long long ldS;
+  long long ld_seg;   // address = S + seg_item * ld_seg + row_item * ld_row  (image-major: ldS, 1; transposed: 1, ldS)
+  long long ld_row;
   long long n_word_rows;
   long long n_region_rows;
   int n_mtiles;
@@ -325,7 +326,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
         const float* Vcol = V + buf * (BM * V_STRIDE) + lane;
         const bool active = lane < nseg;
         const float floor_v = ((clamp >> lane) & 1u) ? 0.f : -INFINITY;   // masked slots take part in the max as 0
-        float* Sout = p.S + static_cast<long long>(img0 + lane) * p.ldS;
+        float* Sout = p.S + static_cast<long long>(img0 + lane) * p.ld_seg;
         unsigned long long lo = runS[buf * EPI_WARPS + 0] | (static_cast<unsigned long long>(runS[buf * EPI_WARPS + 1]) << 32);
         unsigned long long hi = runS[buf * EPI_WARPS + 2] | (static_cast<unsigned long long>(runS[buf * EPI_WARPS + 3]) << 32);
         auto pop_start = [&]() -> int {                    // next run start (128 when exhausted)
@@ -357,7 +358,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
                 s3 += fmaxf(Vcol[(r + 3) * V_STRIDE], floor_v);
               }
               for (; r < end; ++r) s0 += fmaxf(Vcol[r * V_STRIDE], floor_v);
-              atomicAdd(Sout + cap, (s0 + s1) + (s2 + s3));
+              atomicAdd(Sout + cap * p.ld_row, (s0 + s1) + (s2 + s3));
             }
           }
           start = end;
@@ -375,7 +376,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             const int col = chunk * 32 + c;
-            if (row_ok && col < ncols) p.S[static_cast<long long>(n_row0 + col) * p.ldS + mrow] = __uint_as_float(v[c]);
+            if (row_ok && col < ncols) p.S[static_cast<long long>(n_row0 + col) * p.ld_seg + mrow * p.ld_row] = __uint_as_float(v[c]);
           }
         }
         tc_fence_before();
@@ -431,7 +432,10 @@ static int make_map(CUtensorMap* m, const void* ptr, long long rows, int Kp, int
 extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   using namespace alad;
   ALAD_REQUIRE(a != nullptr, "alad_mrsw_scores_fwd: NULL args");
-  ALAD_REQUIRE(a->S != nullptr && a->Ni >= 0 && a->Nc >= 0 && a->ldS >= a->Nc, "alad_mrsw_scores_fwd: bad output");
+  // S is [Ni, ldS] with Ni = #segment items (images) and Nc = #row items (captions), or its
+  // transpose [Nc, ldS] when transpose_out is set; it is zeroed here
+  const int out_rows = a->transpose_out ? a->Nc : a->Ni, out_cols = a->transpose_out ? a->Ni : a->Nc;
+  ALAD_REQUIRE(a->S != nullptr && a->Ni >= 0 && a->Nc >= 0 && a->ldS >= out_cols, "alad_mrsw_scores_fwd: bad output");
   ALAD_REQUIRE(a->Kp > 0 && a->Kp % BK == 0, "alad_mrsw_scores_fwd: Kp=%d must be a positive multiple of %d", a->Kp, BK);
   ALAD_REQUIRE(a->n_word_rows >= 0 && a->n_region_rows >= 0 && a->n_word_rows < (1ll << 31) &&
                    a->n_region_rows < (1ll << 31),
@@ -439,11 +443,11 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   ALAD_REQUIRE(a->epilogue == 0 || a->epilogue == 1, "alad_mrsw_scores_fwd: unknown epilogue %d", a->epilogue);
   cudaStream_t st = as_stream(stream);
   if (a->Ni > 0 && a->Nc > 0) {
-    if (a->ldS == a->Nc) {
-      ALAD_CUDA(cudaMemsetAsync(a->S, 0, sizeof(float) * (size_t)a->Ni * (size_t)a->Nc, st));
+    if (a->ldS == out_cols) {
+      ALAD_CUDA(cudaMemsetAsync(a->S, 0, sizeof(float) * (size_t)out_rows * (size_t)out_cols, st));
     } else {
-      ALAD_CUDA(cudaMemset2DAsync(a->S, sizeof(float) * (size_t)a->ldS, 0, sizeof(float) * (size_t)a->Nc,
-                                  (size_t)a->Ni, st));
+      ALAD_CUDA(cudaMemset2DAsync(a->S, sizeof(float) * (size_t)a->ldS, 0, sizeof(float) * (size_t)out_cols,
+                                  (size_t)out_rows, st));
     }
   }
   if (a->n_word_rows == 0 || a->n_region_rows == 0 || a->n_ntiles == 0 || a->Ni == 0 || a->Nc == 0) return ALAD_OK;
@@ -456,7 +460,8 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   p.row_cap = a->row_cap;
   p.ntiles = a->ntiles;
   p.S = a->S;
-  p.ldS = a->ldS;
+  p.ld_seg = a->transpose_out ? 1 : a->ldS;
+  p.ld_row = a->transpose_out ? a->ldS : 1;
   p.n_word_rows = a->n_word_rows;
   p.n_region_rows = a->n_region_rows;
   p.n_mtiles = (int)((a->n_word_rows + BM - 1) / BM);

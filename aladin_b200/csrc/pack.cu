@@ -94,7 +94,71 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_tokens_kernel(const alad
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// pooled tokens: out[b, :] = sum of the normalised valid tokens of item b (fp32)
+constexpr int POOL_MAX_TOKENS = 256;
+
+__global__ void __launch_bounds__(PACK_WARPS * 32)
+pool_tokens_kernel(const float* __restrict__ src, long long sb, long long ss, int S, int d, int slot0,
+                   const int* __restrict__ count, float eps, float* __restrict__ out) {
+  __shared__ float inv[POOL_MAX_TOKENS];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cnt = min(count[b], POOL_MAX_TOKENS);
+  const float* base = src + (long long)b * sb + (long long)slot0 * ss;
+  for (int t = warp; t < cnt; t += PACK_WARPS) {
+    const float* x = base + (long long)t * ss;
+    float acc = 0.f;
+    for (int e = lane; e < d; e += 32) {
+      const float v = __ldg(x + e);
+      acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) inv[t] = fmaxf(sqrtf(acc), eps);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < d; e += PACK_WARPS * 32) {
+    float acc = 0.f;
+    for (int t = 0; t < cnt; ++t) acc += __ldg(base + (long long)t * ss + e) / inv[t];
+    out[(long long)b * d + e] = acc;
+  }
+}
+
+__global__ void scale_scores_kernel(float* __restrict__ S, long long ld, int Ni, int Nc, const float* __restrict__ col_div,
+                                    float mul) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= Nc) return;
+  float v = S[(long long)i * ld + j] * mul;
+  if (col_div) v = v / col_div[j];
+  S[(long long)i * ld + j] = v;
+}
+
 }  // namespace alad
+
+extern "C" int alad_pool_tokens(const float* src, int64_t stride_b, int64_t stride_s, int32_t B, int32_t S, int32_t d,
+                                int32_t slot0, const int32_t* count, float eps, float* out, void* stream) {
+  using namespace alad;
+  ALAD_REQUIRE(B >= 0 && S >= 0 && d > 0 && slot0 >= 0, "alad_pool_tokens: bad shape");
+  ALAD_REQUIRE(S - slot0 <= POOL_MAX_TOKENS, "alad_pool_tokens: at most %d scored slots per item", POOL_MAX_TOKENS);
+  if (B == 0) return ALAD_OK;
+  ALAD_REQUIRE(src && count && out, "alad_pool_tokens: NULL pointer");
+  pool_tokens_kernel<<<B, PACK_WARPS * 32, 0, as_stream(stream)>>>(src, stride_b, stride_s, S, d, slot0, count, eps, out);
+  ALAD_CUDA(cudaGetLastError());
+  return ALAD_OK;
+}
+
+extern "C" int alad_scale_scores(float* S, int64_t ldS, int32_t Ni, int32_t Nc, const float* col_div, float mul,
+                                 void* stream) {
+  using namespace alad;
+  ALAD_REQUIRE(Ni >= 0 && Nc >= 0 && ldS >= Nc && Ni <= 65535, "alad_scale_scores: bad shape");
+  if (Ni == 0 || Nc == 0) return ALAD_OK;
+  ALAD_REQUIRE(S, "alad_scale_scores: NULL pointer");
+  dim3 grid((Nc + 255) / 256, Ni);
+  scale_scores_kernel<<<grid, 256, 0, as_stream(stream)>>>(S, ldS, Ni, Nc, col_div, mul);
+  ALAD_CUDA(cudaGetLastError());
+  return ALAD_OK;
+}
 
 extern "C" int alad_pack_tokens(const alad_pack_args* a, void* stream) {
   using namespace alad;

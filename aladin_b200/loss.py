@@ -62,7 +62,7 @@ def listnet_fwd_bwd(teacher, student, temperature=6.0, eps=1e-10, want_grad=True
     return loss, dM
 
 
-def mrsw_backward(im_set, s_seq, nr, nw, G0=None, g0_scale=None, G1=None, eps=1e-12):
+def mrsw_backward(im_set, s_seq, nr, nw, G0=None, g0_scale=None, G1=None, eps=1e-12, region_extent=0):
     """(d im_set, d s_seq) for dL/dS = g0_scale*G0 + G1 (alad_mrsw_scores_bwd)."""
     lib = _cabi.lib()
     Bi, S_im, d = im_set.shape
@@ -87,7 +87,7 @@ def mrsw_backward(im_set, s_seq, nr, nw, G0=None, g0_scale=None, G1=None, eps=1e
         Bi=Bi, S_im=S_im, Bc=Bc, S_s=S_s, d=d, nr=nr_d.data_ptr(), nw=nw_d.data_ptr(),
         G0=ptr(G0), ldG0=max(G0.stride(0), Bc) if G0 is not None else 0, g0_scale=ptr(g0_scale),
         G1=ptr(G1), ldG1=max(G1.stride(0), Bc) if G1 is not None else 0,
-        d_im=d_im.data_ptr(), d_s=d_s.data_ptr(), eps=eps, max_pairs=max_pairs,
+        d_im=d_im.data_ptr(), d_s=d_s.data_ptr(), eps=eps, region_extent=region_extent, max_pairs=max_pairs,
         workspace=ws.data_ptr(), workspace_bytes=nbytes)
     _cabi.check(lib.alad_mrsw_scores_bwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_bwd")
     return d_im, d_s
@@ -150,19 +150,19 @@ class _AlignmentFn(torch.autograd.Function):
     """(loss, S) = alignment scores + hinge; backward recomputes only the pairs whose dL/dS != 0."""
 
     @staticmethod
-    def forward(ctx, im_set, s_seq, im_len, s_len, margin, max_violation, want_loss, precision):
+    def forward(ctx, im_set, s_seq, im_len, s_len, margin, max_violation, want_loss, precision, aggregation):
         ctx.set_materialize_grads(False)
         im_c = scoring._require_cuda(im_set.detach(), "im_set")
         s_c = scoring._require_cuda(s_seq.detach(), "s_seq")
-        S = scoring.alignment_scores(im_c, s_c, im_len, s_len, precision=precision)
-        _, _, nr, nw, _ = scoring.scored_counts(im_c.shape, s_c.shape, im_len, s_len)
+        S = scoring.alignment_scores(im_c, s_c, im_len, s_len, precision=precision, aggregation=aggregation)
+        _, W, nr, nw, _ = scoring.scored_counts(im_c.shape, s_c.shape, im_len, s_len)
         needs_grad = im_set.requires_grad or s_seq.requires_grad
         G0 = None
         if want_loss:
             loss, G0, _, _ = triplet_fwd_bwd(S, margin, max_violation, want_grad=needs_grad)
         else:
             loss = torch.zeros((), dtype=torch.float32, device=S.device)
-        ctx.nr, ctx.nw = nr, nw
+        ctx.nr, ctx.nw, ctx.W, ctx.aggregation = nr, nw, W, aggregation
         ctx.devices = (im_set.device, s_seq.device)
         ctx.save_for_backward(im_c, s_c, G0)
         return loss, S
@@ -171,13 +171,32 @@ class _AlignmentFn(torch.autograd.Function):
     def backward(ctx, g_loss, g_S):
         im_c, s_c, G0 = ctx.saved_tensors
         use_G0 = G0 is not None and g_loss is not None
+        none = (None,) * 9
         if not use_G0 and g_S is None:
-            return (None,) * 8
-        g_scale = g_loss.detach().float().reshape(1).contiguous() if use_G0 else None
-        G1 = g_S.detach().float().contiguous() if g_S is not None else None
-        d_im, d_s = mrsw_backward(im_c, s_c, ctx.nr, ctx.nw, G0=G0 if use_G0 else None, g0_scale=g_scale, G1=G1)
+            return none
+        agg = ctx.aggregation
+        if agg in ("sum", "mean"):
+            raise NotImplementedError(f"gradient of aggregation {agg!r} is not ported (no shipped config trains with it)")
+        if agg == "MrSw":
+            g_scale = g_loss.detach().float().reshape(1).contiguous() if use_G0 else None
+            G1 = g_S.detach().float().contiguous() if g_S is not None else None
+            d_im, d_s = mrsw_backward(im_c, s_c, ctx.nr, ctx.nw, G0=G0 if use_G0 else None, g0_scale=g_scale, G1=G1)
+        else:
+            G = G0 * g_loss.detach().float() if use_G0 else None
+            if g_S is not None:
+                G = g_S.detach().float() if G is None else G + g_S.detach().float()
+            d_im = d_s = None
+            if agg in ("MrAVGw", "symm"):
+                Gm = G / scoring._to_dev(ctx.nw.astype(np.float32), G.device)[None, :] if agg == "MrAVGw" else G
+                Gm = torch.nan_to_num(Gm, nan=0.0, posinf=0.0, neginf=0.0) if agg == "MrAVGw" else Gm
+                d_im, d_s = mrsw_backward(im_c, s_c, ctx.nr, ctx.nw, G1=Gm.contiguous())
+            if agg in ("MwSr", "symm"):
+                # roles swapped: max over words (clamped when nw < W), sum over regions
+                d_s2, d_im2 = mrsw_backward(s_c, im_c, ctx.nw, ctx.nr, G1=G.t().contiguous(), region_extent=max(ctx.W, 1))
+                d_im = d_im2 if d_im is None else d_im + d_im2
+                d_s = d_s2 if d_s is None else d_s + d_s2
         return (d_im.to(ctx.devices[0]) if ctx.needs_input_grad[0] else None,
-                d_s.to(ctx.devices[1]) if ctx.needs_input_grad[1] else None, None, None, None, None, None, None)
+                d_s.to(ctx.devices[1]) if ctx.needs_input_grad[1] else None) + none[2:]
 
 
 # --------------------------------------------------------------------------------------
@@ -218,9 +237,10 @@ class Contrastive(nn.Module):
 
 
 class AlignmentContrastiveLoss(Contrastive):
-    """alad/loss.py:70-159.  aggregation 'MrSw' (every shipped config) runs the fused kernel."""
+    """alad/loss.py:70-159.  'MrSw' (every shipped config), 'MrAVGw', 'MwSr', 'symm' run the fused
+    tcgen05 kernel; 'sum' / 'mean' collapse to one GEMM of pooled token sums (forward only)."""
 
-    SUPPORTED = ("MrSw",)
+    SUPPORTED = scoring.AGGREGATIONS
 
     def __init__(self, margin=0, measure=False, max_violation=False, aggregation='sum-max-sentences'):
         super().__init__(margin, measure, max_violation)
@@ -230,11 +250,11 @@ class AlignmentContrastiveLoss(Contrastive):
     def forward(self, im_set, s_seq, im_len, s_len, return_loss=True, return_similarity_mat=False):
         if self.aggregation not in self.SUPPORTED:
             raise NotImplementedError(
-                f"aggregation {self.aggregation!r} is not ported yet (SURVEY §8(f) rank 1); 'MrSw' is what "
-                "configs/*.yaml select")
+                f"aggregation {self.aggregation!r} is not ported ('scan-sentences' is a different algorithm, "
+                "alad/loss.py:136-149); supported: " + ", ".join(self.SUPPORTED))
         out_dev = im_set.device
         loss, S = _AlignmentFn.apply(im_set, s_seq, list(im_len), list(s_len), self.margin, self.max_violation,
-                                     bool(return_loss), self.precision)
+                                     bool(return_loss), self.precision, self.aggregation)
         if out_dev.type != "cuda":
             loss, S = loss.to(out_dev), S.to(out_dev)
         if return_loss and return_similarity_mat:

@@ -99,7 +99,7 @@ def mrsw_scores_packed(words, regions, tiles_dev, n_tiles, Ni, Nc, out=None, num
         n_region_rows=regions.n_rows, Kp=words.Kp, row_cap=words.row_item.data_ptr(),
         ntiles=tiles_dev.data_ptr() if n_tiles else None, n_ntiles=n_tiles, S=out.data_ptr(),
         ldS=out.stride(0) if Ni > 1 else max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=0, num_ctas=num_ctas,
-        cta_group=cta_group)
+        cta_group=cta_group, transpose_out=0)
     if kernel_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -121,8 +121,62 @@ def scored_counts(im_shape, s_shape, im_len, s_len):
     return R, W, nr, nw, nr < R
 
 
-def alignment_scores(im_set, s_seq, im_len, s_len, precision=None, out=None):
-    """MrSw alignment scores S[B_i,B_c] of alad/loss.py:79-125 on the GPU."""
+AGGREGATIONS = ("sum", "mean", "MrSw", "MrAVGw", "symm", "MwSr")
+
+
+def _max_sum_scores(max_x, max_counts, max_clamp, sum_x, sum_counts, precision, transpose_out, out):
+    """out[...] = sum over the valid tokens of `sum_x` items of the max over the valid tokens of
+    `max_x` items (clamped at 0 where `max_clamp`).  The 'max' items become tile columns (N side),
+    the 'sum' items packed rows (M side).  out is [n_max, n_sum], or [n_sum, n_max] if transpose_out."""
+    split = precision == "fp32"
+    rows = pack_tokens(sum_x, sum_counts, slot0=1, mode=1 if split else 0, want_row_item=True)
+    cols = pack_tokens(max_x, max_counts, slot0=1, mode=2 if split else 0)
+    _, table, _ = build_region_tiles(max_counts, max_clamp)
+    tiles_dev = _to_dev(table.view(np.int32).reshape(-1), max_x.device) if len(table) else None
+    n_max, n_sum = max_x.shape[0], sum_x.shape[0]
+    lib = _cabi.lib()
+    a = _cabi.MrswFwdArgs(
+        words=rows.data.data_ptr(), n_word_rows=rows.n_rows, regions=cols.data.data_ptr(), n_region_rows=cols.n_rows,
+        Kp=rows.Kp, row_cap=rows.row_item.data_ptr(), ntiles=tiles_dev.data_ptr() if len(table) else None,
+        n_ntiles=len(table), S=out.data_ptr(), ldS=max(out.stride(0), out.shape[1]), Ni=n_max, Nc=n_sum, epilogue=0,
+        num_ctas=0, cta_group=0, transpose_out=1 if transpose_out else 0)
+    if kernel_timeline is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _cabi.check(lib.alad_mrsw_scores_fwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_fwd")
+    if kernel_timeline is not None:
+        e1.record()
+        kernel_timeline.append((e0, e1, n_max, n_sum, rows.Kp))
+    return out
+
+
+def pool_tokens(x, counts, eps=1e-12):
+    """[B,d] fp32: sum of the normalised valid tokens (slots 1..count) of every item."""
+    B, S, d = x.shape
+    out = torch.empty((B, d), dtype=torch.float32, device=x.device)
+    if B:
+        cnt = _to_dev(np.asarray(counts, np.int32), x.device)
+        _cabi.check(_cabi.lib().alad_pool_tokens(x.data_ptr(), x.stride(0), x.stride(1), B, S, d, 1, cnt.data_ptr(), eps,
+                                                 out.data_ptr(), _cabi.stream_ptr()), "alad_pool_tokens")
+    return out
+
+
+def scale_scores(S, mul=1.0, col_div=None):
+    """In place S[i,j] = S[i,j] * mul / col_div[j]."""
+    Ni, Nc = S.shape
+    assert S.is_cuda and S.dtype == torch.float32 and S.stride(1) == 1
+    _cabi.check(_cabi.lib().alad_scale_scores(S.data_ptr(), max(S.stride(0), Nc), Ni, Nc,
+                                              col_div.data_ptr() if col_div is not None else None, float(mul),
+                                              _cabi.stream_ptr()), "alad_scale_scores")
+    return S
+
+
+def alignment_scores(im_set, s_seq, im_len, s_len, precision=None, out=None, aggregation="MrSw"):
+    """Alignment scores S[B_i,B_c] of alad/loss.py:79-135 on the GPU, every tensor pooling mode:
+    MrSw (max regions, sum words), MrAVGw (/ #words), MwSr (roles swapped), symm (MrSw + MwSr),
+    sum / mean (one GEMM of the pooled token sums)."""
+    if aggregation not in AGGREGATIONS:
+        raise ValueError(f"unsupported aggregation {aggregation!r}")
     precision = precision or _precision
     im_set = _require_cuda(im_set, "im_set")
     s_seq = _require_cuda(s_seq, "s_seq")
@@ -130,12 +184,25 @@ def alignment_scores(im_set, s_seq, im_len, s_len, precision=None, out=None):
         raise ValueError("expected im_set [B_i,S_im,d] and s_seq [B_c,S_s,d] with equal d")
     Ni, Nc = im_set.shape[0], s_seq.shape[0]
     R, W, nr, nw, clamp = scored_counts(im_set.shape, s_seq.shape, im_len, s_len)
-    split = precision == "fp32"
-    words = pack_tokens(s_seq, nw, slot0=1, mode=1 if split else 0, want_row_item=True)
-    regions = pack_tokens(im_set, nr, slot0=1, mode=2 if split else 0)
-    _, table, _ = build_region_tiles(nr, clamp)
-    tiles_dev = _to_dev(table.view(np.int32).reshape(-1), im_set.device) if len(table) else None
-    return mrsw_scores_packed(words, regions, tiles_dev, len(table), Ni, Nc, out=out)
+    if out is None:
+        out = torch.empty((Ni, Nc), dtype=torch.float32, device=im_set.device)
+    assert out.shape == (Ni, Nc) and out.dtype == torch.float32 and out.stride(1) == 1
+    if aggregation in ("sum", "mean"):
+        # sum_{r,w} <r,w> = <sum_r r, sum_w w>; always split precision (the GEMM is tiny)
+        dot_scores(pool_tokens(im_set, nr), pool_tokens(s_seq, nw), precision="fp32", out=out)
+        if aggregation == "mean":
+            scale_scores(out, mul=1.0 / max(R * W, 1))
+        return out
+    if aggregation in ("MrSw", "MrAVGw", "symm"):
+        _max_sum_scores(im_set, nr, clamp, s_seq, nw, precision, False, out)
+        if aggregation == "MrAVGw":
+            scale_scores(out, col_div=_to_dev(nw.astype(np.float32), out.device))
+    if aggregation in ("MwSr", "symm"):
+        dst = out if aggregation == "MwSr" else torch.empty_like(out)
+        _max_sum_scores(s_seq, nw, nw < W, im_set, nr, precision, True, dst)
+        if aggregation == "symm":
+            out += dst
+    return out
 
 
 def dot_scores(im, s, precision=None, normalize=False, eps=0.0, out=None):
@@ -162,6 +229,6 @@ def dot_scores(im, s, precision=None, normalize=False, eps=0.0, out=None):
     a = _cabi.MrswFwdArgs(
         words=words.data.data_ptr(), n_word_rows=Nc, regions=regions.data.data_ptr(), n_region_rows=Ni,
         Kp=words.Kp, row_cap=None, ntiles=tiles_dev.data_ptr(), n_ntiles=len(table), S=out.data_ptr(),
-        ldS=max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=1, num_ctas=0, cta_group=0)
+        ldS=max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=1, num_ctas=0, cta_group=0, transpose_out=0)
     _cabi.check(lib.alad_mrsw_scores_fwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_fwd")
     return out

@@ -109,8 +109,21 @@ typedef struct alad_mrsw_fwd_args {
   int32_t num_ctas;              /* 0 = one persistent CTA per SM                            */
   int32_t cta_group;             /* 0 = default (2, or $ALAD_CTA_GROUP); 1 = one CTA per 128x240 tile;
                                     2 = CTA pair (tcgen05 cta_group::2) per 256x240 tile       */
+  int32_t transpose_out;         /* 1: write S[word item, region item] (S is [Nc, ldS]); used for the
+                                    'MwSr' pooling, which is MrSw with the two token sets swapped */
 } alad_mrsw_fwd_args;
 int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * alad_pool_tokens -- sum of the L2-normalised valid tokens of every item: out[b, :] =
+ * sum_{t < count[b]} normalize(src[b, slot0 + t, :]).  With it the 'sum' / 'mean' pooling modes of
+ * alad/loss.py:120-123 collapse to one GEMM: sum_{r,w} <r, w> = <sum_r r, sum_w w>.
+ * alad_scale_scores -- S[i, j] = S[i, j] * mul / col_div[j] (col_div optional): the division by
+ * the caption lengths of 'MrAVGw' (loss.py:126-129) and the 1/(R*W) of 'mean'.
+ * ------------------------------------------------------------------------------- */
+int alad_pool_tokens(const float* src, int64_t stride_b, int64_t stride_s, int32_t B, int32_t S, int32_t d,
+                     int32_t slot0, const int32_t* count, float eps, float* out, void* stream);
+int alad_scale_scores(float* S, int64_t ldS, int32_t Ni, int32_t Nc, const float* col_div, float mul, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * alad_mrsw_scores_bwd -- autograd of alad/loss.py:80-125 for aggregation 'MrSw': given
@@ -135,6 +148,7 @@ typedef struct alad_mrsw_bwd_args {
   float* d_im;
   float* d_s;
   float eps;                     /* F.normalize eps (1e-12)                                  */
+  int32_t region_extent;         /* container extent R of the max side (clamp iff nr < R); 0 = S_im - 1 */
   int64_t max_pairs;             /* capacity of the pair list (Bi*Bc is always enough)       */
   void* workspace;
   int64_t workspace_bytes;       /* >= alad_mrsw_bwd_workspace_bytes(...)                    */

@@ -158,3 +158,35 @@ def test_training_batch_128_vs_oracle():
     d_im, d_s = O.mrsw_backward(im, s, il, cl, G)
     np.testing.assert_allclose(im_t.grad.cpu().numpy().transpose(1, 0, 2), d_im, rtol=2e-3, atol=2e-5)
     np.testing.assert_allclose(s_t.grad.cpu().numpy().transpose(1, 0, 2), d_s, rtol=2e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("agg", ["MwSr", "symm", "MrAVGw"])
+def test_other_pooling_modes_gradients_vs_torch_autograd(agg):
+    """Gradients of the non-default pooling modes against torch autograd on a plain fp32
+    restatement of alad/loss.py:80-135 (the kernel under test is the CUDA backward)."""
+    from aladin_b200 import loss as L, synth
+    im, s, il, cl = synth.raw_batch(21, 7, 9, 8, 12, 48, related=0.7)
+    cl = [max(c, 5) for c in cl]                                    # MrAVGw: keep #words >= 1 (no 0/0)
+    im_t, s_t = cu(im, True), cu(s, True)
+    crit = L.AlignmentContrastiveLoss(aggregation=agg)
+    crit.precision = "fp32"
+    S = crit(im_t, s_t, il, cl, return_loss=False, return_similarity_mat=True)
+    Gup = cu(np.random.RandomState(5).standard_normal(S.shape))
+    (S * Gup).sum().backward()
+    # reference-shaped fp32 computation in torch (CPU, double) with autograd
+    a = torch.tensor(im, dtype=torch.float64, requires_grad=True)
+    b = torch.tensor(s, dtype=torch.float64, requires_grad=True)
+    an = torch.nn.functional.normalize(a, dim=2)[:, 1:]
+    bn = torch.nn.functional.normalize(b, dim=2)[:, 1:-2]
+    A = torch.einsum("ird,jwd->ijrw", an, bn)
+    R, W = an.shape[1], bn.shape[1]
+    rm = torch.arange(R)[None, :] >= torch.tensor([l - 1 for l in il])[:, None]
+    wm = torch.arange(W)[None, :] >= torch.tensor([l - 3 for l in cl])[:, None]
+    A = A.masked_fill(rm[:, None, :, None] | wm[None, :, None, :], 0.0)
+    mrsw = A.max(2)[0].sum(2)
+    mwsr = A.max(3)[0].sum(2)
+    ref = {"MwSr": mwsr, "symm": mrsw + mwsr, "MrAVGw": mrsw / torch.tensor([l - 3 for l in cl], dtype=torch.float64)[None, :]}[agg]
+    assert_scores_close(S.detach().cpu().numpy(), ref.detach().numpy(), 1e-4, agg)
+    (ref * Gup.cpu().double()).sum().backward()
+    np.testing.assert_allclose(im_t.grad.cpu().numpy(), a.grad.numpy(), rtol=2e-3, atol=2e-5)
+    np.testing.assert_allclose(s_t.grad.cpu().numpy(), b.grad.numpy(), rtol=2e-3, atol=2e-5)

@@ -85,7 +85,7 @@ def test_arbitrary_callable_sim_function():
 def test_coco1k_shape_subset_vs_oracle():
     """Dense 34x50, d=1024 tokens (BASELINE per-pair shape) at 100 images x 500 captions."""
     from aladin_b200 import evaluation as E, loss as L, synth
-    images, captions, il, cl = synth.eval_containers(33, 100, 53, 1024, max_regions=35, max_words=53, dense=True, alpha=0.35)
+    images, captions, il, cl = synth.eval_containers(33, 100, 53, 1024, max_regions=35, max_words=53, dense=True, alpha=0.04)
     scorer = L.AlignmentContrastiveLoss(aggregation="MrSw")
     scorer.precision = "fp32"
     ti, tc = torch.from_numpy(images), torch.from_numpy(captions)

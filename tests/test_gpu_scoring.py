@@ -134,3 +134,32 @@ def test_alignment_scores_is_deterministic():
     a = aladin_b200.alignment_scores(torch.from_numpy(im), torch.from_numpy(s), im_len, s_len)
     b = aladin_b200.alignment_scores(torch.from_numpy(im), torch.from_numpy(s), im_len, s_len)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_all_pooling_modes_golden(precision):
+    """alad/loss.py:120-135: sum, mean, MrSw, MrAVGw, symm, MwSr against the reference's outputs."""
+    import aladin_b200
+    g = load_golden("alignment_scores")
+    for agg in ("sum", "mean", "MrSw", "MrAVGw", "symm", "MwSr"):
+        S = aladin_b200.alignment_scores(torch.from_numpy(g["im"]), torch.from_numpy(g["s"]), g["im_len"].tolist(),
+                                         g["s_len"].tolist(), precision=precision, aggregation=agg).cpu().numpy()
+        ref = g["S_" + agg]
+        ok = np.isfinite(ref)                       # MrAVGw divides by a zero word count for one caption
+        assert np.array_equal(np.isnan(S), np.isnan(ref)), agg
+        if precision == "bf16" and agg not in ("sum", "mean"):
+            assert np.abs(S[ok] - ref[ok]).max() <= 2 * BF16_ATOL, (agg, np.abs(S[ok] - ref[ok]).max())
+        else:
+            assert_scores_close(S[ok], ref[ok], FP32_RTOL, agg)
+
+
+@pytest.mark.parametrize("agg", ["MwSr", "symm", "MrAVGw", "sum", "mean"])
+def test_pooling_modes_vs_oracle_ragged(agg):
+    import aladin_b200
+    from aladin_b200 import synth
+    im, s, im_len, s_len = synth.raw_batch(11, 45, 38, 30, 41, 192, related=0.5)
+    got = aladin_b200.alignment_scores(torch.from_numpy(im), torch.from_numpy(s), im_len, s_len, precision="fp32",
+                                       aggregation=agg).cpu().numpy()
+    ref = O.alignment_scores_small(im, s, im_len, s_len, agg)
+    ok = np.isfinite(ref)
+    assert_scores_close(got[ok], ref[ok], FP32_RTOL, agg)
