@@ -16,7 +16,7 @@ class PackArgs(C.Structure):
         ("B", C.c_int32), ("S", C.c_int32), ("d", C.c_int32), ("slot0", C.c_int32),
         ("count", C.c_void_p), ("row_off", C.c_void_p), ("dst", C.c_void_p),
         ("Kp", C.c_int32), ("mode", C.c_int32), ("normalize", C.c_int32), ("eps", C.c_float),
-        ("row_item", C.c_void_p),
+        ("row_item", C.c_void_p), ("item_base", C.c_int32),
     ]
 
 
@@ -64,6 +64,7 @@ PROTOTYPES = {
     "alad_col_count": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "alad_col_topk": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "alad_topk_merge": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "alad_shortlist_scatter": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P]),
 }
 
 _lib = None
@@ -94,7 +95,7 @@ def lib():
 KERNELS_PER_CALL = {
     "alad_h2d_2d": 0, "alad_pack_tokens": 1, "alad_pool_tokens": 1, "alad_scale_scores": 1, "alad_mrsw_scores_fwd": 1, "alad_mrsw_scores_bwd": 6,
     "alad_triplet_fwd_bwd": 2, "alad_listnet_fwd_bwd": 2, "alad_rank_rows": 1, "alad_col_gt": 1,
-    "alad_col_count": 1, "alad_col_topk": 1, "alad_topk_merge": 1,
+    "alad_col_count": 1, "alad_col_topk": 1, "alad_topk_merge": 1, "alad_shortlist_scatter": 2,
 }
 launch_count = {"kernels": 0}
 

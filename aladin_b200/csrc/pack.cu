@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_tokens_kernel(const alad
       }
     }
     for (int i = used + lane; i < Kp; i += 32) y[i] = __float2bfloat16_rn(0.f);   // K padding
-    if (a.row_item != nullptr && lane == 0) a.row_item[row0 + t] = b;
+    if (a.row_item != nullptr && lane == 0) a.row_item[row0 + t] = a.item_base + b;
   }
 }
 

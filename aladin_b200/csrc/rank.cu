@@ -241,7 +241,52 @@ __global__ void topk_merge_kernel(const float* __restrict__ cand_score, const in
   }
 }
 
+// ------------------------------------------------------------------ two-stage retrieval: keep only shortlisted pairs
+__global__ void fill_kernel(float* __restrict__ x, long long ld, int rows, int cols, float v) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cols) x[(long long)blockIdx.y * ld + j] = v;
+}
+// list q holds up to k gallery indices for query q; by_column: q = caption (column), entries = global image
+// indices; otherwise q = local image (row), entries = caption indices.
+__global__ void shortlist_scatter_kernel(const float* __restrict__ S, long long ldS, float* __restrict__ S2, long long ld2,
+                                         int Ni, int Nc, const int* __restrict__ idx, int n_lists, int k, int by_column,
+                                         int img_off) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)n_lists * k) return;
+  const int q = (int)(e / k);
+  const int g = idx[e];
+  if (g < 0) return;
+  int i, c;
+  if (by_column) {
+    i = g - img_off;
+    c = q;
+  } else {
+    i = q;
+    c = g;
+  }
+  if (i < 0 || i >= Ni || c < 0 || c >= Nc) return;
+  S2[(long long)i * ld2 + c] = S[(long long)i * ldS + c];
+}
+
 }  // namespace alad
+
+extern "C" int alad_shortlist_scatter(const float* S, int64_t ldS, float* S2, int64_t ld2, int32_t Ni, int32_t Nc,
+                                      const int32_t* idx, int32_t n_lists, int32_t k, int32_t by_column, int32_t img_off,
+                                      void* stream) {
+  using namespace alad;
+  ALAD_REQUIRE(Ni >= 0 && Nc >= 0 && ldS >= Nc && ld2 >= Nc && k > 0 && n_lists >= 0 && Ni <= 65535 * 1,
+               "alad_shortlist_scatter: bad shape");
+  if (Ni == 0 || Nc == 0) return ALAD_OK;
+  ALAD_REQUIRE(S && S2 && (idx || n_lists == 0), "alad_shortlist_scatter: NULL pointer");
+  cudaStream_t st = as_stream(stream);
+  dim3 grid((Nc + 255) / 256, Ni);
+  fill_kernel<<<grid, 256, 0, st>>>(S2, ld2, Ni, Nc, -INFINITY);
+  const long long n = (long long)n_lists * k;
+  if (n) shortlist_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S, ldS, S2, ld2, Ni, Nc, idx, n_lists, k,
+                                                                                by_column, img_off);
+  ALAD_CUDA(cudaGetLastError());
+  return ALAD_OK;
+}
 
 extern "C" int alad_rank_rows(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t group, int32_t img_off,
                               int32_t* rank, int32_t* top1, void* stream) {

@@ -84,7 +84,7 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
         world, rank, group = _dist_state()
         gal = retrieval.AlignmentGallery(images, captions, img_lens, cap_lens, n_images=Ni, img_start=0, img_step=5,
                                          precision=precision, world=world, rank=rank)
-        S = gal.scores()
+        S = gal.scores(group=group)
         img_off = gal.lo
     else:
         S = _callback_scores(images, captions, img_lens, cap_lens, sim_function, batches)

@@ -60,7 +60,8 @@ class Packed:
         self.counts, self.row_off, self.row_item, self.mode = counts, row_off, row_item, mode
 
 
-def pack_tokens(x, counts, *, slot0, mode=0, normalize=True, eps=1e-12, want_row_item=False):
+def pack_tokens(x, counts, *, slot0, mode=0, normalize=True, eps=1e-12, want_row_item=False, out=None,
+                out_row_item=None, row_base=0, item_base=0):
     """x [B,S,d] fp32 cuda (any strides on B,S) -> Packed rows for tokens slot0 .. slot0+count-1."""
     lib = _cabi.lib()
     assert x.dim() == 3 and x.is_cuda and x.dtype == torch.float32 and x.stride(2) == 1
@@ -71,17 +72,24 @@ def pack_tokens(x, counts, *, slot0, mode=0, normalize=True, eps=1e-12, want_row
         raise ValueError("token counts exceed the container")
     row_off, n_rows = exclusive_cumsum(counts)
     Kp = round_up(d * (1 if mode == 0 else 3), _cabi.TILE_K)
-    data = torch.empty((max(n_rows, 1), Kp), dtype=torch.bfloat16, device=x.device)
-    row_item = None
-    if want_row_item:
-        row_item = torch.full((max(padded_rows(n_rows), 2 * _cabi.TILE_M),), -1, dtype=torch.int32, device=x.device)
+    if out is not None:
+        # pack into rows [row_base, row_base + n_rows) of a caller-owned buffer (sharded packing)
+        assert out.dtype == torch.bfloat16 and out.shape[1] == Kp and out.is_contiguous() and row_base + n_rows <= out.shape[0]
+        data, row_item = out, out_row_item
+        row_off = row_off + row_base
+    else:
+        data = torch.empty((max(n_rows, 1), Kp), dtype=torch.bfloat16, device=x.device)
+        row_item = None
+        if want_row_item:
+            row_item = torch.full((max(padded_rows(n_rows), 2 * _cabi.TILE_M),), -1, dtype=torch.int32, device=x.device)
     if n_rows:
         cnt_d = _to_dev(counts, x.device)
         off_d = _to_dev(row_off, x.device)
         a = _cabi.PackArgs(
             src=x.data_ptr(), stride_b=x.stride(0), stride_s=x.stride(1), B=B, S=S, d=d, slot0=slot0,
             count=cnt_d.data_ptr(), row_off=off_d.data_ptr(), dst=data.data_ptr(), Kp=Kp, mode=mode,
-            normalize=1 if normalize else 0, eps=eps, row_item=row_item.data_ptr() if row_item is not None else None)
+            normalize=1 if normalize else 0, eps=eps, row_item=row_item.data_ptr() if row_item is not None else None,
+            item_base=item_base)
         _cabi.check(lib.alad_pack_tokens(C.byref(a), _cabi.stream_ptr()), "alad_pack_tokens")
     return Packed(data, n_rows, Kp, counts, row_off, row_item, mode)
 

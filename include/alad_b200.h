@@ -73,7 +73,8 @@ typedef struct alad_pack_args {
   int32_t mode;
   int32_t normalize;         /* 1: F.normalize semantics; 0: copy                    */
   float eps;                 /* 1e-12 (F.normalize) or 0 (alad.utils.l2norm)         */
-  int32_t* row_item;         /* optional [rows]                                      */
+  int32_t* row_item;         /* optional [rows]: receives item_base + b              */
+  int32_t item_base;         /* global index of item 0 (sharded packing)             */
 } alad_pack_args;
 int alad_pack_tokens(const alad_pack_args* a, void* stream);
 
@@ -194,6 +195,14 @@ int alad_col_topk(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t k
 /* merge P sorted candidate lists per caption (after the all-gather across shards). */
 int alad_topk_merge(const float* cand_score, const int32_t* cand_idx, int32_t P, int32_t Nc, int32_t k,
                     float* out_score, int32_t* out_idx, void* stream);
+
+/* Two-stage retrieval (BASELINE config 5; not in the reference): S2 = -inf everywhere except the
+ * shortlisted (image, caption) pairs, which keep their alignment score.  idx is [n_lists, k];
+ * by_column = 1: list q belongs to caption q and holds GLOBAL image indices (t2i shortlist),
+ * by_column = 0: list q belongs to local image q and holds caption indices (i2t shortlist). */
+int alad_shortlist_scatter(const float* S, int64_t ldS, float* S2, int64_t ld2, int32_t Ni, int32_t Nc,
+                           const int32_t* idx, int32_t n_lists, int32_t k, int32_t by_column, int32_t img_off,
+                           void* stream);
 
 #ifdef __cplusplus
 }

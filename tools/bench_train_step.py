@@ -1,0 +1,77 @@
+"""Training-side measurements (BASELINE configs 1 and 4): alignment + matching + hinge + ListNet,
+forward and forward+backward, through the drop-in criteria; plus achieved HBM GB/s of the B x B
+loss kernels at B = 512 and B = 8192 (algorithmic bytes: triplet 8*B^2, listnet 16*B^2).
+Run on the GPU box:  python tools/bench_train_step.py"""
+import json
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import aladin_b200  # noqa: E402
+from aladin_b200 import loss as L, synth  # noqa: E402
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def train_step(B, precision):
+    im, s, il, cl = synth.raw_batch(9, B, B, 35, 53, 1024, related=0.6)
+    r = np.random.RandomState(1)
+    icls = r.standard_normal((B, 1024)).astype(np.float32)
+    ccls = (0.7 * icls + r.standard_normal((B, 1024))).astype(np.float32)
+    icls /= np.linalg.norm(icls, axis=1, keepdims=True)
+    ccls /= np.linalg.norm(ccls, axis=1, keepdims=True)
+    img_set = torch.tensor(im.transpose(1, 0, 2).copy(), device="cuda", requires_grad=True)   # [S,B,d]
+    cap_seq = torch.tensor(s.transpose(1, 0, 2).copy(), device="cuda", requires_grad=True)
+    img_cls = torch.tensor(icls, device="cuda", requires_grad=True)
+    cap_cls = torch.tensor(ccls, device="cuda", requires_grad=True)
+    mc = L.ContrastiveLoss(margin=0.2, measure="dot", max_violation=True)
+    ac = L.AlignmentContrastiveLoss(margin=0.2, measure="dot", max_violation=True, aggregation="MrSw")
+    dl = L.DistillationLoss(mode="listnet")
+    aladin_b200.set_precision(precision)
+
+    def fwd():
+        ml, mm = mc(img_cls, cap_cls, return_similarity_mat=True)
+        al, ts = ac(img_set.permute(1, 0, 2), cap_seq.permute(1, 0, 2), il, cl, return_similarity_mat=True)
+        return al + dl(ts, mm) + 0.1 * ml
+
+    def fwd_bwd():
+        for t in (img_set, cap_seq, img_cls, cap_cls):
+            t.grad = None
+        fwd().backward()
+
+    with torch.no_grad():
+        t_f = timeit(fwd)
+    t_fb = timeit(fwd_bwd)
+    flop = 2.0 * sum(l - 1 for l in il) * sum(l - 3 for l in cl) * 1024
+    return {"B": B, "precision": precision, "fwd_ms": t_f, "fwd_bwd_ms": t_fb, "pairs_per_s_fwd": B * B / t_f * 1e3,
+            "pairs_per_s_fwd_bwd": B * B / t_fb * 1e3, "fwd_algorithmic_tflops": flop / t_f / 1e9}
+
+
+def loss_kernels(B):
+    r = np.random.RandomState(B)
+    S = torch.tensor(r.standard_normal((B, B)).astype(np.float32), device="cuda")
+    M = torch.tensor(np.clip(r.standard_normal((B, B)) * 0.3, -1, 1).astype(np.float32), device="cuda")
+    T = S * 2 + 3
+    t_tri = timeit(lambda: L.triplet_fwd_bwd(S, 0.2, True))
+    t_ln = timeit(lambda: L.listnet_fwd_bwd(T, M))
+    return {"B": B, "triplet_ms": t_tri, "triplet_GBs": 8.0 * B * B / t_tri / 1e6, "listnet_ms": t_ln,
+            "listnet_GBs": 16.0 * B * B / t_ln / 1e6}
+
+
+if __name__ == "__main__":
+    out = {"train_step": [train_step(B, p) for B in (128, 512) for p in ("bf16", "fp32")],
+           "loss_kernels": [loss_kernels(B) for B in (512, 8192)]}
+    print(json.dumps(out, indent=1))
