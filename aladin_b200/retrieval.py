@@ -54,7 +54,7 @@ class AlignmentGallery:
     i2t reads row 5i, t2i rows 0::5 -- alad/evaluation.py:178,252)."""
 
     def __init__(self, images, captions, img_lens, cap_lens, n_images, img_start=0, img_step=1,
-                 precision=None, world=1, rank=0, caption_chunk=4096):
+                 precision=None, world=1, rank=0, caption_chunk=4096, caption_phases=4):
         if not torch.cuda.is_available():
             raise _cabi.AladError("aladin_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.precision = precision or scoring.get_precision()
@@ -64,11 +64,12 @@ class AlignmentGallery:
         self.world, self.rank = world, rank
         self.lo, self.hi = shard_bounds(self.Ni, world, rank)
         self.caption_chunk = caption_chunk
+        self.caption_phases = max(1, caption_phases)
         img_lens_g = [img_lens[img_start + i * img_step] for i in range(self.Ni)]
         self.R, self.W, self.nr, self.nw, self.clamp = scoring.scored_counts(
             (self.Ni, images.shape[1]), captions.shape, img_lens_g, cap_lens)
 
-    def _pack_caption_range(self, c_lo, c_hi, words_buf, cap_buf, row_base, split, dev):
+    def _pack_caption_range(self, c_lo, c_hi, words_buf, cap_buf, row_base, split, dev, item_origin=0):
         """Upload (if on the host) and pack captions [c_lo, c_hi) into rows row_base.. of
         words_buf / cap_buf.  Host sources are double-buffered: the pitched H2D copy of chunk k+1
         overlaps the packing of chunk k.  Returns the number of rows written."""
@@ -97,7 +98,7 @@ class AlignmentGallery:
             else:
                 cap_dev = self.captions[c0:c1]
             scoring.pack_tokens(cap_dev, nw[c0:c1], slot0=1, mode=1 if split else 0, out=words_buf, out_row_item=cap_buf,
-                                row_base=row_base + rows, item_base=c0)
+                                row_base=row_base + rows, item_base=c0 - item_origin)
             rows += int(nw[c0:c1].sum())
             if on_cpu:
                 freed[bsel] = torch.cuda.Event()
@@ -134,18 +135,46 @@ class AlignmentGallery:
             tiles_dev = scoring._to_dev(table.view(np.int32).reshape(-1), dev) if n_tiles else None
         # ---- words: all captions (single rank / device-resident) or this rank's share + all-gather
         if shard_caps:
-            spans = [shard_bounds(self.Nc, self.world, r) for r in range(self.world)]
-            rows_per = [int(nw[a:b].sum()) for a, b in spans]
-            pad = ((max(rows_per) + 2 * _cabi.TILE_M - 1) // (2 * _cabi.TILE_M)) * (2 * _cabi.TILE_M)
-            words_all = torch.empty((self.world * pad, Kp), dtype=torch.bfloat16, device=dev)
-            caps_all = torch.full((self.world * pad,), -1, dtype=torch.int32, device=dev)
-            mine_w = words_all[self.rank * pad:(self.rank + 1) * pad]
-            mine_c = caps_all[self.rank * pad:(self.rank + 1) * pad]
-            c_lo, c_hi = spans[self.rank]
-            self._pack_caption_range(c_lo, c_hi, mine_w, mine_c, 0, split, dev)
-            dist.all_gather_into_tensor(words_all, mine_w.clone(), group=group)   # gap rows are never scored (row_cap -1)
-            dist.all_gather_into_tensor(caps_all, mine_c.clone(), group=group)
-            n_rows = self.world * pad
+            # captions are processed in phases; inside a phase every rank uploads + packs its 1/world
+            # share, the packed rows are all-gathered (NVLink) and the phase is scored while the next
+            # phase is being prepared on a side stream
+            P = self.caption_phases if self.Nc >= self.caption_phases * self.world * 64 else 1
+            pb = [(p * self.Nc // P, (p + 1) * self.Nc // P) for p in range(P)]
+            plans = []
+            for c0, c1 in pb:
+                spans = [tuple(c0 + x for x in shard_bounds(c1 - c0, self.world, r)) for r in range(self.world)]
+                rows_max = max(int(nw[a:b].sum()) for a, b in spans)
+                pad = ((rows_max + 2 * _cabi.TILE_M - 1) // (2 * _cabi.TILE_M)) * (2 * _cabi.TILE_M)
+                plans.append((spans[self.rank], max(pad, 2 * _cabi.TILE_M)))
+            pad_max = max(pad for _, pad in plans)
+            words_buf = [torch.empty((self.world * pad_max, Kp), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+            caps_buf = [torch.empty((self.world * pad_max,), dtype=torch.int32, device=dev) for _ in range(2)]
+            mine_w = [torch.empty((pad_max, Kp), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+            mine_c = [torch.empty((pad_max,), dtype=torch.int32, device=dev) for _ in range(2)]
+            main = torch.cuda.current_stream()
+            prep = torch.cuda.Stream()
+            prep.wait_stream(main)
+            freed = [None, None]
+            for p, ((c0, c1), ((m0, m1), pad)) in enumerate(zip(pb, plans)):
+                b = p & 1
+                with torch.cuda.stream(prep):
+                    if freed[b] is not None:
+                        prep.wait_event(freed[b])
+                    mw, mc = mine_w[b][:pad], mine_c[b][:pad]
+                    mc.fill_(-1)
+                    self._pack_caption_range(m0, m1, mw, mc, 0, split, dev, item_origin=c0)
+                    wa, ca = words_buf[b][:self.world * pad], caps_buf[b][:self.world * pad]
+                    dist.all_gather_into_tensor(wa, mw, group=group)      # gap rows are never scored (row_cap -1)
+                    dist.all_gather_into_tensor(ca, mc, group=group)
+                    ready = torch.cuda.Event()
+                    ready.record(prep)
+                main.wait_event(ready)
+                if n_loc:
+                    words = scoring.Packed(wa, self.world * pad, Kp, None, None, ca, 1 if split else 0)
+                    scoring.mrsw_scores_packed(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, out=S[:, c0:c1])
+                freed[b] = torch.cuda.Event()
+                freed[b].record(main)
+            return S
         else:
             # one rank owns all captions: score chunk k while chunk k+1 is uploaded (host sources)
             on_cpu = not self.captions.is_cuda
@@ -176,11 +205,6 @@ class AlignmentGallery:
                     freed[bsel] = torch.cuda.Event()
                     freed[bsel].record(main)
             return S
-        if n_loc == 0:
-            return S
-        words = scoring.Packed(words_all, n_rows, Kp, None, None, caps_all, 1 if split else 0)
-        scoring.mrsw_scores_packed(words, regions, tiles_dev, n_tiles, n_loc, self.Nc, out=S)
-        return S
 
 
 def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=None, gather_i2t=True, ops=ranking):
