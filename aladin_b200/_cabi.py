@@ -59,6 +59,14 @@ PROTOTYPES = {
     "alad_loss_workspace_bytes": (C.c_int64, [_I32]),
     "alad_triplet_fwd_bwd": (C.c_int, [_P, _I64, _I32, C.c_float, _I32, _P, _P, _I64, _P, _P, _P, _P]),
     "alad_listnet_fwd_bwd": (C.c_int, [_P, _I64, _P, _I64, _I32, C.c_float, C.c_float, _P, _P, _I64, _P, _P]),
+    "alad_distill_workspace_bytes": (C.c_int64, [_I32, _I32]),
+    "alad_distill_mse_fwd_bwd": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _P, _P, _P]),
+    "alad_distill_contrastive_fwd_bwd": (C.c_int, [_P, _I64, _P, _I64, _I32, C.c_float, _I32, _P, _P, _I64, _P, _P]),
+    "alad_distill_ordinal_fwd_bwd": (C.c_int, [_P, _I64, _P, _I64, _I32, C.c_float, C.c_float, _I32, _P, _P, _I64, _P, _P]),
+    "alad_order_scores": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _I64, _P]),
+    "alad_order_scores_bwd": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _P, _P]),
+    "alad_normalize_bwd": (C.c_int, [_P, _I64, _I64, _I32, C.c_float, _P, _I64, _P]),
+    "alad_pool_tokens_bwd": (C.c_int, [_P, _I64, _I64, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P, _P]),
     "alad_rank_rows": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "alad_col_gt": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "alad_col_count": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
@@ -96,6 +104,8 @@ KERNELS_PER_CALL = {
     "alad_h2d_2d": 0, "alad_pack_tokens": 1, "alad_pool_tokens": 1, "alad_scale_scores": 1, "alad_mrsw_scores_fwd": 1, "alad_mrsw_scores_bwd": 6,
     "alad_triplet_fwd_bwd": 2, "alad_listnet_fwd_bwd": 2, "alad_rank_rows": 1, "alad_col_gt": 1,
     "alad_col_count": 1, "alad_col_topk": 1, "alad_topk_merge": 1, "alad_shortlist_scatter": 2,
+    "alad_distill_mse_fwd_bwd": 1, "alad_distill_contrastive_fwd_bwd": 2, "alad_distill_ordinal_fwd_bwd": 2,
+    "alad_order_scores": 1, "alad_order_scores_bwd": 1, "alad_normalize_bwd": 1, "alad_pool_tokens_bwd": 1,
 }
 launch_count = {"kernels": 0}
 

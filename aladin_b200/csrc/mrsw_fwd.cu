@@ -73,6 +73,7 @@ struct MrswParams {
   int num_kb;
   int epilogue;
   int n_block;      // N tiles swept per pass over the M tiles (their region rows stay hot in L2)
+  int l2_hints;     // TMA L2 policies: bit 0 = words evict_first, bit 1 = region block evict_last
 };
 
 __device__ __forceinline__ void tile_coord(int t, int n_mtiles, int n_ntiles, int n_block, int& mt, int& nt) {
@@ -142,6 +143,10 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // the word rows stream past once per region block; the region block is re-read by every M unit
+      const bool hints = p.l2_hints != 0;
+      const uint64_t pol_words = (p.l2_hints & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+      const uint64_t pol_regions = (p.l2_hints & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
       for (int t = unit; t < total_tiles; t += n_units) {
         int mu, nt;
         tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt);
@@ -154,12 +159,22 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
           if (CG == 2) {
             // completion bytes of BOTH CTAs are credited to the leader's barrier
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-            tma_load_2d_cg2(sa, &map_words, &full_bar[stage], kb * BK, m_row0);
-            tma_load_2d_cg2(sb, &map_regions, &full_bar[stage], kb * BK, n_row0);
+            if (hints) {
+              tma_load_2d_cg2_hint(sa, &map_words, &full_bar[stage], kb * BK, m_row0, pol_words);
+              tma_load_2d_cg2_hint(sb, &map_regions, &full_bar[stage], kb * BK, n_row0, pol_regions);
+            } else {
+              tma_load_2d_cg2(sa, &map_words, &full_bar[stage], kb * BK, m_row0);
+              tma_load_2d_cg2(sb, &map_regions, &full_bar[stage], kb * BK, n_row0);
+            }
           } else {
             mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            tma_load_2d(sa, &map_words, &full_bar[stage], kb * BK, m_row0);
-            tma_load_2d(sb, &map_regions, &full_bar[stage], kb * BK, n_row0);
+            if (hints) {
+              tma_load_2d_hint(sa, &map_words, &full_bar[stage], kb * BK, m_row0, pol_words);
+              tma_load_2d_hint(sb, &map_regions, &full_bar[stage], kb * BK, n_row0, pol_regions);
+            } else {
+              tma_load_2d(sa, &map_words, &full_bar[stage], kb * BK, m_row0);
+              tma_load_2d(sb, &map_regions, &full_bar[stage], kb * BK, n_row0);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -471,16 +486,22 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   {
     // keep one block of region tiles (n_block x 240 rows x Kp bf16) resident in the 126 MB L2 while
     // all word tiles stream past it; ALAD_L2_BLOCK_MB overrides the budget for experiments
-    static const long long budget_mb = [] {
-      const char* e = getenv("ALAD_L2_BLOCK_MB");
-      const long long v = e ? atoll(e) : 0;
-      return v > 0 ? v : 30;
-    }();
+    // (the environment is read per call so that one process can sweep the setting)
+    const char* e = getenv("ALAD_L2_BLOCK_MB");
+    const long long ev = e ? atoll(e) : 0;
+    const long long budget_mb = ev > 0 ? ev : 30;
     const long long tile_bytes = (long long)BN * a->Kp * 2;
     long long nb = (budget_mb << 20) / tile_bytes;
     nb = nb < 8 ? 8 : nb;
+    const char* eb = getenv("ALAD_N_BLOCK");          // block size in tiles (experiments)
+    if (eb && atoll(eb) > 0) nb = atoll(eb);
     p.n_block = (int)(nb > p.n_ntiles ? p.n_ntiles : nb);
     if ((long long)p.n_mtiles * p.n_block >= (1ll << 31)) p.n_block = 8;
+  }
+  {
+    const char* e = getenv("ALAD_L2_HINTS");
+    const int env_hints = e ? atoi(e) : 0;
+    p.l2_hints = env_hints;
   }
   const long long total = (long long)p.n_mtiles * p.n_ntiles;
   ALAD_REQUIRE(total < (1ll << 31), "alad_mrsw_scores_fwd: too many tiles (%lld)", total);

@@ -62,6 +62,98 @@ def listnet_fwd_bwd(teacher, student, temperature=6.0, eps=1e-10, want_grad=True
     return loss, dM
 
 
+def _square_pair(teacher, student, what):
+    T = teacher.detach()
+    M = student.detach()
+    if T.shape != M.shape or T.dim() != 2 or T.shape[0] != T.shape[1]:
+        raise RuntimeError(f"{what} distillation expects two square matrices of equal shape")
+    if T.dtype != torch.float32 or T.stride(1) != 1:
+        T = T.float().contiguous()
+    if M.dtype != torch.float32 or M.stride(1) != 1:
+        M = M.float().contiguous()
+    return T, M
+
+
+def distill_mse_fwd_bwd(teacher, student, wb, want_grad=True):
+    """(loss 0-d, dM or None, dwb [2] or None) -- alad/loss.py:371-373."""
+    lib = _cabi.lib()
+    T, M = _square_pair(teacher, student, "mse")
+    B, dev = T.shape[0], M.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dM = torch.empty((B, B), dtype=torch.float32, device=dev) if want_grad else None
+    dwb = torch.empty(2, dtype=torch.float32, device=dev) if want_grad else None
+    wb_d = wb.detach().to(device=dev, dtype=torch.float32).contiguous()
+    ws = _ws(lib.alad_distill_workspace_bytes(B, 0), dev)
+    _cabi.check(lib.alad_distill_mse_fwd_bwd(T.data_ptr(), max(T.stride(0), B), M.data_ptr(), max(M.stride(0), B), B,
+                                             wb_d.data_ptr(), loss.data_ptr(), dM.data_ptr() if want_grad else None, B,
+                                             dwb.data_ptr() if want_grad else None, ws.data_ptr(), _cabi.stream_ptr()),
+                "alad_distill_mse_fwd_bwd")
+    return loss, dM, dwb
+
+
+def distill_contrastive_fwd_bwd(teacher, student, margin, want_grad=True, mutate_teacher=True):
+    """(loss 0-d, dM or None) -- alad/loss.py:397-418.  With mutate_teacher the diagonal of the caller's
+    teacher matrix is zeroed in place, which is what the reference's `.detach().masked_fill_` does."""
+    lib = _cabi.lib()
+    M = student.detach()
+    if M.dtype != torch.float32 or M.stride(1) != 1:
+        M = M.float().contiguous()
+    T = teacher.detach()
+    in_place = mutate_teacher and T.is_cuda and T.dtype == torch.float32 and T.dim() == 2 and T.stride(1) == 1
+    if not in_place:
+        T = T.to(device=M.device, dtype=torch.float32).contiguous().clone()
+    if T.shape != M.shape or T.dim() != 2 or T.shape[0] != T.shape[1]:
+        raise RuntimeError("contrastive distillation expects two square matrices of equal shape")
+    B, dev = T.shape[0], M.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dM = torch.empty((B, B), dtype=torch.float32, device=dev) if want_grad else None
+    ws = _ws(lib.alad_distill_workspace_bytes(B, 1), dev)
+    _cabi.check(lib.alad_distill_contrastive_fwd_bwd(T.data_ptr(), max(T.stride(0), B), M.data_ptr(), max(M.stride(0), B),
+                                                     B, float(margin), 1 if mutate_teacher else 0, loss.data_ptr(),
+                                                     dM.data_ptr() if want_grad else None, B, ws.data_ptr(),
+                                                     _cabi.stream_ptr()), "alad_distill_contrastive_fwd_bwd")
+    if mutate_teacher and not in_place:
+        with torch.no_grad():
+            teacher.detach().fill_diagonal_(0)       # same observable side effect for exotic layouts
+    return loss, dM
+
+
+def distill_ordinal_fwd_bwd(teacher, student, margin, threshold, stride, want_grad=True):
+    """(loss 0-d, dM or None) -- alad/loss.py:374-396."""
+    lib = _cabi.lib()
+    T, M = _square_pair(teacher, student, "ordinal")
+    B, dev = T.shape[0], M.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dM = torch.empty((B, B), dtype=torch.float32, device=dev) if want_grad else None
+    ws = _ws(lib.alad_distill_workspace_bytes(B, 2), dev)
+    _cabi.check(lib.alad_distill_ordinal_fwd_bwd(T.data_ptr(), max(T.stride(0), B), M.data_ptr(), max(M.stride(0), B), B,
+                                                 float(margin), float(threshold), int(stride), loss.data_ptr(),
+                                                 dM.data_ptr() if want_grad else None, B, ws.data_ptr(),
+                                                 _cabi.stream_ptr()), "alad_distill_ordinal_fwd_bwd")
+    return loss, dM
+
+
+def normalize_bwd_(x, dx, eps):
+    """In place dx <- J(x) dx for row-wise x / max(||x||, eps) (alad_normalize_bwd)."""
+    rows, d = x.shape
+    assert dx.shape == x.shape and x.stride(1) == 1 and dx.stride(1) == 1
+    _cabi.check(_cabi.lib().alad_normalize_bwd(x.data_ptr(), x.stride(0), rows, d, float(eps), dx.data_ptr(), dx.stride(0),
+                                               _cabi.stream_ptr()), "alad_normalize_bwd")
+    return dx
+
+
+def pool_tokens_bwd(x, counts, d_pool, eps=1e-12):
+    """[B,S,d] gradient of scoring.pool_tokens (alad_pool_tokens_bwd)."""
+    B, S, d = x.shape
+    out = torch.empty((B, S, d), dtype=torch.float32, device=x.device)
+    if B and S:
+        cnt = scoring._to_dev(np.asarray(counts, np.int32), x.device)
+        _cabi.check(_cabi.lib().alad_pool_tokens_bwd(x.data_ptr(), x.stride(0), x.stride(1), B, S, d, 1, cnt.data_ptr(),
+                                                     float(eps), d_pool.data_ptr(), out.data_ptr(), _cabi.stream_ptr()),
+                    "alad_pool_tokens_bwd")
+    return out
+
+
 def mrsw_backward(im_set, s_seq, nr, nw, G0=None, g0_scale=None, G1=None, eps=1e-12, region_extent=0):
     """(d im_set, d s_seq) for dL/dS = g0_scale*G0 + G1 (alad_mrsw_scores_bwd)."""
     lib = _cabi.lib()
@@ -135,15 +227,93 @@ class _DotScoresFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, G):
         im, s = ctx.saved_tensors
-        if ctx.normalize:
-            raise NotImplementedError("gradient of cosine_sim is not ported (no shipped config trains with it)")
         G = G.contiguous().float()
+        im_f, s_f = im.detach().float().contiguous(), s.detach().float().contiguous()
         d_im = d_s = None
+        # cosine_sim: the GEMM operands are the unit rows; the l2norm Jacobian (alad/utils.py:134-139,
+        # no eps) is applied in place afterwards
         if ctx.needs_input_grad[0]:
-            d_im = scoring.dot_scores(G, s.detach().float().t().contiguous(), precision="fp32")       # G @ s
+            # G @ s(hat): "regions" = G rows [Bi, Bc], "words" = s columns [d, Bc]
+            s_op = scoring.unit_rows(s_f) if ctx.normalize else s_f
+            d_im = scoring.dot_scores(G, s_op.t().contiguous(), precision="fp32")
+            if ctx.normalize:
+                normalize_bwd_(im_f, d_im, 0.0)
         if ctx.needs_input_grad[1]:
-            d_s = scoring.dot_scores(G.t().contiguous(), im.detach().float().t().contiguous(), precision="fp32")  # G.T @ im
+            im_op = scoring.unit_rows(im_f) if ctx.normalize else im_f
+            d_s = scoring.dot_scores(G.t().contiguous(), im_op.t().contiguous(), precision="fp32")   # G.T @ im(hat)
+            if ctx.normalize:
+                normalize_bwd_(s_f, d_s, 0.0)
         return d_im, d_s, None, None
+
+
+class _OrderScoresFn(torch.autograd.Function):
+    """order_sim (alad/loss.py:20-26) forward + gradient on CUDA cores (not a bilinear form)."""
+
+    @staticmethod
+    def forward(ctx, im, s):
+        im_c = scoring._require_cuda(im.detach(), "im").contiguous()
+        s_c = scoring._require_cuda(s.detach(), "s").contiguous()
+        if im_c.dim() != 2 or s_c.dim() != 2 or im_c.shape[1] != s_c.shape[1]:
+            raise ValueError("expected im [B_i,d] and s [B_c,d]")
+        Ni, Nc, d = im_c.shape[0], s_c.shape[0], im_c.shape[1]
+        out = torch.empty((Ni, Nc), dtype=torch.float32, device=im_c.device)
+        _cabi.check(_cabi.lib().alad_order_scores(im_c.data_ptr(), d, s_c.data_ptr(), d, Ni, Nc, d, out.data_ptr(),
+                                                  max(Nc, 1), _cabi.stream_ptr()), "alad_order_scores")
+        ctx.save_for_backward(im_c, s_c, out)
+        ctx.devices = (im.device, s.device)
+        return out
+
+    @staticmethod
+    def backward(ctx, G):
+        im_c, s_c, out = ctx.saved_tensors
+        Ni, Nc, d = im_c.shape[0], s_c.shape[0], im_c.shape[1]
+        G = G.contiguous().float()
+        d_im = torch.empty_like(im_c)
+        d_s = torch.empty_like(s_c)
+        _cabi.check(_cabi.lib().alad_order_scores_bwd(im_c.data_ptr(), d, s_c.data_ptr(), d, Ni, Nc, d, out.data_ptr(),
+                                                      max(Nc, 1), G.data_ptr(), max(Nc, 1), d_im.data_ptr(),
+                                                      d_s.data_ptr(), _cabi.stream_ptr()), "alad_order_scores_bwd")
+        return d_im.to(ctx.devices[0]), d_s.to(ctx.devices[1])
+
+
+class _DistillMseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, teacher, student, wb):
+        loss, dM, dwb = distill_mse_fwd_bwd(teacher, student, wb, want_grad=student.requires_grad or wb.requires_grad)
+        ctx.save_for_backward(dM, dwb)
+        ctx.wb_device = wb.device
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dM, dwb = ctx.saved_tensors
+        return None, dM * g, (dwb * g).to(ctx.wb_device)
+
+
+class _DistillContrastiveFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, teacher, student, margin):
+        loss, dM = distill_contrastive_fwd_bwd(teacher, student, margin, want_grad=student.requires_grad)
+        ctx.save_for_backward(dM)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dM,) = ctx.saved_tensors
+        return None, dM * g, None
+
+
+class _DistillOrdinalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, teacher, student, margin, threshold, stride):
+        loss, dM = distill_ordinal_fwd_bwd(teacher, student, margin, threshold, stride, want_grad=student.requires_grad)
+        ctx.save_for_backward(dM)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dM,) = ctx.saved_tensors
+        return None, dM * g, None, None, None
 
 
 class _AlignmentFn(torch.autograd.Function):
@@ -176,8 +346,19 @@ class _AlignmentFn(torch.autograd.Function):
             return none
         agg = ctx.aggregation
         if agg in ("sum", "mean"):
-            raise NotImplementedError(f"gradient of aggregation {agg!r} is not ported (no shipped config trains with it)")
-        if agg == "MrSw":
+            # S = <pool(im), pool(s)> (/ (R*W)): two small GEMMs + the pooled-token Jacobian kernel
+            G = G0 * g_loss.detach().float() if use_G0 else None
+            if g_S is not None:
+                G = g_S.detach().float() if G is None else G + g_S.detach().float()
+            if agg == "mean":
+                G = G / max((im_c.shape[1] - 1) * ctx.W, 1)
+            G = G.contiguous()
+            pi, ps = scoring.pool_tokens(im_c, ctx.nr), scoring.pool_tokens(s_c, ctx.nw)
+            d_pi = scoring.dot_scores(G, ps.t().contiguous(), precision="fp32")
+            d_ps = scoring.dot_scores(G.t().contiguous(), pi.t().contiguous(), precision="fp32")
+            d_im = pool_tokens_bwd(im_c, ctx.nr, d_pi)
+            d_s = pool_tokens_bwd(s_c, ctx.nw, d_ps)
+        elif agg == "MrSw":
             g_scale = g_loss.detach().float().reshape(1).contiguous() if use_G0 else None
             G1 = g_S.detach().float().contiguous() if g_S is not None else None
             d_im, d_s = mrsw_backward(im_c, s_c, ctx.nr, ctx.nw, G0=G0 if use_G0 else None, g0_scale=g_scale, G1=G1)
@@ -208,12 +389,13 @@ def dot_sim(im, s):
 
 
 def cosine_sim(im, s):
-    """alad/loss.py:13-18 (l2norm without eps, then mm); forward only."""
+    """alad/loss.py:13-18 (l2norm without eps, then mm)."""
     return _DotScoresFn.apply(im, s, None, True)
 
 
 def order_sim(im, s):
-    raise NotImplementedError("order_sim (alad/loss.py:20-26) is outside the ported path: unused by every config")
+    """alad/loss.py:20-26: -||max(0, s - im)||_2 for all pairs."""
+    return _OrderScoresFn.apply(im, s)
 
 
 class Contrastive(nn.Module):
@@ -280,7 +462,7 @@ class ContrastiveLoss(Contrastive):
 
 
 class DistillationLoss(nn.Module):
-    """alad/loss.py:359-447; mode 'listnet' (every shipped config) is ported."""
+    """alad/loss.py:359-447; modes 'mse', 'ordinal', 'contrastive', 'listnet' (every shipped config uses 'listnet')."""
 
     def __init__(self, mode='mse', margin=0.2, threshold=0.1, stride=3):
         super().__init__()
@@ -292,9 +474,17 @@ class DistillationLoss(nn.Module):
             self.wb = nn.Parameter(torch.FloatTensor([0.5, 0.5]), requires_grad=True)
 
     def forward(self, teacher_scores, student_scores):
-        if self.mode != 'listnet':
-            raise NotImplementedError(f"distillation mode {self.mode!r} is not ported yet (SURVEY §8(f) rank 3); "
-                                      "configs/*.yaml select 'listnet'")
         if not student_scores.is_cuda:
             student_scores = student_scores.cuda()
-        return _ListnetFn.apply(teacher_scores.detach().to(student_scores.device), student_scores)
+        teacher = teacher_scores.detach()                     # alad/loss.py:370
+        if self.mode == 'mse':
+            return _DistillMseFn.apply(teacher.to(student_scores.device), student_scores, self.wb)
+        elif self.mode == 'ordinal':
+            return _DistillOrdinalFn.apply(teacher.to(student_scores.device), student_scores, self.margin, self.threshold,
+                                           self.stride)
+        elif self.mode == 'contrastive':
+            return _DistillContrastiveFn.apply(teacher, student_scores, self.margin)
+        elif self.mode == 'listnet':
+            return _ListnetFn.apply(teacher.to(student_scores.device), student_scores)
+        # the reference falls through to `return loss` with loss unbound (alad/loss.py:447)
+        raise UnboundLocalError(f"DistillationLoss: unknown mode {self.mode!r}")

@@ -179,6 +179,18 @@ def scale_scores(S, mul=1.0, col_div=None):
     return S
 
 
+def unit_rows(x, eps=0.0):
+    """Rows of x [B,d] scaled to unit L2 norm (alad.utils.l2norm, no eps by default): fp32 [B,d] on the
+    device, produced by the pooling kernel with one token per item."""
+    B, d = x.shape
+    out = torch.empty((B, d), dtype=torch.float32, device=x.device)
+    if B:
+        cnt = torch.ones(B, dtype=torch.int32, device=x.device)
+        _cabi.check(_cabi.lib().alad_pool_tokens(x.data_ptr(), x.stride(0), d, B, 1, d, 0, cnt.data_ptr(), eps,
+                                                 out.data_ptr(), _cabi.stream_ptr()), "alad_pool_tokens")
+    return out
+
+
 def alignment_scores(im_set, s_seq, im_len, s_len, precision=None, out=None, aggregation="MrSw"):
     """Alignment scores S[B_i,B_c] of alad/loss.py:79-135 on the GPU, every tensor pooling mode:
     MrSw (max regions, sum words), MrAVGw (/ #words), MwSr (roles swapped), symm (MrSw + MwSr),

@@ -174,6 +174,53 @@ int alad_listnet_fwd_bwd(const float* teacher, int64_t ldT, const float* student
                          void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * The remaining DistillationLoss modes (alad/loss.py:371-425), forward + gradient in one call;
+ * workspace: alad_distill_workspace_bytes(B, mode) with mode 0 = mse, 1 = contrastive, 2 = ordinal.
+ * alad_distill_mse_fwd_bwd -- 'mse' (loss.py:371-373): loss = mean((student*wb[0] + wb[1] - teacher)^2);
+ *   wb is the module's DEVICE parameter [2]; dM (optional) = dloss/dstudent, dwb (optional) = dloss/dwb.
+ * alad_distill_contrastive_fwd_bwd -- 'contrastive' (loss.py:397-418): hinge on the student with the
+ *   hard negatives picked by the teacher (arg-max per row / column with the diagonal zeroed, first
+ *   occurrence); like the reference, WHOLE columns / rows of the un-cleared hinge matrices are
+ *   selected and summed.  zero_teacher_diag = 1 reproduces the reference's in-place
+ *   `teacher.masked_fill_(eye, 0)` side effect on the caller's matrix (loss.py:400).
+ * alad_distill_ordinal_fwd_bwd -- 'ordinal' (loss.py:374-396): per row and per column, the student
+ *   reordered by the ascending (stable) teacher order must keep that order by `margin` between
+ *   entries `stride` apart, counted where the later teacher value >= threshold; each direction is a
+ *   mean over its selected pairs (NaN when none, like torch).  B <= 16384.
+ * ------------------------------------------------------------------------------- */
+int64_t alad_distill_workspace_bytes(int32_t B, int32_t mode);
+int alad_distill_mse_fwd_bwd(const float* teacher, int64_t ldT, const float* student, int64_t ldM, int32_t B,
+                             const float* wb, float* loss, float* dM, int64_t ldG, float* dwb, void* workspace,
+                             void* stream);
+int alad_distill_contrastive_fwd_bwd(float* teacher, int64_t ldT, const float* student, int64_t ldM, int32_t B,
+                                     float margin, int32_t zero_teacher_diag, float* loss, float* dM, int64_t ldG,
+                                     void* workspace, void* stream);
+int alad_distill_ordinal_fwd_bwd(const float* teacher, int64_t ldT, const float* student, int64_t ldM, int32_t B,
+                                 float margin, float threshold, int32_t stride, float* loss, float* dM, int64_t ldG,
+                                 void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Similarity measures other than the dot product, and gradient helpers.
+ * alad_order_scores(_bwd) -- order_sim, alad/loss.py:20-26: scores[i, j] = -||max(0, s_j - im_i)||_2
+ *   (d_im [Ni, d], d_s [Nc, d] contiguous; entries with a zero score get no gradient).
+ * alad_normalize_bwd -- in place dx <- J(x) dx, J = Jacobian of x / max(||x||, eps) per row: with the two
+ *   GEMMs of dot_sim it is the gradient of cosine_sim (loss.py:13-18; eps = 0 like alad.utils.l2norm).
+ * alad_pool_tokens_bwd -- gradient of alad_pool_tokens: d_src[b, slot, :] = J(src[b, slot]) d_pool[b, :]
+ *   for slot0 <= slot < slot0 + count[b], 0 elsewhere (d_src contiguous [B, S, d]); serves the
+ *   'sum' / 'mean' aggregations of loss.py:120-123.
+ * ------------------------------------------------------------------------------- */
+int alad_order_scores(const float* im, int64_t ld_im, const float* s, int64_t ld_s, int32_t Ni, int32_t Nc, int32_t d,
+                      float* scores, int64_t ldS, void* stream);
+int alad_order_scores_bwd(const float* im, int64_t ld_im, const float* s, int64_t ld_s, int32_t Ni, int32_t Nc,
+                          int32_t d, const float* scores, int64_t ldS, const float* G, int64_t ldG, float* d_im,
+                          float* d_s, void* stream);
+int alad_normalize_bwd(const float* x, int64_t ld_x, int64_t rows, int32_t d, float eps, float* dx, int64_t ld_dx,
+                       void* stream);
+int alad_pool_tokens_bwd(const float* src, int64_t stride_b, int64_t stride_s, int32_t B, int32_t S, int32_t d,
+                         int32_t slot0, const int32_t* count, float eps, const float* d_pool, float* d_src,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Ranking -- replaces numpy.argsort + numpy.where of alad/evaluation.py:213-223,303-308
  * and alad/recall_auxiliary.py:34-56.  Order = score descending, index descending on
  * exact ties (= stable argsort reversed).  S is image-major [Ni, ldS]; ground truth of

@@ -272,6 +272,140 @@ def listnet_grad(teacher, student, temperature: float = 6.0, eps: float = 1e-10)
 
 
 # --------------------------------------------------------------------------------------
+# DistillationLoss, remaining modes (alad/loss.py:371-425) and their gradients
+# --------------------------------------------------------------------------------------
+
+
+def distill_mse(teacher, student, wb):
+    """mode 'mse' (alad/loss.py:371-373): mean((student*wb0 + wb1 - teacher)^2) over all B*B entries.
+    Returns (loss, d_student, d_wb) -- gradients in fp64, cast to fp32."""
+    T = np.asarray(teacher, dtype=np.float64)
+    M = np.asarray(student, dtype=np.float64)
+    w0, w1 = float(wb[0]), float(wb[1])
+    diff = M * w0 + w1 - T
+    n = diff.size
+    loss = (diff * diff).sum() / n
+    dM = (2.0 * w0 / n) * diff
+    dwb = np.array([(2.0 / n) * (diff * M).sum(), (2.0 / n) * diff.sum()])
+    return F32(loss), dM.astype(F32), dwb.astype(F32)
+
+
+def distill_contrastive(teacher, student, margin: float = 0.2):
+    """mode 'contrastive' (alad/loss.py:397-418).  The hard negatives come from the teacher with
+    its diagonal zeroed: ns[k] = argmax_j Tnd[k, j], ni[k] = argmax_i Tnd[i, k].  The reference then
+    index_selects WHOLE columns / rows of the (un-cleared) hinge matrices and sums everything:
+      loss = sum_i sum_k [m + M[i, ns[k]] - M[i, i]]_+  +  sum_k sum_j [m + M[ni[k], j] - M[j, j]]_+
+    (so the diagonal terms contribute the margin itself).  Returns (loss, d_student)."""
+    T = np.array(teacher, dtype=F32, copy=True)
+    M = np.asarray(student, dtype=F32)
+    B = T.shape[0]
+    T[np.eye(B, dtype=bool)] = 0
+    ns = T.argmax(axis=1)                      # first occurrence, like torch CPU
+    ni = T.argmax(axis=0)
+    diag = np.diag(M).astype(F32)
+    cost_s = np.maximum(F32(margin) + M - diag[:, None], F32(0))
+    cost_im = np.maximum(F32(margin) + M - diag[None, :], F32(0))
+    sel_s = cost_s[:, ns]                      # [B, B]: column ns[k] for every k
+    sel_im = cost_im[ni, :]
+    loss = F32(sel_s.sum(dtype=F32) + sel_im.sum(dtype=F32))
+    G = np.zeros((B, B), dtype=np.float64)
+    for k in range(B):
+        a = cost_s[:, ns[k]] > 0               # rows i with an active hinge on column ns[k]
+        G[a, ns[k]] += 1
+        G[np.arange(B)[a], np.arange(B)[a]] -= 1
+        b = cost_im[ni[k], :] > 0              # columns j with an active hinge on row ni[k]
+        G[ni[k], b] += 1
+        G[np.arange(B)[b], np.arange(B)[b]] -= 1
+    return loss, G.astype(F32)
+
+
+def distill_ordinal(teacher, student, margin: float = 0.2, threshold: float = 0.1, stride: int = 3):
+    """mode 'ordinal' (alad/loss.py:374-396): every row (column) of the student is reordered by the
+    ascending teacher order; entries `stride` apart must keep that order by `margin`, counted only
+    where the LATER teacher value is >= threshold.  Each direction is a mean over its selected
+    differences (NaN when nothing is selected, like torch's mean of an empty tensor).
+    Returns (loss, d_student)."""
+    T = np.asarray(teacher, dtype=F32)
+    M = np.asarray(student, dtype=np.float64)
+    G = np.zeros_like(M)
+    total = 0.0
+    for axis in (1, 0):
+        Tt = T if axis == 1 else T.T
+        Mt = M if axis == 1 else M.T
+        Gt = np.zeros_like(Mt)
+        order = np.argsort(Tt, axis=1, kind="stable")
+        Ts = np.take_along_axis(Tt, order, axis=1)
+        Ms = np.take_along_axis(Mt, order, axis=1)
+        diff = Ms[:, :-stride] - Ms[:, stride:]
+        valid = Ts[:, stride:] >= F32(threshold)
+        n = int(valid.sum())
+        if n == 0:
+            total = float("nan")
+            continue
+        h = margin + diff
+        total += np.where(valid, np.maximum(h, 0.0), 0.0).sum() / n
+        act = valid & (h > 0)
+        rows, pos = np.nonzero(act)
+        np.add.at(Gt, (rows, order[rows, pos]), 1.0 / n)
+        np.add.at(Gt, (rows, order[rows, pos + stride]), -1.0 / n)
+        G += Gt if axis == 1 else Gt.T
+    return F32(total), G.astype(F32)
+
+
+def order_scores(im, s):
+    """``order_sim`` (alad/loss.py:20-26): score[i, j] = -|| max(0, s_j - im_i) ||_2."""
+    im = np.asarray(im, F32)
+    s = np.asarray(s, F32)
+    y = np.maximum(s[None, :, :] - im[:, None, :], F32(0))
+    return (-np.sqrt((y * y).sum(axis=2, dtype=F32))).astype(F32)
+
+
+def cosine_backward(im, s, G):
+    """Gradient of sum(G * cosine_sim(im, s)) w.r.t. the raw inputs (alad/loss.py:13-18 through
+    alad.utils.l2norm, no eps), fp64 internally."""
+    im = np.asarray(im, np.float64)
+    s = np.asarray(s, np.float64)
+    G = np.asarray(G, np.float64)
+    ni = np.sqrt((im * im).sum(1, keepdims=True))
+    ns = np.sqrt((s * s).sum(1, keepdims=True))
+    ih, sh = im / ni, s / ns
+    d_ih, d_sh = G @ sh, G.T @ ih
+    d_im = (d_ih - ih * (ih * d_ih).sum(1, keepdims=True)) / ni
+    d_s = (d_sh - sh * (sh * d_sh).sum(1, keepdims=True)) / ns
+    return d_im.astype(F32), d_s.astype(F32)
+
+
+def pooled_sum_backward(im_set, s_seq, im_len, s_len, G, mean: bool = False):
+    """Gradient of sum(G * S) for aggregation 'sum' / 'mean' (alad/loss.py:120-123):
+    S[i,j] = <sum_r imhat(i,r), sum_w shat(j,w)> over the valid tokens (/ (R*W) for 'mean')."""
+    im_raw = np.asarray(im_set, dtype=np.float64)
+    s_raw = np.asarray(s_seq, dtype=np.float64)
+    G = np.asarray(G, dtype=np.float64)
+    R, W, nr, nw = scored_extents(im_raw.shape, s_raw.shape, im_len, s_len)
+    if mean:
+        G = G / max(R * W, 1)
+
+    def norm(x):
+        n = np.maximum(np.sqrt((x * x).sum(-1, keepdims=True)), 1e-12)
+        return x / n, n
+
+    imh, imn = norm(im_raw)
+    sh, sn = norm(s_raw)
+    rv = (np.arange(im_raw.shape[1])[None, :] >= 1) & (np.arange(im_raw.shape[1])[None, :] < 1 + nr[:, None])
+    wv = (np.arange(s_raw.shape[1])[None, :] >= 1) & (np.arange(s_raw.shape[1])[None, :] < 1 + nw[:, None])
+    pi = (imh * rv[:, :, None]).sum(1)          # [Bi,d]
+    ps = (sh * wv[:, :, None]).sum(1)           # [Bc,d]
+    d_pi, d_ps = G @ ps, G.T @ pi
+    d_imh = rv[:, :, None] * d_pi[:, None, :]
+    d_sh = wv[:, :, None] * d_ps[:, None, :]
+
+    def norm_bwd(xh, n, dxh):
+        return (dxh - xh * (xh * dxh).sum(-1, keepdims=True)) / n
+
+    return norm_bwd(imh, imn, d_imh).astype(F32), norm_bwd(sh, sn, d_sh).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
 # MrSw backward (SURVEY A.3): d im_set, d s_seq from G = dL/dS
 # --------------------------------------------------------------------------------------
 

@@ -266,6 +266,71 @@ def golden_train_step():
          d_cap_seq=ts[3].grad.numpy())
 
 
+# ---------------------------------------------------------------------------------------
+# 7. the remaining DistillationLoss modes (alad/loss.py:371-425) + gradients, order_sim,
+#    and the gradients of the 'sum' / 'mean' pooling modes
+# ---------------------------------------------------------------------------------------
+def golden_distill_modes():
+    r = rs(17)
+    B = 11
+    T = (r.standard_normal((B, B)) * 0.6 + 0.4).astype(np.float32)      # teacher: some entries below the 0.1 threshold
+    T[np.arange(B), np.arange(B)] += 1.0
+    M = np.clip(r.standard_normal((B, B)) * 0.35, -1, 1).astype(np.float32)
+    M[np.arange(B), np.arange(B)] += 0.3
+    out = {"T": T, "M": M}
+    # mse (owns the wb parameter)
+    dl = rloss.DistillationLoss(mode="mse")
+    with torch.no_grad():
+        dl.wb.copy_(torch.tensor([0.7, 0.25]))
+    M_t = t(M, True)
+    loss = dl(t(T), M_t)
+    loss.backward()
+    out.update(mse_wb=np.array([0.7, 0.25], np.float32), mse_loss=loss.detach().numpy(), mse_dM=M_t.grad.numpy(),
+               mse_dwb=dl.wb.grad.numpy())
+    # contrastive (hard negatives chosen by the teacher); the reference zeroes the teacher diagonal IN PLACE
+    for margin in (0.2, 0.05):
+        dl = rloss.DistillationLoss(mode="contrastive", margin=margin)
+        M_t = t(M, True)
+        T_t = t(T)
+        loss = dl(T_t, M_t)
+        loss.backward()
+        k = f"contrastive_m{margin}"
+        out.update({k + "_loss": loss.detach().numpy(), k + "_dM": M_t.grad.numpy(), k + "_T_after": T_t.numpy().copy()})
+    # ordinal, default and non-default stride / threshold
+    for (margin, thr, stride) in ((0.2, 0.1, 3), (0.1, 0.5, 1), (0.2, 100.0, 3)):
+        dl = rloss.DistillationLoss(mode="ordinal", margin=margin, threshold=thr, stride=stride)
+        M_t = t(M, True)
+        loss = dl(t(T), M_t)
+        k = f"ordinal_m{margin}_t{thr}_s{stride}"
+        if torch.isfinite(loss):
+            loss.backward()
+            out[k + "_dM"] = M_t.grad.numpy()
+        out[k + "_loss"] = loss.detach().numpy()
+    # order_sim forward (alad/loss.py:20-26)
+    im = np.abs(r.standard_normal((7, 20))).astype(np.float32)
+    s = np.abs(r.standard_normal((9, 20))).astype(np.float32)
+    out.update(order_im=im, order_s=s, order_S=rloss.order_sim(t(im), t(s)).numpy())
+    save("distill_modes", **out)
+
+
+def golden_pooled_grads():
+    r = rs(18)
+    Bi, Bc, S_im, S_s, d = 4, 5, 7, 9, 24
+    im = r.standard_normal((Bi, S_im, d)).astype(np.float32) * 1.3
+    s = r.standard_normal((Bc, S_s, d)).astype(np.float32) * 0.8
+    im_len = [7, 3, 5, 7]
+    s_len = [9, 5, 4, 9, 7]
+    Gup = r.standard_normal((Bi, Bc)).astype(np.float32)
+    out = dict(im=im, s=s, im_len=np.array(im_len), s_len=np.array(s_len), Gup=Gup)
+    for agg in ("sum", "mean", "MrAVGw", "MwSr", "symm"):
+        im_t, s_t = t(im, True), t(s, True)
+        crit = rloss.AlignmentContrastiveLoss(aggregation=agg)
+        S = crit(im_t, s_t, im_len, s_len, return_loss=False, return_similarity_mat=True)
+        (S * t(Gup)).sum().backward()
+        out.update({f"S_{agg}": S.detach().numpy(), f"dim_{agg}": im_t.grad.numpy(), f"ds_{agg}": s_t.grad.numpy()})
+    save("pooled_grads", **out)
+
+
 if __name__ == "__main__":
     golden_alignment_scores()
     golden_alignment_loss()
@@ -273,3 +338,5 @@ if __name__ == "__main__":
     golden_triplet_listnet()
     golden_retrieval()
     golden_train_step()
+    golden_distill_modes()
+    golden_pooled_grads()

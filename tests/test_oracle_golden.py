@@ -146,3 +146,61 @@ def test_train_step_composite_matches_reference():
     d_im, d_s = O.mrsw_backward(im, s, il, cl, O.triplet_grad(T, 0.2, True))
     np.testing.assert_allclose(np.transpose(d_im, (1, 0, 2)), g["d_img_set"], rtol=1e-4, atol=2e-6)
     np.testing.assert_allclose(np.transpose(d_s, (1, 0, 2)), g["d_cap_seq"], rtol=1e-4, atol=2e-6)
+
+
+# ------------------------------------------------------------------ remaining distillation modes
+def test_distill_mse_matches_reference():
+    g = load_golden("distill_modes")
+    loss, dM, dwb = O.distill_mse(g["T"], g["M"], g["mse_wb"])
+    np.testing.assert_allclose(loss, g["mse_loss"], rtol=1e-6)
+    np.testing.assert_allclose(dM, g["mse_dM"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(dwb, g["mse_dwb"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("margin", [0.2, 0.05])
+def test_distill_contrastive_matches_reference(margin):
+    g = load_golden("distill_modes")
+    loss, dM = O.distill_contrastive(g["T"], g["M"], margin)
+    k = f"contrastive_m{margin}"
+    np.testing.assert_allclose(loss, g[k + "_loss"], rtol=1e-6)
+    np.testing.assert_array_equal(dM, g[k + "_dM"])                  # integer-valued gradient
+    # the reference zeroes the caller's teacher diagonal in place (alad/loss.py:400)
+    assert np.all(np.diag(g[k + "_T_after"]) == 0)
+
+
+@pytest.mark.parametrize("margin,thr,stride", [(0.2, 0.1, 3), (0.1, 0.5, 1)])
+def test_distill_ordinal_matches_reference(margin, thr, stride):
+    g = load_golden("distill_modes")
+    loss, dM = O.distill_ordinal(g["T"], g["M"], margin, thr, stride)
+    k = f"ordinal_m{margin}_t{thr}_s{stride}"
+    np.testing.assert_allclose(loss, g[k + "_loss"], rtol=1e-6)
+    np.testing.assert_allclose(dM, g[k + "_dM"], rtol=1e-6, atol=1e-9)
+
+
+def test_distill_ordinal_empty_selection_is_nan_like_reference():
+    g = load_golden("distill_modes")
+    loss, _ = O.distill_ordinal(g["T"], g["M"], 0.2, 100.0, 3)
+    assert np.isnan(loss) and np.isnan(g["ordinal_m0.2_t100.0_s3_loss"])
+
+
+def test_order_sim_matches_reference():
+    g = load_golden("distill_modes")
+    np.testing.assert_allclose(O.order_scores(g["order_im"], g["order_s"]), g["order_S"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("agg", ["sum", "mean"])
+def test_pooled_sum_backward_matches_reference(agg):
+    g = load_golden("pooled_grads")
+    d_im, d_s = O.pooled_sum_backward(g["im"], g["s"], g["im_len"].tolist(), g["s_len"].tolist(), g["Gup"], mean=agg == "mean")
+    np.testing.assert_allclose(d_im, g["dim_" + agg], rtol=1e-4, atol=1e-6 * np.abs(g["dim_" + agg]).max())
+    np.testing.assert_allclose(d_s, g["ds_" + agg], rtol=1e-4, atol=1e-6 * np.abs(g["ds_" + agg]).max())
+
+
+@pytest.mark.parametrize("key", ["cosine_mv", "cosine_sum"])
+def test_cosine_backward_matches_reference(key):
+    g = load_golden("matching")
+    im = g["im"] * 2.5
+    G = O.triplet_grad(g["S_" + key], 0.2, key.endswith("mv"))
+    d_im, d_s = O.cosine_backward(im, g["s"], G)
+    np.testing.assert_allclose(d_im, g["dim_" + key], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(d_s, g["ds_" + key], rtol=1e-4, atol=1e-6)
