@@ -57,6 +57,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// Prefetch one box of a tiled tensor into L2 (no shared-memory destination, no completion signal).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // L2 eviction-priority policies for the TMA loads: the streamed operand is marked evict_first,
 // the operand block that is re-read by every tile of a sweep evict_last.
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {

@@ -32,6 +32,9 @@ def _find_scorer(fn):
 
 
 def _key(images, captions, img_lens, cap_lens, mode, precision):
+    from .gallery import DeviceContainer
+    if isinstance(images, DeviceContainer):
+        return (id(images), id(captions), images.packed.data.data_ptr(), captions.packed.data.data_ptr(), mode, precision)
     return (images.data_ptr(), captions.data_ptr(), tuple(images.shape), tuple(captions.shape), images._version,
             captions._version, hash(tuple(img_lens)), hash(tuple(cap_lens)), mode, precision)
 
@@ -78,8 +81,15 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
     Ni = images.shape[0] // 5
     world, rank, group = (1, 0, None)
     img_off = 0
+    from .gallery import DeviceContainer
+    if isinstance(images, DeviceContainer) and mode == "callback":
+        raise TypeError("DeviceContainer galleries hold packed tokens only: pass sim_function=None or a closure over "
+                        "aladin_b200.loss.AlignmentContrastiveLoss('MrSw')")
     if mode == "global":
-        S = scoring.dot_scores(images[0::5][:, 0, :], captions[:, 0, :], precision=precision)
+        if isinstance(images, DeviceContainer):
+            S = scoring.dot_scores(images[:, 0, :][0::5], captions[:, 0, :], precision=precision)
+        else:
+            S = scoring.dot_scores(images[0::5][:, 0, :], captions[:, 0, :], precision=precision)
     elif mode == "fused":
         world, rank, group = _dist_state()
         gal = retrieval.AlignmentGallery(images, captions, img_lens, cap_lens, n_images=Ni, img_start=0, img_step=5,

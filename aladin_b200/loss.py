@@ -316,6 +316,40 @@ class _DistillOrdinalFn(torch.autograd.Function):
         return None, dM * g, None, None, None
 
 
+def alignment_backward(im_c, s_c, nr, nw, W, agg, G1=None, G0=None, g0_scale=None):
+    """(d im_set, d s_seq) of the alignment scores for dL/dS = g0_scale * G0 + G1, every pooling mode
+    of alad/loss.py:120-135 (im_c / s_c: raw fp32 CUDA tokens; nr / nw: valid scored counts)."""
+    if agg == "MrSw":
+        return mrsw_backward(im_c, s_c, nr, nw, G0=G0, g0_scale=g0_scale, G1=G1)
+    G = G0 * g0_scale if G0 is not None and g0_scale is not None else G0
+    if G1 is not None:
+        G = G1 if G is None else G + G1
+    if agg in ("sum", "mean"):
+        # S = <pool(im), pool(s)> (/ (R*W)): two small GEMMs + the pooled-token Jacobian kernel
+        if agg == "mean":
+            G = G / max((im_c.shape[1] - 1) * W, 1)
+        G = G.contiguous()
+        pi, ps = scoring.pool_tokens(im_c, nr), scoring.pool_tokens(s_c, nw)
+        d_pi = scoring.dot_scores(G, ps.t().contiguous(), precision="fp32")
+        d_ps = scoring.dot_scores(G.t().contiguous(), pi.t().contiguous(), precision="fp32")
+        return pool_tokens_bwd(im_c, nr, d_pi), pool_tokens_bwd(s_c, nw, d_ps)
+    d_im = d_s = None
+    if agg in ("MrAVGw", "symm"):
+        Gm = G
+        if agg == "MrAVGw":
+            Gm = G / scoring._to_dev(np.asarray(nw, np.float32), G.device)[None, :]
+            Gm = torch.nan_to_num(Gm, nan=0.0, posinf=0.0, neginf=0.0)
+        d_im, d_s = mrsw_backward(im_c, s_c, nr, nw, G1=Gm.contiguous())
+    if agg in ("MwSr", "symm"):
+        # roles swapped: max over words (clamped when nw < W), sum over regions
+        d_s2, d_im2 = mrsw_backward(s_c, im_c, nw, nr, G1=G.t().contiguous(), region_extent=max(W, 1))
+        d_im = d_im2 if d_im is None else d_im + d_im2
+        d_s = d_s2 if d_s is None else d_s + d_s2
+    if d_im is None:
+        raise ValueError(f"unsupported aggregation {agg!r}")
+    return d_im, d_s
+
+
 class _AlignmentFn(torch.autograd.Function):
     """(loss, S) = alignment scores + hinge; backward recomputes only the pairs whose dL/dS != 0."""
 
@@ -344,38 +378,10 @@ class _AlignmentFn(torch.autograd.Function):
         none = (None,) * 9
         if not use_G0 and g_S is None:
             return none
-        agg = ctx.aggregation
-        if agg in ("sum", "mean"):
-            # S = <pool(im), pool(s)> (/ (R*W)): two small GEMMs + the pooled-token Jacobian kernel
-            G = G0 * g_loss.detach().float() if use_G0 else None
-            if g_S is not None:
-                G = g_S.detach().float() if G is None else G + g_S.detach().float()
-            if agg == "mean":
-                G = G / max((im_c.shape[1] - 1) * ctx.W, 1)
-            G = G.contiguous()
-            pi, ps = scoring.pool_tokens(im_c, ctx.nr), scoring.pool_tokens(s_c, ctx.nw)
-            d_pi = scoring.dot_scores(G, ps.t().contiguous(), precision="fp32")
-            d_ps = scoring.dot_scores(G.t().contiguous(), pi.t().contiguous(), precision="fp32")
-            d_im = pool_tokens_bwd(im_c, ctx.nr, d_pi)
-            d_s = pool_tokens_bwd(s_c, ctx.nw, d_ps)
-        elif agg == "MrSw":
-            g_scale = g_loss.detach().float().reshape(1).contiguous() if use_G0 else None
-            G1 = g_S.detach().float().contiguous() if g_S is not None else None
-            d_im, d_s = mrsw_backward(im_c, s_c, ctx.nr, ctx.nw, G0=G0 if use_G0 else None, g0_scale=g_scale, G1=G1)
-        else:
-            G = G0 * g_loss.detach().float() if use_G0 else None
-            if g_S is not None:
-                G = g_S.detach().float() if G is None else G + g_S.detach().float()
-            d_im = d_s = None
-            if agg in ("MrAVGw", "symm"):
-                Gm = G / scoring._to_dev(ctx.nw.astype(np.float32), G.device)[None, :] if agg == "MrAVGw" else G
-                Gm = torch.nan_to_num(Gm, nan=0.0, posinf=0.0, neginf=0.0) if agg == "MrAVGw" else Gm
-                d_im, d_s = mrsw_backward(im_c, s_c, ctx.nr, ctx.nw, G1=Gm.contiguous())
-            if agg in ("MwSr", "symm"):
-                # roles swapped: max over words (clamped when nw < W), sum over regions
-                d_s2, d_im2 = mrsw_backward(s_c, im_c, ctx.nw, ctx.nr, G1=G.t().contiguous(), region_extent=max(ctx.W, 1))
-                d_im = d_im2 if d_im is None else d_im + d_im2
-                d_s = d_s2 if d_s is None else d_s + d_s2
+        g_scale = g_loss.detach().float().reshape(1).contiguous() if use_G0 else None
+        G1 = g_S.detach().float().contiguous() if g_S is not None else None
+        d_im, d_s = alignment_backward(im_c, s_c, ctx.nr, ctx.nw, ctx.W, ctx.aggregation, G1, G0=G0 if use_G0 else None,
+                                       g0_scale=g_scale)
         return (d_im.to(ctx.devices[0]) if ctx.needs_input_grad[0] else None,
                 d_s.to(ctx.devices[1]) if ctx.needs_input_grad[1] else None) + none[2:]
 

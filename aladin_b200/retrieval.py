@@ -57,6 +57,17 @@ class AlignmentGallery:
                  precision=None, world=1, rank=0, caption_chunk=4096, caption_phases=4):
         if not torch.cuda.is_available():
             raise _cabi.AladError("aladin_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        from .gallery import DeviceContainer
+        self.prepacked = isinstance(images, DeviceContainer)
+        if self.prepacked != isinstance(captions, DeviceContainer):
+            raise TypeError("images and captions must both be DeviceContainers (gallery.encode_data) or both tensors")
+        if self.prepacked:
+            if images.precision != captions.precision:
+                raise ValueError("image and caption containers were packed with different precisions")
+            if (img_start, img_step) not in ((0, 5), (0, 1)):
+                raise ValueError("DeviceContainer images are the distinct gallery images (rows 0::5)")
+            precision = images.precision            # the packed operands fix the mode
+            img_step = 5
         self.precision = precision or scoring.get_precision()
         self.images, self.captions = images, captions
         self.Ni, self.Nc = int(n_images), int(captions.shape[0])
@@ -117,6 +128,15 @@ class AlignmentGallery:
         n_loc = hi - lo
         dev = torch.device("cuda", torch.cuda.current_device())
         S = torch.empty((n_loc, self.Nc), dtype=torch.float32, device=dev)
+        if self.prepacked:
+            # backbone outputs were packed on the device by gallery.GalleryWriter: no upload, no pack
+            if n_loc == 0 or self.Nc == 0:
+                return S
+            regions, nr_loc = self.images.rows_of(lo, hi)
+            assert np.array_equal(nr_loc, self.nr[lo:hi]) and np.array_equal(self.captions.counts, self.nw)
+            _, table, _ = build_region_tiles(nr_loc, self.clamp[lo:hi])
+            tiles_dev = scoring._to_dev(table.view(np.int32).reshape(-1), dev) if len(table) else None
+            return scoring.mrsw_scores_packed(self.captions.packed, regions, tiles_dev, len(table), n_loc, self.Nc, out=S)
         shard_caps = (group is not None and self.world > 1 and not self.captions.is_cuda and dist.is_initialized())
         if (n_loc == 0 and not shard_caps) or self.Nc == 0:
             return S

@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cublas-probe", action="store_true",
+                    help="skip the same-box cuBLAS bf16 sustained-GEMM probe reported beside the roofline (context only)")
     return ap.parse_args()
 
 
@@ -296,6 +298,17 @@ def main():
             img_lens5 = [l for l in im_len for _ in range(5)]
         v, desc, cores = cpu_baseline_sample(imgs_h.numpy(), caps_h.numpy(), img_lens5, s_len, args.cpu_seconds)
         cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc}
+
+    # ---- context for the roofline: cuBLAS bf16 GEMM sustained on THIS box (after all timed regions)
+    if rank == 0 and world == 1 and not args.no_cublas_probe:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import cublas_probe
+            probe = cublas_probe.sustained_bf16_tflops(2.5)
+            roofline["same_box_cublas_bf16_tflops_sustained"] = probe["cublas_bf16_tflops_sustained"]
+            roofline["frac_of_same_box_cublas"] = achieved / probe["cublas_bf16_tflops_sustained"]
+        except Exception as e:      # the probe is context, never a reason to lose the bench line
+            roofline["same_box_cublas_bf16_tflops_sustained"] = f"probe failed: {e}"
 
     if rank == 0:
         line = {"metric": "alignment_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,

@@ -1,0 +1,53 @@
+"""Multi-GPU parity check, run under torchrun on N GPUs of one box:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/dist_check.py
+Every rank runs the public drop-ins (aladin_b200.evaluation.i2t / t2i) on the same seeded host
+containers with the gallery images sharded across the ranks (NCCL exchange of ground-truth
+scores, counts and top-50 candidates), then recomputes everything unsharded on its own GPU and
+requires identical ranks / top-1 / top-50 / metrics."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from aladin_b200 import evaluation, loss as L, retrieval, synth
+    ok = True
+    for seed, Ni, d, mr, mw, precision in ((5, 203, 128, 36, 30, "fp32"), (6, 640, 256, 34, 50, "bf16")):
+        images, captions, img_lens, cap_lens = synth.eval_containers(seed, Ni, 71, d, max_regions=mr, max_words=mw)
+        ti, tc = torch.from_numpy(images).pin_memory(), torch.from_numpy(captions).pin_memory()
+        crit = L.AlignmentContrastiveLoss(aggregation="MrSw")
+        crit.precision = precision
+        evaluation.clear_cache()
+        mi, (ri, t1) = evaluation.i2t(ti, tc, img_lens, cap_lens, return_ranks=True, sim_function=crit, cap_batches=5)
+        mt, (rt, t50) = evaluation.t2i(ti, tc, img_lens, cap_lens, return_ranks=True, sim_function=crit, im_batches=5)
+        # unsharded on this GPU
+        gal = retrieval.AlignmentGallery(ti, tc, img_lens, cap_lens, n_images=Ni, img_start=0, img_step=5,
+                                         precision=precision, world=1, rank=0)
+        S = gal.scores()
+        ri1, t11, rt1, t501 = retrieval.rank_both_directions(S, Ni, k=50, group=None)
+        same = (np.array_equal(ri, ri1) and np.array_equal(t1, t11) and np.array_equal(rt, rt1) and np.array_equal(t50, t501)
+                and mi[:5] == retrieval.recall_tuple(ri1) and mt[:5] == retrieval.recall_tuple(rt1))
+        print(f"[rank {rank}/{world}] Ni={Ni} {precision}: sharded == unsharded: {same}; i2t R@1 {mi[0]:.1f} t2i R@1 {mt[0]:.1f}",
+              flush=True)
+        ok = ok and same
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if int(flag.item()) != 1:
+        sys.exit(1)
+    if rank == 0:
+        print("dist_check ok")
+
+
+if __name__ == "__main__":
+    main()

@@ -69,7 +69,8 @@ def main():
                 os.environ["ALAD_N_BLOCK"] = str(mb - 1000)
             else:
                 os.environ.pop("ALAD_N_BLOCK", None)
-            os.environ["ALAD_L2_HINTS"] = str(h)
+            os.environ["ALAD_L2_HINTS"] = str(h & 3)
+            os.environ["ALAD_L2_PREFETCH"] = "1" if h & 4 else "0"     # hints bit 2 = word-row L2 prefetch
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()
