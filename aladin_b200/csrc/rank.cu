@@ -139,7 +139,35 @@ col_count_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int
 
 // ------------------------------------------------------------------ t2i step 3: running top-k per caption
 // One warp per (32 captions, row slice); thread <-> caption (coalesced 128 B row reads).
-// The k-best buffer lives in shared memory, laid out [k][32] so lane == bank.
+// The k best entries of every caption live in a binary MIN-heap (root = worst kept entry) in
+// shared memory, laid out [k][32] so that lane == bank whatever node a lane touches.  An insertion
+// costs <= log2(k) levels instead of a k-entry rescan; the final order comes from k heap pops.
+__device__ __forceinline__ void heap_sift_down(float* bs, int* bi, int k, int lane, float v, int vi) {
+  int j = 0;
+  while (true) {
+    const int l = 2 * j + 1;
+    if (l >= k) break;
+    float cs = bs[l * 32 + lane];
+    int ci = bi[l * 32 + lane];
+    int cj = l;
+    if (l + 1 < k) {
+      const float rs = bs[(l + 1) * 32 + lane];
+      const int ri = bi[(l + 1) * 32 + lane];
+      if (ahead(cs, ci, rs, ri)) {          // the right child is the worse one
+        cs = rs;
+        ci = ri;
+        cj = l + 1;
+      }
+    }
+    if (!ahead(v, vi, cs, ci)) break;       // (v, vi) is not better than the worse child: it stays above
+    bs[j * 32 + lane] = cs;
+    bi[j * 32 + lane] = ci;
+    j = cj;
+  }
+  bs[j * 32 + lane] = v;
+  bi[j * 32 + lane] = vi;
+}
+
 __global__ void __launch_bounds__(32)
 col_topk_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int k, int img_off, int splits,
                 float* __restrict__ cand_score, int* __restrict__ cand_idx) {
@@ -152,13 +180,12 @@ col_topk_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int 
   const int per = (Ni + splits - 1) / splits;
   const int r_begin = split * per;
   const int r_end = min(Ni, r_begin + per);
-  for (int j = 0; j < k; ++j) {
+  for (int j = 0; j < k; ++j) {             // k "empty" entries: every real entry is ahead of (-inf, -1)
     bs[j * 32 + lane] = -INFINITY;
     bi[j * 32 + lane] = -1;
   }
-  float ws = -INFINITY;   // worst entry currently kept
+  float ws = -INFINITY;   // root of the heap = worst entry currently kept
   int wi = -1;
-  int wj = 0;
   const bool col_ok = c < Nc;
   const float* col = S + (col_ok ? c : 0);
   for (int r = r_begin; r < r_end; r += 4) {
@@ -169,45 +196,22 @@ col_topk_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int 
     for (int u = 0; u < 4; ++u) {
       const int gi = img_off + r + u;
       if (col_ok && r + u < r_end && ahead(v[u], gi, ws, wi)) {
-        bs[wj * 32 + lane] = v[u];
-        bi[wj * 32 + lane] = gi;
-        // rescan for the new worst entry
+        heap_sift_down(bs, bi, k, lane, v[u], gi);          // replaces the root
         ws = bs[lane];
         wi = bi[lane];
-        wj = 0;
-        for (int j = 1; j < k; ++j) {
-          const float s = bs[j * 32 + lane];
-          const int ii = bi[j * 32 + lane];
-          if (ahead(ws, wi, s, ii)) {
-            ws = s;
-            wi = ii;
-            wj = j;
-          }
-        }
       }
     }
   }
   if (!col_ok) return;
-  // selection sort into the output (best first)
+  // heap sort: pop the worst entry k times, filling the output from the back (best first)
   float* out_s = cand_score + ((long long)split * Nc + c) * k;
   int* out_i = cand_idx + ((long long)split * Nc + c) * k;
-  for (int o = 0; o < k; ++o) {
-    float s0 = bs[lane];
-    int i0 = bi[lane];
-    int j0 = 0;
-    for (int j = 1; j < k; ++j) {
-      const float s = bs[j * 32 + lane];
-      const int ii = bi[j * 32 + lane];
-      if (ahead(s, ii, s0, i0)) {
-        s0 = s;
-        i0 = ii;
-        j0 = j;
-      }
-    }
-    out_s[o] = s0;
-    out_i[o] = i0;
-    bs[j0 * 32 + lane] = -INFINITY;
-    bi[j0 * 32 + lane] = -2;          // consumed: ordered after every real or empty (-1) entry
+  for (int n = k; n > 0; --n) {
+    out_s[n - 1] = bs[lane];
+    out_i[n - 1] = bi[lane];
+    const float ls = bs[(n - 1) * 32 + lane];
+    const int li = bi[(n - 1) * 32 + lane];
+    if (n > 1) heap_sift_down(bs, bi, n - 1, lane, ls, li);
   }
 }
 

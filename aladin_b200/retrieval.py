@@ -250,32 +250,48 @@ def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=No
     if dist_on:
         dist.all_reduce(gt, group=group)                       # every entry is owned by exactly one shard
     count = ops.col_count(Sq, gt, 5, img_off)
-    k_eff = k
-    cs, ci = ops.col_topk(Sq, k_eff, img_off)
+    cs, ci = ops.col_topk(Sq, k, img_off)
     ts, ti = ops.topk_merge(cs, ci)
     if dist_on:
         world = dist.get_world_size(group)
-        dist.all_reduce(count, group=group)
-        gs = [torch.empty_like(ts) for _ in range(world)]
-        gi = [torch.empty_like(ti) for _ in range(world)]
-        dist.all_gather(gs, ts, group=group)
-        dist.all_gather(gi, ti, group=group)
-        ts, ti = ops.topk_merge(torch.stack(gs).contiguous(), torch.stack(gi).contiguous())
+        # per-shard k-best lists -> every rank, then one merge of `world` sorted lists per caption
+        gs = torch.empty((world * ts.shape[0], ts.shape[1]), dtype=ts.dtype, device=S.device)
+        gi = torch.empty((world * ti.shape[0], ti.shape[1]), dtype=ti.dtype, device=S.device)
+        dist.all_gather_into_tensor(gs, ts.contiguous(), group=group)       # output = concatenation along dim 0
+        dist.all_gather_into_tensor(gi, ti.contiguous(), group=group)
+        ts, ti = ops.topk_merge(gs.view(world, *ts.shape), gi.view(world, *ti.shape))
+        # counts (summed over the shards) and the i2t results of every image block in one small gather
+        per = (Ni_total + world - 1) // world
+        small = torch.full((ncq + 2 * per,), -1, dtype=torch.int32, device=S.device)
+        small[:ncq] = count
+        small[ncq:ncq + q_loc] = rank_i
+        small[ncq + per:ncq + per + q_loc] = top1_i
+        gsm = torch.empty((world * (ncq + 2 * per),), dtype=torch.int32, device=S.device)
+        dist.all_gather_into_tensor(gsm, small, group=group)
+        gsm = gsm.view(world, ncq + 2 * per)
+        count = gsm[:, :ncq].sum(dim=0, dtype=torch.int32)
         if gather_i2t:
-            per = (Ni_total + world - 1) // world
-            pad_r = torch.full((per,), -1, dtype=torch.int32, device=S.device)
-            pad_t = torch.full((per,), -1, dtype=torch.int32, device=S.device)
-            pad_r[:q_loc] = rank_i
-            pad_t[:q_loc] = top1_i
-            gr = [torch.empty_like(pad_r) for _ in range(world)]
-            gt1 = [torch.empty_like(pad_t) for _ in range(world)]
-            dist.all_gather(gr, pad_r, group=group)
-            dist.all_gather(gt1, pad_t, group=group)
-            rank_i = torch.cat(gr)[:npts]
-            top1_i = torch.cat(gt1)[:npts]
-    out = (rank_i.cpu().numpy().astype(np.float64), top1_i.cpu().numpy().astype(np.float64),
-           count.cpu().numpy().astype(np.float64), ti.cpu().numpy().astype(np.float64))
-    return out
+            rank_i = gsm[:, ncq:ncq + per].reshape(-1)[:npts]
+            top1_i = gsm[:, ncq + per:].reshape(-1)[:npts]
+    return _to_host_f64(rank_i, top1_i, count, ti)
+
+
+def _to_host_f64(*tensors):
+    """Device int tensors -> float64 numpy arrays (the reference returns numpy.zeros-typed arrays:
+    alad/evaluation.py:166-167,255-256) with ONE device->host copy into pinned memory and one sync."""
+    if not tensors[0].is_cuda:
+        return tuple(t.numpy().astype(np.float64) for t in tensors)
+    sizes = [t.numel() for t in tensors]
+    flat = torch.cat([t.reshape(-1).to(torch.float64) for t in tensors])
+    host = torch.empty(flat.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(flat, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out, o = [], 0
+    arr = host.numpy()
+    for t, n in zip(tensors, sizes):
+        out.append(arr[o:o + n].reshape(tuple(t.shape)))
+        o += n
+    return tuple(out)
 
 
 def recall_tuple(ranks):
