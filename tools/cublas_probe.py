@@ -16,17 +16,21 @@ def sustained_bf16_tflops(seconds=3.0, n=8192):
     for _ in range(5):
         torch.matmul(a, b, out=c)
     torch.cuda.synchronize()
+    # calibrate, then queue the whole run without host round trips (a busy host must not starve the GPU)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters, t0 = 0, time.perf_counter()
     e0.record()
-    while time.perf_counter() - t0 < seconds:
-        for _ in range(20):
-            torch.matmul(a, b, out=c)
-        iters += 20
-        torch.cuda.synchronize()
+    for _ in range(10):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    iters = max(20, int(seconds * 1e3 / (e0.elapsed_time(e1) / 10)))
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    time.sleep(seconds * 0.7)
     clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-i", "0"],
                          capture_output=True, text=True).stdout.strip()
-    e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     return {"cublas_bf16_tflops_sustained": 2.0 * n ** 3 * iters / (ms * 1e-3) / 1e12, "seconds": ms * 1e-3,
