@@ -204,3 +204,23 @@ def test_cosine_backward_matches_reference(key):
     d_im, d_s = O.cosine_backward(im, g["s"], G)
     np.testing.assert_allclose(d_im, g["dim_" + key], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(d_s, g["ds_" + key], rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------ torch-CPU port used as the timed CPU baseline
+def test_torch_port_matches_reference_golden():
+    import torch
+    from oracle import alad_torch_port as TP
+    g = load_golden("alignment_scores")
+    S = TP.alignment_scores(torch.from_numpy(g["im"]), torch.from_numpy(g["s"]), g["im_len"].tolist(), g["s_len"].tolist())
+    np.testing.assert_allclose(S.numpy(), g["S_MrSw"], rtol=2e-5, atol=2e-6)
+    r = load_golden("retrieval")
+    images = np.repeat(r["images"], 5, axis=0)
+    il, cl = r["img_lens"].tolist(), r["cap_lens"].tolist()
+    m_i, (ranks_i, top1) = TP.i2t(images, r["captions"], il, cl, cap_batches=5)
+    m_t, (ranks_t, top50) = TP.t2i(images, r["captions"], il, cl, im_batches=5)
+    np.testing.assert_array_equal(ranks_i, r["ranks_i2t"])
+    np.testing.assert_array_equal(top1, r["top1"])
+    np.testing.assert_array_equal(ranks_t, r["ranks_t2i"])
+    np.testing.assert_array_equal(top50, r["top50"])
+    np.testing.assert_allclose(m_i[:5], r["m_i2t"][:5])
+    np.testing.assert_allclose(m_t[:5], r["m_t2i"][:5])
