@@ -193,6 +193,8 @@ def main():
     torch.cuda.set_device(local_rank)
     import torch.distributed as dist
     if world > 1:
+        # NCCL prints its version banner (and any NCCL_DEBUG output) on stdout; keep stdout for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     group = dist.group.WORLD if world > 1 else None
     import aladin_b200
