@@ -102,7 +102,7 @@ def lib():
 # kernels launched per successful entry-point call (bench.py reports the total as gpu_launches)
 KERNELS_PER_CALL = {
     "alad_h2d_2d": 0, "alad_pack_tokens": 1, "alad_pool_tokens": 1, "alad_scale_scores": 1, "alad_mrsw_scores_fwd": 1, "alad_mrsw_scores_bwd": 6,
-    "alad_triplet_fwd_bwd": 2, "alad_listnet_fwd_bwd": 2, "alad_rank_rows": 1, "alad_col_gt": 1,
+    "alad_triplet_fwd_bwd": 2, "alad_listnet_fwd_bwd": 3, "alad_rank_rows": 1, "alad_col_gt": 1,
     "alad_col_count": 1, "alad_col_topk": 1, "alad_topk_merge": 1, "alad_shortlist_scatter": 2,
     "alad_distill_mse_fwd_bwd": 1, "alad_distill_contrastive_fwd_bwd": 2, "alad_distill_ordinal_fwd_bwd": 2,
     "alad_order_scores": 1, "alad_order_scores_bwd": 1, "alad_normalize_bwd": 1, "alad_pool_tokens_bwd": 1,

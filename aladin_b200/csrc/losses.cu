@@ -2,8 +2,10 @@
 //   alad_triplet_fwd_bwd  -- VSE++ hinge with hardest negatives, alad/loss.py:42-67
 //   alad_listnet_fwd_bwd  -- ListNet distillation, alad/loss.py:427-445 (teacher detached :370)
 // Row direction: one CTA per row, coalesced 128-bit-friendly sweeps, warp-shuffle reductions.
-// Column direction: 32-column strips x 8 row slices per CTA (coalesced 128 B row segments).
-// The loss scalar is reduced in a fixed order by the last CTA to finish (deterministic).
+// Column direction: 32-column strips x 8 row slices per CTA (coalesced 128 B row segments), the rows
+// split into chunks of chunk_rows_of(B) along the grid so that large B fills the machine; per-chunk partial
+// results are combined in a fixed order.  The loss scalar is reduced in a fixed order by the last
+// CTA to finish (deterministic).
 #include <math.h>
 
 #include "common.h"
@@ -12,6 +14,16 @@ namespace alad {
 
 constexpr int LT = 256;          // threads per CTA
 constexpr int CS = 8;            // row slices of a column-strip CTA
+constexpr int CV = 4;            // 32-column groups per column-strip CTA (4 x 128 B contiguous per visited row)
+constexpr int SW = 32 * CV;      // columns per strip
+__host__ __device__ inline int n_strips_of(int B) { return (B + SW - 1) / SW; }
+// rows per column-strip CTA: B/16 rounded up to a multiple of CS, within [32, 256] -- enough CTAs to fill the
+// machine at B = 512 without long partial lists at B = 8192
+__host__ __device__ inline int chunk_rows_of(int B) {
+  const int r = ((B + 15) / 16 + CS - 1) / CS * CS;
+  return r < 32 ? 32 : (r > 256 ? 256 : r);
+}
+__host__ __device__ inline int n_chunks_of(int B) { return (B + chunk_rows_of(B) - 1) / chunk_rows_of(B); }
 
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -72,6 +84,20 @@ __device__ __forceinline__ bool last_cta_done(unsigned int* counter) {
   return is_last;
 }
 
+// true in every thread of the LAST of `expected` CTAs to arrive on `counter` (which is re-armed to 0)
+__device__ __forceinline__ bool last_of_group(unsigned int* counter, unsigned int expected) {
+  __shared__ bool group_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    group_last = (atomicAdd(counter, 1u) == expected - 1);
+    if (group_last) *counter = 0;
+  }
+  __syncthreads();
+  if (group_last) __threadfence();
+  return group_last;
+}
+
 __global__ void diag_kernel(const float* __restrict__ S, long long ld, int B, float* __restrict__ diag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) diag[i] = S[(long long)i * ld + i];
@@ -93,14 +119,17 @@ struct TripletParams {
   float* colval;
   int* rowarg;         // max_violation: hardest negative (-1 = none); sum mode: #violations
   int* colarg;
+  float* cpart_val;    // [n_chunks][B] per-chunk column partials (best value / hinge sum)
+  int* cpart_arg;      // [n_chunks][B]                           (arg-max row / violation count)
+  unsigned int* strip_cnt;   // [n_strips] arrivals of the chunk CTAs of a 32-column strip
   unsigned int* counter;
 };
 
 __global__ void __launch_bounds__(LT) triplet_kernel(const TripletParams p) {
   __shared__ float sf[LT / 32];
   __shared__ int si[LT / 32];
-  __shared__ float cv[CS][32];
-  __shared__ int ci[CS][32];
+  __shared__ float cv[CS][SW];
+  __shared__ int ci[CS][SW];
   const int B = p.B;
   if ((int)blockIdx.x < B) {
     // ---------------- row direction: cost_s[i, j] = [margin + S_ij - S_ii]_+ (caption retrieval)
@@ -146,36 +175,78 @@ __global__ void __launch_bounds__(LT) triplet_kernel(const TripletParams p) {
   } else {
     // ---------------- column direction: cost_im[i, j] = [margin + S_ij - S_jj]_+ (image retrieval)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = (blockIdx.x - B) * 32 + tx;
-    float best = 0.f, sum = 0.f;
-    int barg = B, cnt = 0;
-    if (j < B) {
-      const float djj = p.diag[j];
-      for (int i = ty; i < B; i += CS) {
-        const float c_i = (i == j) ? 0.f : fmaxf(p.margin + __ldg(p.S + (long long)i * p.ld + j) - djj, 0.f);
+    const int n_strips = n_strips_of(B);
+    const int cta = blockIdx.x - B;
+    const int strip = cta % n_strips, chunk = cta / n_strips;
+    const int j0 = strip * SW + tx;                   // this thread's columns: j0 + 32 * u
+    const int chunk_rows = chunk_rows_of(B);
+    const int r_end = min(B, (chunk + 1) * chunk_rows);
+    float best[CV], sum[CV], djj[CV];
+    int barg[CV], cnt[CV];
+#pragma unroll
+    for (int u = 0; u < CV; ++u) {
+      best[u] = 0.f; sum[u] = 0.f; barg[u] = B; cnt[u] = 0;
+      djj[u] = (j0 + 32 * u < B) ? p.diag[j0 + 32 * u] : 0.f;
+    }
+    for (int i = chunk * chunk_rows + ty; i < r_end; i += CS) {
+      const float* row = p.S + (long long)i * p.ld;
+      float v[CV];
+#pragma unroll
+      for (int u = 0; u < CV; ++u) v[u] = (j0 + 32 * u < B) ? __ldg(row + j0 + 32 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < CV; ++u) {
+        const int j = j0 + 32 * u;
+        const float c_i = (i == j || j >= B) ? 0.f : fmaxf(p.margin + v[u] - djj[u], 0.f);
         if (p.max_violation) {
-          argmax_combine(best, barg, c_i, i);
+          argmax_combine(best[u], barg[u], c_i, i);
         } else {
-          sum += c_i;
-          cnt += c_i > 0.f;
+          sum[u] += c_i;
+          cnt[u] += c_i > 0.f;
         }
       }
     }
-    cv[ty][tx] = p.max_violation ? best : sum;
-    ci[ty][tx] = p.max_violation ? barg : cnt;
+#pragma unroll
+    for (int u = 0; u < CV; ++u) {
+      cv[ty][tx + 32 * u] = p.max_violation ? best[u] : sum[u];
+      ci[ty][tx + 32 * u] = p.max_violation ? barg[u] : cnt[u];
+    }
     __syncthreads();
-    if (ty == 0 && j < B) {
-      if (p.max_violation) {
-        for (int y = 1; y < CS; ++y) argmax_combine(best, barg, cv[y][tx], ci[y][tx]);
-        p.colval[j] = best;
-        p.colarg[j] = best > 0.f ? barg : -1;
-      } else {
+    if (ty < CV) {                                    // warp ty finishes column group ty
+      const int c = tx + 32 * ty, j = strip * SW + c;
+      if (j < B) {
+        float v = cv[0][c];
+        int a = ci[0][c];
         for (int y = 1; y < CS; ++y) {
-          sum += cv[y][tx];
-          cnt += ci[y][tx];
+          if (p.max_violation) {
+            argmax_combine(v, a, cv[y][c], ci[y][c]);
+          } else {
+            v += cv[y][c];
+            a += ci[y][c];
+          }
         }
-        p.colval[j] = sum;
-        p.colarg[j] = cnt;
+        p.cpart_val[(long long)chunk * B + j] = v;
+        p.cpart_arg[(long long)chunk * B + j] = a;
+      }
+    }
+    // the last chunk CTA of this strip combines the partials in chunk order (ties: lower row index wins)
+    const int nch = n_chunks_of(B);
+    if (last_of_group(p.strip_cnt + strip, nch) && ty < CV) {
+      const int j = strip * SW + tx + 32 * ty;
+      if (j < B) {
+        float v = __ldcg(p.cpart_val + j);
+        int a = __ldcg(p.cpart_arg + j);
+        for (int ch = 1; ch < nch; ++ch) {
+          const float ov = __ldcg(p.cpart_val + (long long)ch * B + j);
+          const int oa = __ldcg(p.cpart_arg + (long long)ch * B + j);
+          if (p.max_violation) {
+            argmax_combine(v, a, ov, oa);
+          } else {
+            v += ov;
+            a += oa;
+          }
+        }
+        p.colval[j] = v;
+        p.colarg[j] = p.max_violation ? (v > 0.f ? a : -1) : a;
       }
     }
   }
@@ -242,6 +313,8 @@ struct ListnetParams {
   float* cstat;        // [B][5]                          (column direction, dim=0)
   float* rcost;        // [B]
   float* ccost;        // [B]
+  float* cpart;        // [n_chunks][B][4] per-chunk column partials: softmax stats, then (cost, A)
+  unsigned int* strip_cnt;   // [n_strips]
   unsigned int* counter;
 };
 
@@ -258,8 +331,7 @@ __device__ __forceinline__ void listnet_elem(float xm, float xt, const SoftStats
 __global__ void __launch_bounds__(LT) listnet_stats_kernel(const ListnetParams p) {
   __shared__ float sf[LT / 32];
   __shared__ float sm[4][LT / 32];
-  __shared__ float cs[CS][32][4];
-  __shared__ SoftStats fin[32];
+  __shared__ float cs[CS][SW][4];
   const int B = p.B;
   if ((int)blockIdx.x < B) {
     // ---------------- row i: softmax over j (sentence retrieval, dim=1)
@@ -306,48 +378,148 @@ __global__ void __launch_bounds__(LT) listnet_stats_kernel(const ListnetParams p
       p.rcost[i] = ctot;
     }
   } else {
-    // ---------------- 32 columns: softmax over i (image retrieval, dim=0)
+    // ---------------- SW columns x one row chunk: partial softmax statistics over i (image retrieval, dim=0)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = (blockIdx.x - B) * 32 + tx;
-    float ms = -INFINITY, zs = 0.f, mt = -INFINITY, zt = 0.f;
-    if (j < B) {
-      for (int i = ty; i < B; i += CS) {
-        online_update(ms, zs, p.tau * __ldg(p.M + (long long)i * p.ldM + j));
-        online_update(mt, zt, __ldg(p.T + (long long)i * p.ldT + j));
+    const int n_strips = n_strips_of(B);
+    const int cta = blockIdx.x - B;
+    const int strip = cta % n_strips, chunk = cta / n_strips;
+    const int j0 = strip * SW + tx;
+    const int chunk_rows = chunk_rows_of(B);
+    const int r_end = min(B, (chunk + 1) * chunk_rows);
+    float ms[CV], zs[CV], mt[CV], zt[CV];
+#pragma unroll
+    for (int u = 0; u < CV; ++u) {
+      ms[u] = -INFINITY; zs[u] = 0.f; mt[u] = -INFINITY; zt[u] = 0.f;
+    }
+    for (int i = chunk * chunk_rows + ty; i < r_end; i += CS) {
+      const float* rm = p.M + (long long)i * p.ldM;
+      const float* rt = p.T + (long long)i * p.ldT;
+      float vm[CV], vt[CV];
+#pragma unroll
+      for (int u = 0; u < CV; ++u) {
+        const bool ok = j0 + 32 * u < B;
+        vm[u] = ok ? __ldg(rm + j0 + 32 * u) : 0.f;
+        vt[u] = ok ? __ldg(rt + j0 + 32 * u) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < CV; ++u) {
+        online_update(ms[u], zs[u], p.tau * vm[u]);
+        online_update(mt[u], zt[u], vt[u]);
       }
     }
-    cs[ty][tx][0] = ms; cs[ty][tx][1] = zs; cs[ty][tx][2] = mt; cs[ty][tx][3] = zt;
-    __syncthreads();
-    if (ty == 0) {
-      for (int y = 1; y < CS; ++y) {
-        online_merge(ms, zs, cs[y][tx][0], cs[y][tx][1]);
-        online_merge(mt, zt, cs[y][tx][2], cs[y][tx][3]);
-      }
-      fin[tx].m_s = ms; fin[tx].z_s = zs; fin[tx].m_t = mt; fin[tx].z_t = zt;
+#pragma unroll
+    for (int u = 0; u < CV; ++u) {
+      float* c = cs[ty][tx + 32 * u];
+      c[0] = ms[u]; c[1] = zs[u]; c[2] = mt[u]; c[3] = zt[u];
     }
     __syncthreads();
-    const SoftStats st = fin[tx];
-    float cost = 0.f, A = 0.f;
-    if (j < B) {
-      for (int i = ty; i < B; i += CS) {
+    if (ty < CV) {
+      const int c = tx + 32 * ty, j = strip * SW + c;
+      if (j < B) {
+        float a0 = cs[0][c][0], a1 = cs[0][c][1], a2 = cs[0][c][2], a3 = cs[0][c][3];
+        for (int y = 1; y < CS; ++y) {
+          online_merge(a0, a1, cs[y][c][0], cs[y][c][1]);
+          online_merge(a2, a3, cs[y][c][2], cs[y][c][3]);
+        }
+        float* o = p.cpart + 4 * ((long long)chunk * B + j);
+        o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
+      }
+    }
+    // the last chunk CTA of this strip merges the partial statistics in chunk order
+    const int nch = n_chunks_of(B);
+    if (last_of_group(p.strip_cnt + strip, nch) && ty < CV) {
+      const int j = strip * SW + tx + 32 * ty;
+      if (j < B) {
+        float a = -INFINITY, b = 0.f, c = -INFINITY, d = 0.f;
+        for (int ch = 0; ch < nch; ++ch) {
+          const float* o = p.cpart + 4 * ((long long)ch * B + j);
+          online_merge(a, b, __ldcg(o), __ldcg(o + 1));
+          online_merge(c, d, __ldcg(o + 2), __ldcg(o + 3));
+        }
+        float* o = p.cstat + 5 * (long long)j;
+        o[0] = a; o[1] = b; o[2] = c; o[3] = d;
+      }
+    }
+  }
+}
+
+// second column pass: final statistics of every column (merge of the chunk partials, fixed order), then the
+// chunk's share of cost and A = sum t*p/(p+eps); the last CTA adds the shares up and writes the loss
+__global__ void __launch_bounds__(LT) listnet_colcost_kernel(const ListnetParams p) {
+  __shared__ float sf[LT / 32];
+  __shared__ float cs[CS][SW][2];
+  __shared__ SoftStats fin[SW];
+  const int B = p.B;
+  const int nch = n_chunks_of(B);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n_strips = n_strips_of(B);
+  const int strip = blockIdx.x % n_strips, chunk = blockIdx.x / n_strips;
+  const int j0 = strip * SW + tx;
+  const int chunk_rows = chunk_rows_of(B);
+  const int r_end = min(B, (chunk + 1) * chunk_rows);
+  if (ty < CV) {
+    const int c = tx + 32 * ty, j = strip * SW + c;
+    const float* o = p.cstat + 5 * (long long)(j < B ? j : 0);
+    fin[c].m_s = o[0]; fin[c].z_s = o[1]; fin[c].m_t = o[2]; fin[c].z_t = o[3];
+  }
+  __syncthreads();
+  SoftStats st[CV];
+  float cost[CV], A[CV];
+#pragma unroll
+  for (int u = 0; u < CV; ++u) {
+    st[u] = fin[tx + 32 * u];
+    cost[u] = 0.f;
+    A[u] = 0.f;
+  }
+  for (int i = chunk * chunk_rows + ty; i < r_end; i += CS) {
+    const float* rm = p.M + (long long)i * p.ldM;
+    const float* rt = p.T + (long long)i * p.ldT;
+    float vm[CV], vt[CV];
+#pragma unroll
+    for (int u = 0; u < CV; ++u) {
+      const bool ok = j0 + 32 * u < B;
+      vm[u] = ok ? __ldg(rm + j0 + 32 * u) : 0.f;
+      vt[u] = ok ? __ldg(rt + j0 + 32 * u) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < CV; ++u) {
+      if (j0 + 32 * u < B) {
         float c, a, pr;
-        listnet_elem(__ldg(p.M + (long long)i * p.ldM + j), __ldg(p.T + (long long)i * p.ldT + j), st, p.tau, p.eps,
-                     c, a, pr);
-        cost += c;
-        A += a;
+        listnet_elem(vm[u], vt[u], st[u], p.tau, p.eps, c, a, pr);
+        cost[u] += c;
+        A[u] += a;
       }
     }
-    __syncthreads();
-    cs[ty][tx][0] = cost; cs[ty][tx][1] = A;
-    __syncthreads();
-    if (ty == 0 && j < B) {
+  }
+#pragma unroll
+  for (int u = 0; u < CV; ++u) {
+    cs[ty][tx + 32 * u][0] = cost[u];
+    cs[ty][tx + 32 * u][1] = A[u];
+  }
+  __syncthreads();
+  float* share = p.cpart;      // the statistic partials are dead by now: reuse the buffer as [n_chunks][B][2]
+  if (ty < CV) {
+    const int c = tx + 32 * ty, j = strip * SW + c;
+    if (j < B) {
+      float ct = cs[0][c][0], at = cs[0][c][1];
       for (int y = 1; y < CS; ++y) {
-        cost += cs[y][tx][0];
-        A += cs[y][tx][1];
+        ct += cs[y][c][0];
+        at += cs[y][c][1];
       }
-      float* o = p.cstat + 5 * (long long)j;
-      o[0] = st.m_s; o[1] = st.z_s; o[2] = st.m_t; o[3] = st.z_t; o[4] = A;
-      p.ccost[j] = cost;
+      share[2 * ((long long)chunk * B + j)] = ct;
+      share[2 * ((long long)chunk * B + j) + 1] = at;
+    }
+  }
+  if (last_of_group(p.strip_cnt + strip, nch) && ty < CV) {
+    const int j = strip * SW + tx + 32 * ty;
+    if (j < B) {
+      float ct = 0.f, at = 0.f;
+      for (int ch = 0; ch < nch; ++ch) {
+        ct += __ldcg(share + 2 * ((long long)ch * B + j));
+        at += __ldcg(share + 2 * ((long long)ch * B + j) + 1);
+      }
+      p.cstat[5 * (long long)j + 4] = at;
+      p.ccost[j] = ct;
     }
   }
   if (!last_cta_done(p.counter)) return;
@@ -378,8 +550,10 @@ __global__ void __launch_bounds__(LT) listnet_grad_kernel(const ListnetParams p)
 }  // namespace alad
 
 extern "C" int64_t alad_loss_workspace_bytes(int32_t B) {
-  // generous upper bound shared by both losses: 12 arrays of B 4-byte words + counter + padding
-  return (int64_t)12 * 4 * (B > 0 ? B : 1) + 256;
+  // shared by both losses: 12 arrays of B 4-byte words + counter + padding, plus the per-chunk column
+  // partials (listnet: 4 + 2 floats, triplet: 2 words per chunk and column)
+  const int64_t b = B > 0 ? B : 1;
+  return 12 * 4 * b + 256 + 6 * 4 * b * alad::n_chunks_of((int)b) + 4 * ((b + 31) / 32) + 64;
 }
 
 extern "C" int alad_triplet_fwd_bwd(const float* S, int64_t ldS, int32_t B, float margin, int32_t max_violation,
@@ -400,9 +574,14 @@ extern "C" int alad_triplet_fwd_bwd(const float* S, int64_t ldS, int32_t B, floa
   p.diag = w; p.rowval = w + B; p.colval = w + 2 * (size_t)B;
   p.rowarg = row_arg; p.colarg = col_arg;
   p.counter = reinterpret_cast<unsigned int*>(w + 3 * (size_t)B);
+  const int nch = n_chunks_of(B);
+  p.cpart_val = w + 12 * (size_t)B + 64;
+  p.cpart_arg = reinterpret_cast<int*>(p.cpart_val + (size_t)nch * B);
+  p.strip_cnt = reinterpret_cast<unsigned int*>(p.cpart_val + 6 * (size_t)nch * B);
   ALAD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
+  ALAD_CUDA(cudaMemsetAsync(p.strip_cnt, 0, sizeof(unsigned int) * (size_t)((B + 31) / 32), st));
   diag_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, ldS, B, p.diag);
-  triplet_kernel<<<B + (B + 31) / 32, LT, 0, st>>>(p);
+  triplet_kernel<<<B + n_strips_of(B) * nch, LT, 0, st>>>(p);
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;
 }
@@ -425,8 +604,13 @@ extern "C" int alad_listnet_fwd_bwd(const float* teacher, int64_t ldT, const flo
   p.loss = loss; p.dM = dM; p.ldG = ldG;
   p.rstat = w; p.cstat = w + 5 * (size_t)B; p.rcost = w + 10 * (size_t)B; p.ccost = w + 11 * (size_t)B;
   p.counter = reinterpret_cast<unsigned int*>(w + 12 * (size_t)B);
+  const int nch = n_chunks_of(B);
+  p.cpart = w + 12 * (size_t)B + 64;
+  p.strip_cnt = reinterpret_cast<unsigned int*>(p.cpart + 6 * (size_t)nch * B);
   ALAD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
-  listnet_stats_kernel<<<B + (B + 31) / 32, LT, 0, st>>>(p);
+  ALAD_CUDA(cudaMemsetAsync(p.strip_cnt, 0, sizeof(unsigned int) * (size_t)((B + 31) / 32), st));
+  listnet_stats_kernel<<<B + n_strips_of(B) * nch, LT, 0, st>>>(p);
+  listnet_colcost_kernel<<<n_strips_of(B) * nch, LT, 0, st>>>(p);
   if (dM) {
     dim3 grid((B + LT - 1) / LT, B);
     listnet_grad_kernel<<<grid, LT, 0, st>>>(p);
