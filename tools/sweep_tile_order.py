@@ -2,7 +2,7 @@
 at COCO-5k shape: the operands are packed once, every configuration is launched in rotation
 (ABCABC...) so that thermal / power-cap drift hits all of them alike; per launch: CUDA-event time,
 SM clock and board power sampled by nvidia-smi while the kernel runs.
-usage: python tools/sweep_tile_order.py [rounds] [Ni] [Nc]"""
+usage: python tools/sweep_tile_order.py [rounds] [Ni] [Nc] [fp32]"""
 import json
 import os
 import subprocess
@@ -44,10 +44,11 @@ def main():
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     Ni = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
     Nc = int(sys.argv[3]) if len(sys.argv) > 3 else 25000
+    split = len(sys.argv) > 4 and sys.argv[4] == "fp32"       # 3x split-precision operands (Kp = 3 * d)
     images, captions, im_len, s_len = synth.dense_gallery_device(Ni, Nc, 34, 50, 1024)
     R, W, nr, nw, clamp = scoring.scored_counts(images.shape, captions.shape, im_len, s_len)
-    words = scoring.pack_tokens(captions, nw, slot0=1, want_row_item=True)
-    regions = scoring.pack_tokens(images, nr, slot0=1)
+    words = scoring.pack_tokens(captions, nw, slot0=1, mode=1 if split else 0, want_row_item=True)
+    regions = scoring.pack_tokens(images, nr, slot0=1, mode=2 if split else 0)
     _, table, _ = build_region_tiles(nr, clamp)
     tiles_dev = scoring._to_dev(table.view(np.int32).reshape(-1), images.device)
     del images, captions
@@ -56,7 +57,7 @@ def main():
     if os.environ.get("SWEEP_CONFIGS"):
         configs = [tuple(int(x) for x in c.split(":")) for c in os.environ["SWEEP_CONFIGS"].split(",")]
     smi = Smi()
-    flops = 2.0 * 34 * 50 * 1024 * Ni * Nc
+    flops = 2.0 * 34 * 50 * 1024 * Ni * Nc * (3 if split else 1)       # issued FLOP in split mode
     res = {c: [] for c in configs}
     # warm-up
     for _ in range(3):
