@@ -170,8 +170,10 @@ def main():
         img_lens5 = [l for l in im_len for _ in range(5)]
         vals = []
         desc = cores = None
+        # every step is a bounded sample; the whole --steps/--warmup run stays within a few minutes
+        per_step = min(args.cpu_seconds, 150.0 / max(args.steps + args.warmup, 1))
         for it in range(args.warmup + args.steps):
-            budget = args.cpu_seconds if it >= args.warmup else min(args.cpu_seconds, 5.0)
+            budget = per_step if it >= args.warmup else min(per_step, 5.0)
             v, desc, cores = cpu_baseline_sample(imgs_h.numpy(), caps_h.numpy(), img_lens5, s_len, budget)
             if it >= args.warmup:
                 vals.append(v)
