@@ -37,6 +37,8 @@ def build(force=False, verbose=False):
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES]
+    if os.environ.get("ALAD_NVCC_EXTRA"):               # experiments: extra -D flags
+        cmd += os.environ["ALAD_NVCC_EXTRA"].split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -41,7 +41,10 @@ static_assert(NTILE_WORDS <= 32, "one lane per table word");
 // cuts the shared-memory fill per SM from 46 KB to 31 KB per K block and leaves room for 6 stages.
 template <int CG>
 struct Cfg {
-  static constexpr int STAGES = CG == 2 ? 6 : 4;
+#ifndef ALAD_STAGES_CG2
+#define ALAD_STAGES_CG2 6
+#endif
+  static constexpr int STAGES = CG == 2 ? ALAD_STAGES_CG2 : 4;
   static constexpr int B_ROWS = BN / CG;                       // region rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;

@@ -255,18 +255,21 @@ def main():
     k_pairs = sum(ni * nc for _, _, ni, nc, _ in timeline)
     k_mult = 3.0 if args.precision == "fp32" else 1.0
     achieved = k_pairs * FLOP_PER_PAIR(regions, words, d) / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    traffic = None
+    traffic = traffic_detail = None       # DRAM read + write bytes of ONE launch from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(f"{args.workload}_{args.precision}_n{world}")
+            traffic_detail = json.load(f).get(f"{args.workload}_{args.precision}_n{world}")
+        if traffic_detail:
+            traffic = traffic_detail.get("bytes")
     roofline = {"kernel": "alad::mrsw_fwd_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"] if pk["bf16_sustained"] else None,
                 "peak_burst": pk["bf16_burst"], "frac_of_burst": achieved / pk["bf16_burst"] if pk["bf16_burst"] else None,
                 "peak_source": pk["source"] + "; sustained figure: the kernel runs ~0.3 s per launch inside the step",
                 "launches": len(timeline), "avg_launch_ms": k_ms / max(len(timeline), 1),
                 "algorithmic_flop_per_launch": k_pairs * FLOP_PER_PAIR(regions, words, d) / max(len(timeline), 1),
-                "issued_flop_multiplier": k_mult, "kernel_share_of_step": k_ms / (ms_step * args.steps), "traffic": traffic}
+                "issued_flop_multiplier": k_mult, "kernel_share_of_step": k_ms / (ms_step * args.steps), "traffic": traffic,
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_detail": traffic_detail}
 
     # ---- end to end through the public drop-ins, host tensors in the reference layout
     e2e = None
