@@ -44,18 +44,25 @@ struct Cfg {
 #ifndef ALAD_STAGES_CG2
 #define ALAD_STAGES_CG2 6
 #endif
+#ifndef ALAD_RES_KB
+#define ALAD_RES_KB 0
+#endif
   static constexpr int STAGES = CG == 2 ? ALAD_STAGES_CG2 : 4;
+  // K blocks of the region tile kept RESIDENT in shared memory across consecutive tiles (CTA pairs in the
+  // lock-step tile order meet the same region tile for a whole sweep): those B loads are skipped
+  static constexpr int RES = CG == 2 ? ALAD_RES_KB : 0;
   static constexpr int B_ROWS = BN / CG;                       // region rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
-  static constexpr int OFF_V = OFF_B + STAGES * B_BYTES;
+  static constexpr int OFF_RES = OFF_B + STAGES * B_BYTES;
+  static constexpr int OFF_V = OFF_RES + RES * B_BYTES;
   static constexpr int OFF_CAP = OFF_V + 2 * V_BYTES;          // int capS[2][128]
   static constexpr int OFF_TAB = OFF_CAP + 2 * BM * 4;         // uint32 tab[4 warps][32]
   static constexpr int OFF_RUN = OFF_TAB + EPI_WARPS * 32 * 4; // uint32 run_start_mask[2][4]
   static constexpr int OFF_BAR = OFF_RUN + 2 * EPI_WARPS * 4;  // mbarriers
-  static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
+  static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES + 2;   // + resident full / empty
   static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_USED = OFF_TMEMPTR + 16;
   static constexpr int SMEM_BYTES = SMEM_USED + 1024;          // slack for manual 1024 B alignment
@@ -78,15 +85,22 @@ struct MrswParams {
   int n_block;      // N tiles swept per pass over the M tiles (their region rows stay hot in L2)
   int l2_hints;     // TMA L2 policies: bit 0 = words evict_first, bit 1 = region block evict_last
   int l2_prefetch;  // 1: the CTAs cooperatively prefetch the next M unit's word rows into L2
+  int b_resident;   // 1: keep the first Cfg::RES K blocks of the unit's region tile resident in shared memory
 };
 
-__device__ __forceinline__ void tile_coord(int t, int n_mtiles, int n_ntiles, int n_block, int& mt, int& nt) {
+// full = the tile lies in a complete block of n_block region tiles (the last block may be shorter)
+__device__ __forceinline__ void tile_coord(int t, int n_mtiles, int n_ntiles, int n_block, int& mt, int& nt, bool& full) {
   const int per_block = n_mtiles * n_block;
   const int nb = t / per_block;
   const int rem = t - nb * per_block;
   const int nb_size = min(n_block, n_ntiles - nb * n_block);
   mt = rem / nb_size;
   nt = nb * n_block + (rem - mt * nb_size);
+  full = nb_size == n_block;
+}
+__device__ __forceinline__ void tile_coord(int t, int n_mtiles, int n_ntiles, int n_block, int& mt, int& nt) {
+  bool full;
+  tile_coord(t, n_mtiles, n_ntiles, n_block, mt, nt, full);
 }
 
 template <int CG>
@@ -104,6 +118,10 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;
+  uint64_t* res_full = bars + 2 * STAGES + 2 * ACC_STAGES;
+  uint64_t* res_empty = res_full + 1;
+  const bool use_res = C::RES > 0 && p.b_resident != 0;
+  const int res_kb = min(C::RES, p.num_kb);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEMPTR);
 
   const int warp = threadIdx.x >> 5;
@@ -126,6 +144,8 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], EPI_THREADS * CG);   // the leader's copy collects both CTAs' epilogues
     }
+    mbar_init(res_full, 1);
+    mbar_init(res_empty, 1);
     fence_mbar_init();
   }
   if (warp == 5) {
@@ -149,13 +169,27 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
       uint32_t phase = 0;
       // the word rows stream past once per region block; the region block is re-read by every M unit
       const bool hints = p.l2_hints != 0;
+      int res_nt = -1;
+      uint32_t res_loads = 0;
       const uint64_t pol_words = (p.l2_hints & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
       const uint64_t pol_regions = (p.l2_hints & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
       for (int t = unit; t < total_tiles; t += n_units) {
         int mu, nt;
-        tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt);
+        bool full_block;
+        tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt, full_block);
+        const bool res_t = CG == 2 && use_res && full_block;    // resident rows only where the unit keeps its tile
         const int n_row0 = __ldg(&p.ntiles[nt].row_start) + cta_rank * C::B_ROWS;
         const int m_row0 = (mu * CG + cta_rank) * BM;
+        if (res_t && nt != res_nt) {
+          // new region tile for this unit: wait until the MMAs of the previous one have read the resident
+          // rows (in both CTAs), then load the first res_kb K blocks once
+          if (res_loads > 0) mbar_wait(res_empty, (res_loads - 1) & 1u);
+          if (leader) mbar_expect_tx(res_full, 2 * res_kb * C::B_BYTES);
+          for (int kb = 0; kb < res_kb; ++kb)
+            tma_load_2d_cg2(smem + C::OFF_RES + kb * C::B_BYTES, &map_regions, res_full, kb * BK, n_row0);
+          res_nt = nt;
+          ++res_loads;
+        }
         if (p.l2_prefetch && t + n_units < total_tiles) {
           // All units sweep the M units in near lock step, so the word rows of the next M unit are
           // about to be requested by every SM at once; concurrent first-touch misses on the same
@@ -177,13 +211,14 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
           uint8_t* sb = smem + C::OFF_B + stage * C::B_BYTES;
           if (CG == 2) {
             // completion bytes of BOTH CTAs are credited to the leader's barrier
-            if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            const bool b_ring = !(res_t && kb < res_kb);       // resident K blocks need no B load
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * (A_BYTES + (b_ring ? C::B_BYTES : 0)));
             if (hints) {
               tma_load_2d_cg2_hint(sa, &map_words, &full_bar[stage], kb * BK, m_row0, pol_words);
-              tma_load_2d_cg2_hint(sb, &map_regions, &full_bar[stage], kb * BK, n_row0, pol_regions);
+              if (b_ring) tma_load_2d_cg2_hint(sb, &map_regions, &full_bar[stage], kb * BK, n_row0, pol_regions);
             } else {
               tma_load_2d_cg2(sa, &map_words, &full_bar[stage], kb * BK, m_row0);
-              tma_load_2d_cg2(sb, &map_regions, &full_bar[stage], kb * BK, n_row0);
+              if (b_ring) tma_load_2d_cg2(sb, &map_regions, &full_bar[stage], kb * BK, n_row0);
             }
           } else {
             mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
@@ -210,9 +245,26 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      int res_nt = -1;
+      uint32_t res_loads = 0;
       for (int t = unit; t < total_tiles; t += n_units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
+        int nt = 0, nt_next = -1;
+        bool res_t = false;
+        if (CG == 2 && use_res) {
+          int mu;
+          bool full_block, full_next = false;
+          tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt, full_block);
+          if (t + n_units < total_tiles) tile_coord(t + n_units, n_munits, p.n_ntiles, p.n_block, mu, nt_next, full_next);
+          if (!full_next) nt_next = -1;                // the next tile does not use the resident rows
+          res_t = full_block;
+          if (res_t && nt != res_nt) {                 // first tile on a new region tile: wait for its resident rows
+            mbar_wait(res_full, res_loads & 1u);
+            res_nt = nt;
+            ++res_loads;
+          }
+        }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
@@ -220,7 +272,9 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem + C::OFF_A + stage * A_BYTES));
-          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem + C::OFF_B + stage * C::B_BYTES));
+          const uint64_t b_desc = (res_t && kb < res_kb)
+                                      ? make_sw128_kmajor_desc(smem_u32(smem + C::OFF_RES + kb * C::B_BYTES))
+                                      : make_sw128_kmajor_desc(smem_u32(smem + C::OFF_B + stage * C::B_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // +32 B per K step inside the 128 B swizzle row: start-address field is in 16 B units
@@ -236,6 +290,8 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
         }
         // accumulator complete -> epilogue warps (of both CTAs)
         if (CG == 2) umma_commit_cg2_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+        // last tile on this region tile: the resident rows may be overwritten once these MMAs are done
+        if (res_t && nt_next != nt) umma_commit_cg2_both(res_empty);
       }
     }
     __syncwarp();
@@ -558,6 +614,9 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
     // tile per unit): measured +0.6 % at 74 tiles / bf16, but -8 % at 148 tiles and -19 % at 37 tiles / 3x split
     const char* ep = getenv("ALAD_L2_PREFETCH");
     p.l2_prefetch = ep ? atoi(ep) : (p.n_block == units_in_flight ? 1 : 0);
+    // resident region K blocks (compile-time Cfg<2>::RES > 0): only where a unit keeps its region tile
+    const char* er = getenv("ALAD_B_RESIDENT");
+    p.b_resident = er ? atoi(er) : (p.n_block > 0 && units_in_flight % p.n_block == 0 ? 1 : 0);
   }
 
   cudaLaunchConfig_t cfg = {};
