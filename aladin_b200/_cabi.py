@@ -31,6 +31,20 @@ class MrswFwdArgs(C.Structure):
     ]
 
 
+class ScoresFusedArgs(C.Structure):
+    _fields_ = [
+        ("max_x", C.c_void_p), ("max_stride_b", C.c_int64), ("max_stride_s", C.c_int64),
+        ("sum_x", C.c_void_p), ("sum_stride_b", C.c_int64), ("sum_stride_s", C.c_int64),
+        ("n_max", C.c_int32), ("S_max", C.c_int32), ("slot0_max", C.c_int32),
+        ("n_sum", C.c_int32), ("S_sum", C.c_int32), ("slot0_sum", C.c_int32),
+        ("d", C.c_int32),
+        ("max_count", C.c_void_p), ("sum_count", C.c_void_p), ("max_clamp", C.c_void_p),
+        ("precision", C.c_int32), ("epilogue", C.c_int32), ("normalize", C.c_int32), ("eps", C.c_float),
+        ("S", C.c_void_p), ("ldS", C.c_int64), ("transpose_out", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 class MrswBwdArgs(C.Structure):
     _fields_ = [
         ("im", C.c_void_p), ("im_stride_b", C.c_int64), ("im_stride_s", C.c_int64),
@@ -41,6 +55,8 @@ class MrswBwdArgs(C.Structure):
         ("d_im", C.c_void_p), ("d_s", C.c_void_p), ("eps", C.c_float), ("region_extent", C.c_int32),
         ("max_pairs", C.c_int64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("d_im_stride_b", C.c_int64), ("d_im_stride_s", C.c_int64),
+        ("d_s_stride_b", C.c_int64), ("d_s_stride_s", C.c_int64),
     ]
 
 
@@ -50,8 +66,11 @@ PROTOTYPES = {
     "alad_abi_version": (C.c_int, []),
     "alad_last_error": (C.c_char_p, []),
     "alad_h2d_2d": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P]),
+    "alad_region_tiles": (C.c_int, [_P, _P, _I32, _P, _I32, _P]),
     "alad_pack_tokens": (C.c_int, [C.POINTER(PackArgs), _P]),
     "alad_mrsw_scores_fwd": (C.c_int, [C.POINTER(MrswFwdArgs), _P]),
+    "alad_scores_fused_workspace_bytes": (C.c_int64, [_I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32]),
+    "alad_scores_fused": (C.c_int, [C.POINTER(ScoresFusedArgs), _P]),
     "alad_pool_tokens": (C.c_int, [_P, _I64, _I64, _I32, _I32, _I32, _I32, _P, C.c_float, _P, _P]),
     "alad_scale_scores": (C.c_int, [_P, _I64, _I32, _I32, _P, C.c_float, _P]),
     "alad_mrsw_bwd_workspace_bytes": (C.c_int64, [_I32, _I32, _I32, _I32, _I64]),
@@ -101,7 +120,7 @@ def lib():
 
 # kernels launched per successful entry-point call (bench.py reports the total as gpu_launches)
 KERNELS_PER_CALL = {
-    "alad_h2d_2d": 0, "alad_pack_tokens": 1, "alad_pool_tokens": 1, "alad_scale_scores": 1, "alad_mrsw_scores_fwd": 1, "alad_mrsw_scores_bwd": 6,
+    "alad_h2d_2d": 0, "alad_pack_tokens": 1, "alad_pool_tokens": 1, "alad_scale_scores": 1, "alad_mrsw_scores_fwd": 1, "alad_scores_fused": 3, "alad_mrsw_scores_bwd": 4,
     "alad_triplet_fwd_bwd": 2, "alad_listnet_fwd_bwd": 3, "alad_rank_rows": 1, "alad_col_gt": 1,
     "alad_col_count": 1, "alad_col_topk": 1, "alad_topk_merge": 1, "alad_shortlist_scatter": 2,
     "alad_distill_mse_fwd_bwd": 1, "alad_distill_contrastive_fwd_bwd": 2, "alad_distill_ordinal_fwd_bwd": 2,
@@ -118,5 +137,7 @@ def check(rc, what):
 
 
 def stream_ptr():
+    """Raw cudaStream_t of torch's current stream on the current device (one C call: this runs before every
+    entry point, and torch.cuda.current_stream() costs several microseconds of Python)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()) or None

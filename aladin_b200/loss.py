@@ -154,19 +154,29 @@ def pool_tokens_bwd(x, counts, d_pool, eps=1e-12):
     return out
 
 
+def _grad_like(x):
+    """Uninitialised fp32 [B,S,d] gradient buffer: the strides of x when x is a dense [S,B,d] tensor viewed as
+    [B,S,d], contiguous otherwise."""
+    B, S, d = x.shape
+    if B > 1 and S > 1 and x.stride() == (d, B * d, 1):
+        return torch.empty((S, B, d), dtype=torch.float32, device=x.device).permute(1, 0, 2)
+    return torch.empty((B, S, d), dtype=torch.float32, device=x.device)
+
+
 def mrsw_backward(im_set, s_seq, nr, nw, G0=None, g0_scale=None, G1=None, eps=1e-12, region_extent=0):
     """(d im_set, d s_seq) for dL/dS = g0_scale*G0 + G1 (alad_mrsw_scores_bwd)."""
     lib = _cabi.lib()
     Bi, S_im, d = im_set.shape
     Bc, S_s, _ = s_seq.shape
     dev = im_set.device
-    d_im = torch.empty((Bi, S_im, d), dtype=torch.float32, device=dev)
-    d_s = torch.empty((Bc, S_s, d), dtype=torch.float32, device=dev)
+    # gradients are produced in the memory layout of the inputs: ALADModel hands over [S,B,d] tensors permuted to
+    # [B,S,d] (alad_model.py:377-378), and a gradient with the same strides is accumulated into the leaf without a copy
+    d_im = _grad_like(im_set)
+    d_s = _grad_like(s_seq)
     max_pairs = max(Bi * Bc, 1)
     nbytes = lib.alad_mrsw_bwd_workspace_bytes(Bi, S_im, Bc, S_s, max_pairs)
     ws = _ws(nbytes, dev)
-    nr_d = scoring._to_dev(np.asarray(nr, np.int32), dev)
-    nw_d = scoring._to_dev(np.asarray(nw, np.int32), dev)
+    nr_d, nw_d = scoring._to_dev_group([np.asarray(nr, np.int32), np.asarray(nw, np.int32)], dev)
 
     def ptr(t):
         return t.data_ptr() if t is not None else None
@@ -180,7 +190,8 @@ def mrsw_backward(im_set, s_seq, nr, nw, G0=None, g0_scale=None, G1=None, eps=1e
         G0=ptr(G0), ldG0=max(G0.stride(0), Bc) if G0 is not None else 0, g0_scale=ptr(g0_scale),
         G1=ptr(G1), ldG1=max(G1.stride(0), Bc) if G1 is not None else 0,
         d_im=d_im.data_ptr(), d_s=d_s.data_ptr(), eps=eps, region_extent=region_extent, max_pairs=max_pairs,
-        workspace=ws.data_ptr(), workspace_bytes=nbytes)
+        workspace=ws.data_ptr(), workspace_bytes=nbytes,
+        d_im_stride_b=d_im.stride(0), d_im_stride_s=d_im.stride(1), d_s_stride_b=d_s.stride(0), d_s_stride_s=d_s.stride(1))
     _cabi.check(lib.alad_mrsw_scores_bwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_bwd")
     return d_im, d_s
 
@@ -358,8 +369,9 @@ class _AlignmentFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         im_c = scoring._require_cuda(im_set.detach(), "im_set")
         s_c = scoring._require_cuda(s_seq.detach(), "s_seq")
-        S = scoring.alignment_scores(im_c, s_c, im_len, s_len, precision=precision, aggregation=aggregation)
-        _, W, nr, nw, _ = scoring.scored_counts(im_c.shape, s_c.shape, im_len, s_len)
+        counts = scoring.scored_counts(im_c.shape, s_c.shape, im_len, s_len)
+        _, W, nr, nw, _ = counts
+        S = scoring.alignment_scores(im_c, s_c, im_len, s_len, precision=precision, aggregation=aggregation, counts=counts)
         needs_grad = im_set.requires_grad or s_seq.requires_grad
         G0 = None
         if want_loss:

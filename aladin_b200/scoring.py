@@ -5,6 +5,7 @@ Reference call sites replaced (mesnico/ALADIN):
   alad/loss.py:79-125  AlignmentContrastiveLoss.forward (aggregation 'MrSw')
   alad/loss.py:8-18    dot_sim / cosine_sim
 """
+import collections
 import ctypes as C
 
 import numpy as np
@@ -33,10 +34,20 @@ def get_precision():
     return _precision
 
 
+_cuda_checked = False
+
+
+def _cuda_ok():
+    global _cuda_checked
+    if not _cuda_checked:
+        _cuda_checked = torch.cuda.is_available()      # only a positive answer is remembered
+    return _cuda_checked
+
+
 def _require_cuda(x, name):
     if not isinstance(x, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
-    if not torch.cuda.is_available():
+    if not _cuda_ok():
         raise _cabi.AladError("aladin_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
     if x.device.type != "cuda":
         x = x.cuda(non_blocking=True)
@@ -47,8 +58,49 @@ def _require_cuda(x, name):
     return x
 
 
+# Small per-call metadata (token counts, packed row offsets, tile tables) is derived on the host from the Python
+# length lists the reference passes around (alad/dataset.py:358-361), so every call needs it on the device.  Uploads
+# are memoised by content, device and stream: the shape-only tables of dot_scores, and the lengths a backward pass
+# shares with its forward, hit the cache; a new batch of lengths costs one merged upload per operand group.
+_META_CACHE = collections.OrderedDict()
+_META_CACHE_ENTRIES = 256
+_META_CACHE_MAX_BYTES = 1 << 16
+_TORCH_DTYPE = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64, np.dtype(np.uint32): torch.int32,
+                np.dtype(np.float32): torch.float32, np.dtype(np.uint8): torch.uint8}
+
+
 def _to_dev(arr, device):
-    return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=True)
+    arr = np.ascontiguousarray(arr)
+    if arr.nbytes > _META_CACHE_MAX_BYTES:
+        return torch.from_numpy(arr).to(device, non_blocking=True)
+    device = torch.device(device)
+    index = device.index if device.index is not None else torch._C._cuda_getDevice()
+    key = (index, torch._C._cuda_getCurrentRawStream(index), arr.dtype.num, arr.shape, arr.tobytes())
+    hit = _META_CACHE.get(key)
+    if hit is not None:
+        _META_CACHE.move_to_end(key)
+        return hit
+    if arr.dtype == np.uint32:
+        arr = arr.view(np.int32)
+    out = torch.from_numpy(arr).to(device, non_blocking=True)
+    _META_CACHE[key] = out
+    if len(_META_CACHE) > _META_CACHE_ENTRIES:
+        _META_CACHE.popitem(last=False)
+    return out
+
+
+def _to_dev_group(arrays, device):
+    """Several small host arrays -> ONE upload; returns typed device views (16-byte aligned)."""
+    arrs = [np.ascontiguousarray(a) for a in arrays]
+    offs, total = [], 0
+    for a in arrs:
+        offs.append(total)
+        total += (a.nbytes + 15) & ~15
+    blob = np.zeros(max(total, 16), dtype=np.uint8)
+    for a, o in zip(arrs, offs):
+        blob[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+    d = _to_dev(blob, device)
+    return [d[o:o + a.nbytes].view(_TORCH_DTYPE[a.dtype]).reshape(a.shape) for a, o in zip(arrs, offs)]
 
 
 class Packed:
@@ -60,17 +112,27 @@ class Packed:
         self.counts, self.row_off, self.row_item, self.mode = counts, row_off, row_item, mode
 
 
+def pack_meta(counts, row_base=0):
+    """Host arrays (counts int32, row_off int64, n_rows) of one pack call."""
+    counts = np.asarray(counts, dtype=np.int32)
+    row_off, n_rows = exclusive_cumsum(counts)
+    return counts, row_off + row_base if row_base else row_off, n_rows
+
+
 def pack_tokens(x, counts, *, slot0, mode=0, normalize=True, eps=1e-12, want_row_item=False, out=None,
-                out_row_item=None, row_base=0, item_base=0):
+                out_row_item=None, row_base=0, item_base=0, meta_dev=None):
     """x [B,S,d] fp32 cuda (any strides on B,S) -> Packed rows for tokens slot0 .. slot0+count-1."""
     lib = _cabi.lib()
     assert x.dim() == 3 and x.is_cuda and x.dtype == torch.float32 and x.stride(2) == 1
     B, S, d = x.shape
     counts = np.asarray(counts, dtype=np.int32)
     assert counts.shape == (B,)
-    if B and (counts.min() < 0 or counts.max() > max(S - slot0, 0)):
-        raise ValueError("token counts exceed the container")
-    row_off, n_rows = exclusive_cumsum(counts)
+    if meta_dev is not None and len(meta_dev) == 4:
+        row_off, n_rows = meta_dev[2], meta_dev[3]       # host offsets / row count computed by the caller
+    else:
+        if B and (counts.min() < 0 or counts.max() > max(S - slot0, 0)):
+            raise ValueError("token counts exceed the container")
+        row_off, n_rows = exclusive_cumsum(counts)
     Kp = round_up(d * (1 if mode == 0 else 3), _cabi.TILE_K)
     if out is not None:
         # pack into rows [row_base, row_base + n_rows) of a caller-owned buffer (sharded packing)
@@ -83,8 +145,8 @@ def pack_tokens(x, counts, *, slot0, mode=0, normalize=True, eps=1e-12, want_row
         if want_row_item:
             row_item = torch.full((max(padded_rows(n_rows), 2 * _cabi.TILE_M),), -1, dtype=torch.int32, device=x.device)
     if n_rows:
-        cnt_d = _to_dev(counts, x.device)
-        off_d = _to_dev(row_off, x.device)
+        # meta_dev = (counts, row offsets incl. row_base) already on the device (merged upload by the caller)
+        off_d, cnt_d = meta_dev[:2] if meta_dev is not None else _to_dev_group([row_off, counts], x.device)
         a = _cabi.PackArgs(
             src=x.data_ptr(), stride_b=x.stride(0), stride_s=x.stride(1), B=B, S=S, d=d, slot0=slot0,
             count=cnt_d.data_ptr(), row_off=off_d.data_ptr(), dst=data.data_ptr(), Kp=Kp, mode=mode,
@@ -132,30 +194,41 @@ def scored_counts(im_shape, s_shape, im_len, s_len):
 AGGREGATIONS = ("sum", "mean", "MrSw", "MrAVGw", "symm", "MwSr")
 
 
+def _scores_fused(max_x, max_counts, max_clamp, sum_x, sum_counts, slot0, precision, epilogue, normalize, eps,
+                  transpose_out, out):
+    """alad_scores_fused: pack both operands and score them in one native call (host bookkeeping included)."""
+    lib = _cabi.lib()
+    n_max, S_max, d = max_x.shape
+    n_sum, S_sum, _ = sum_x.shape
+    max_counts = np.ascontiguousarray(max_counts, dtype=np.int32)
+    sum_counts = np.ascontiguousarray(sum_counts, dtype=np.int32)
+    clamp = np.ascontiguousarray(max_clamp, dtype=np.uint8) if max_clamp is not None else None
+    split = 1 if precision == "fp32" else 0
+    nbytes = lib.alad_scores_fused_workspace_bytes(n_max, S_max, slot0, n_sum, S_sum, slot0, d, split)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=max_x.device)
+    a = _cabi.ScoresFusedArgs(
+        max_x.data_ptr(), max_x.stride(0), max_x.stride(1), sum_x.data_ptr(), sum_x.stride(0), sum_x.stride(1),
+        n_max, S_max, slot0, n_sum, S_sum, slot0, d, max_counts.ctypes.data, sum_counts.ctypes.data,
+        clamp.ctypes.data if clamp is not None else None, split, epilogue, 1 if normalize else 0, eps,
+        out.data_ptr(), max(out.stride(0), out.shape[1]), 1 if transpose_out else 0, ws.data_ptr(), nbytes)
+    if kernel_timeline is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _cabi.check(lib.alad_scores_fused(C.byref(a), _cabi.stream_ptr()), "alad_scores_fused")
+    if kernel_timeline is not None:
+        e1.record()
+        kernel_timeline.append((e0, e1, n_max, n_sum, round_up(d * (3 if split else 1), _cabi.TILE_K)))
+    return out
+
+
 def _max_sum_scores(max_x, max_counts, max_clamp, sum_x, sum_counts, precision, transpose_out, out):
     """out[...] = sum over the valid tokens of `sum_x` items of the max over the valid tokens of
     `max_x` items (clamped at 0 where `max_clamp`).  The 'max' items become tile columns (N side),
     the 'sum' items packed rows (M side).  out is [n_max, n_sum], or [n_sum, n_max] if transpose_out."""
-    split = precision == "fp32"
-    rows = pack_tokens(sum_x, sum_counts, slot0=1, mode=1 if split else 0, want_row_item=True)
-    cols = pack_tokens(max_x, max_counts, slot0=1, mode=2 if split else 0)
-    _, table, _ = build_region_tiles(max_counts, max_clamp)
-    tiles_dev = _to_dev(table.view(np.int32).reshape(-1), max_x.device) if len(table) else None
-    n_max, n_sum = max_x.shape[0], sum_x.shape[0]
-    lib = _cabi.lib()
-    a = _cabi.MrswFwdArgs(
-        words=rows.data.data_ptr(), n_word_rows=rows.n_rows, regions=cols.data.data_ptr(), n_region_rows=cols.n_rows,
-        Kp=rows.Kp, row_cap=rows.row_item.data_ptr(), ntiles=tiles_dev.data_ptr() if len(table) else None,
-        n_ntiles=len(table), S=out.data_ptr(), ldS=max(out.stride(0), out.shape[1]), Ni=n_max, Nc=n_sum, epilogue=0,
-        num_ctas=0, cta_group=0, transpose_out=1 if transpose_out else 0)
-    if kernel_timeline is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    _cabi.check(lib.alad_mrsw_scores_fwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_fwd")
-    if kernel_timeline is not None:
-        e1.record()
-        kernel_timeline.append((e0, e1, n_max, n_sum, rows.Kp))
-    return out
+    if len(max_counts) and int(np.max(max_counts)) > _cabi.TILE_N:
+        raise ValueError(f"an item has {int(np.max(max_counts))} scored tokens on the max side; the kernel supports at most "
+                         f"{_cabi.TILE_N}")
+    return _scores_fused(max_x, max_counts, max_clamp, sum_x, sum_counts, 1, precision, 0, True, 1e-12, transpose_out, out)
 
 
 def pool_tokens(x, counts, eps=1e-12):
@@ -191,7 +264,7 @@ def unit_rows(x, eps=0.0):
     return out
 
 
-def alignment_scores(im_set, s_seq, im_len, s_len, precision=None, out=None, aggregation="MrSw"):
+def alignment_scores(im_set, s_seq, im_len, s_len, precision=None, out=None, aggregation="MrSw", counts=None):
     """Alignment scores S[B_i,B_c] of alad/loss.py:79-135 on the GPU, every tensor pooling mode:
     MrSw (max regions, sum words), MrAVGw (/ #words), MwSr (roles swapped), symm (MrSw + MwSr),
     sum / mean (one GEMM of the pooled token sums)."""
@@ -203,7 +276,7 @@ def alignment_scores(im_set, s_seq, im_len, s_len, precision=None, out=None, agg
     if im_set.dim() != 3 or s_seq.dim() != 3 or im_set.shape[2] != s_seq.shape[2]:
         raise ValueError("expected im_set [B_i,S_im,d] and s_seq [B_c,S_s,d] with equal d")
     Ni, Nc = im_set.shape[0], s_seq.shape[0]
-    R, W, nr, nw, clamp = scored_counts(im_set.shape, s_seq.shape, im_len, s_len)
+    R, W, nr, nw, clamp = counts if counts is not None else scored_counts(im_set.shape, s_seq.shape, im_len, s_len)
     if out is None:
         out = torch.empty((Ni, Nc), dtype=torch.float32, device=im_set.device)
     assert out.shape == (Ni, Nc) and out.dtype == torch.float32 and out.stride(1) == 1
@@ -225,6 +298,9 @@ def alignment_scores(im_set, s_seq, im_len, s_len, precision=None, out=None, agg
     return out
 
 
+_ONES = {}           # n -> np.ones(n, int32): the "one row per item" count arrays of dot_scores
+
+
 def dot_scores(im, s, precision=None, normalize=False, eps=0.0, out=None):
     """scores[B_i,B_c] = im @ s.T (alad/loss.py:8-11; cosine_sim :13-18 with normalize=True)
     through the same tcgen05 mainloop with the plain-GEMM epilogue."""
@@ -235,20 +311,15 @@ def dot_scores(im, s, precision=None, normalize=False, eps=0.0, out=None):
     if im.dim() != 2 or s.dim() != 2 or im.shape[1] != s.shape[1]:
         raise ValueError("expected im [B_i,d] and s [B_c,d]")
     Ni, Nc = im.shape[0], s.shape[0]
-    split = precision == "fp32"
-    words = pack_tokens(s.unsqueeze(1), np.ones(Nc, np.int32), slot0=0, mode=1 if split else 0,
-                        normalize=normalize, eps=eps)
-    regions = pack_tokens(im.unsqueeze(1), np.ones(Ni, np.int32), slot0=0, mode=2 if split else 0,
-                          normalize=normalize, eps=eps)
     if out is None:
         out = torch.empty((Ni, Nc), dtype=torch.float32, device=im.device)
     if Ni == 0 or Nc == 0:
         return out
-    table = gemm_tiles(Ni)
-    tiles_dev = _to_dev(table.view(np.int32).reshape(-1), im.device)
-    a = _cabi.MrswFwdArgs(
-        words=words.data.data_ptr(), n_word_rows=Nc, regions=regions.data.data_ptr(), n_region_rows=Ni,
-        Kp=words.Kp, row_cap=None, ntiles=tiles_dev.data_ptr(), n_ntiles=len(table), S=out.data_ptr(),
-        ldS=max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=1, num_ctas=0, cta_group=0, transpose_out=0)
-    _cabi.check(lib.alad_mrsw_scores_fwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_fwd")
+    assert out.shape == (Ni, Nc) and out.dtype == torch.float32 and out.stride(1) == 1
+    ones = _ONES.get(max(Ni, Nc))
+    if ones is None:
+        if len(_ONES) >= 64:
+            _ONES.clear()
+        ones = _ONES[max(Ni, Nc)] = np.ones(max(Ni, Nc), np.int32)
+    _scores_fused(im.unsqueeze(1), ones[:Ni], None, s.unsqueeze(1), ones[:Nc], 0, precision, 1, normalize, eps, False, out)
     return out

@@ -94,6 +94,14 @@ typedef struct alad_ntile {      /* one 240-column tile of packed region rows (d
   uint16_t seg[ALAD_MAX_SEG];    /* image s: low byte = first column, high byte = #columns   */
 } alad_ntile;
 
+/* Host-side helper (HOST pointers, no CUDA work): greedy grouping of consecutive images into tiles of
+ * <= ALAD_TILE_N packed region rows and <= ALAD_MAX_SEG images; images with nr == 0 own no column.  Writes
+ * the table to tiles[0 .. return value) (capacity Ni always suffices) and, if row_off != NULL, the first packed
+ * region row of every image.  Returns the number of tiles or a negative alad_status.  Replaces the Python
+ * mask loops of alad/loss.py:105-106 as the per-call host bookkeeping. */
+int alad_region_tiles(const int32_t* nr, const uint8_t* clamp, int32_t Ni, alad_ntile* tiles, int32_t capacity,
+                      int64_t* row_off);
+
 typedef struct alad_mrsw_fwd_args {
   const void* words;             /* [n_word_rows, Kp] bf16 packed (mode 0 or 1)              */
   int64_t n_word_rows;
@@ -114,6 +122,40 @@ typedef struct alad_mrsw_fwd_args {
                                     'MwSr' pooling, which is MrSw with the two token sets swapped */
 } alad_mrsw_fwd_args;
 int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * alad_scores_fused -- "pack both operands + score" in ONE call on RAW fp32 tokens and HOST count arrays:
+ * the body of AlignmentContrastiveLoss.forward up to `aggr_similarity` (alad/loss.py:80-125, epilogue 0) or of
+ * dot_sim / cosine_sim (alad/loss.py:8-18, epilogue 1: one row per item, slot0 = 0).  The "max" items
+ * become tile columns (images for 'MrSw'), the "sum" items packed rows (captions).  Host work done inside:
+ * row offsets, the greedy region tile table (alad_region_tiles), one metadata upload; device work: the two
+ * alad_pack_tokens launches and alad_mrsw_scores_fwd.  The packed operands live in `workspace`
+ * (alad_scores_fused_workspace_bytes: an upper bound from the container extents; 256-byte aligned).
+ * ------------------------------------------------------------------------------- */
+typedef struct alad_scores_fused_args {
+  const float* max_x;            /* [n_max, S_max, d] fp32 device, innermost stride 1         */
+  int64_t max_stride_b, max_stride_s;
+  const float* sum_x;            /* [n_sum, S_sum, d]                                         */
+  int64_t sum_stride_b, sum_stride_s;
+  int32_t n_max, S_max, slot0_max;
+  int32_t n_sum, S_sum, slot0_sum;
+  int32_t d;
+  const int32_t* max_count;      /* HOST [n_max] scored tokens per item (from slot0 on)       */
+  const int32_t* sum_count;      /* HOST [n_sum]                                              */
+  const uint8_t* max_clamp;      /* HOST [n_max] or NULL: item has masked slots -> max starts at 0 */
+  int32_t precision;             /* 0 = bf16 operands, 1 = split hi/lo (fp32-grade)           */
+  int32_t epilogue;              /* 0 = max/sum pooling, 1 = plain GEMM                       */
+  int32_t normalize;             /* 1: F.normalize the tokens while packing                   */
+  float eps;
+  float* S;                      /* [n_max, ldS] (or [n_sum, ldS] when transpose_out)         */
+  int64_t ldS;
+  int32_t transpose_out;
+  void* workspace;
+  int64_t workspace_bytes;
+} alad_scores_fused_args;
+int64_t alad_scores_fused_workspace_bytes(int32_t n_max, int32_t S_max, int32_t slot0_max, int32_t n_sum, int32_t S_sum,
+                                          int32_t slot0_sum, int32_t d, int32_t precision);
+int alad_scores_fused(const alad_scores_fused_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * alad_pool_tokens -- sum of the L2-normalised valid tokens of every item: out[b, :] =
@@ -146,13 +188,15 @@ typedef struct alad_mrsw_bwd_args {
   const float* g0_scale;         /* optional device scalar multiplying G0                    */
   const float* G1;               /* optional [Bi, ldG1]                                      */
   int64_t ldG1;
-  float* d_im;
-  float* d_s;
+  float* d_im;                   /* [Bi, S_im, d] gradient, zeroed here (all Bi*S_im*d floats from d_im on:    */
+  float* d_s;                    /* contiguous, or a dense permutation of the item / slot dims -- strides below) */
   float eps;                     /* F.normalize eps (1e-12)                                  */
   int32_t region_extent;         /* container extent R of the max side (clamp iff nr < R); 0 = S_im - 1 */
   int64_t max_pairs;             /* capacity of the pair list (Bi*Bc is always enough)       */
   void* workspace;
   int64_t workspace_bytes;       /* >= alad_mrsw_bwd_workspace_bytes(...)                    */
+  int64_t d_im_stride_b, d_im_stride_s;   /* element strides of d_im / d_s over items and slots; 0 = contiguous.   */
+  int64_t d_s_stride_b, d_s_stride_s;     /* e.g. (d, Bi*d) for the [S, B, d] layout of alad_model.py:377-378      */
 } alad_mrsw_bwd_args;
 int64_t alad_mrsw_bwd_workspace_bytes(int32_t Bi, int32_t S_im, int32_t Bc, int32_t S_s, int64_t max_pairs);
 int alad_mrsw_scores_bwd(const alad_mrsw_bwd_args* a, void* stream);

@@ -190,3 +190,56 @@ def test_other_pooling_modes_gradients_vs_torch_autograd(agg):
     (ref * Gup.cpu().double()).sum().backward()
     np.testing.assert_allclose(im_t.grad.cpu().numpy(), a.grad.numpy(), rtol=2e-3, atol=2e-5)
     np.testing.assert_allclose(s_t.grad.cpu().numpy(), b.grad.numpy(), rtol=2e-3, atol=2e-5)
+
+
+def _autograd_reference(im, s, il, cl, agg, Gup):
+    """float64 torch restatement of alad/loss.py:80-135 with autograd: (S, d im, d s)."""
+    a = torch.tensor(im, dtype=torch.float64, requires_grad=True)
+    b = torch.tensor(s, dtype=torch.float64, requires_grad=True)
+    an = torch.nn.functional.normalize(a, dim=2)[:, 1:]
+    bn = torch.nn.functional.normalize(b, dim=2)[:, 1:-2]
+    A = torch.einsum("ird,jwd->ijrw", an, bn)
+    R, W = an.shape[1], bn.shape[1]
+    rm = torch.arange(R)[None, :] >= torch.tensor([l - 1 for l in il])[:, None]
+    wm = torch.arange(W)[None, :] >= torch.tensor([l - 3 for l in cl])[:, None]
+    A = A.masked_fill(rm[:, None, :, None] | wm[None, :, None, :], 0.0)
+    S = {"MrSw": A.max(2)[0].sum(2), "MwSr": A.max(3)[0].sum(2)}[agg]
+    (S * torch.tensor(Gup, dtype=torch.float64)).sum().backward()
+    return S.detach().numpy(), a.grad.numpy(), b.grad.numpy()
+
+
+@pytest.mark.parametrize("shape", [(6, 9, 35, 53, 64), (5, 7, 71, 71, 96), (4, 6, 20, 90, 64), (4, 5, 90, 40, 32)])
+@pytest.mark.parametrize("agg", ["MrSw", "MwSr"])
+def test_tiled_pair_backward_vs_autograd_and_generic(shape, agg, monkeypatch):
+    """The register-tiled pair kernel (all three tile shapes, fused F.normalize Jacobian, gradients written in a
+    permuted [S,B,d] layout) against float64 autograd and against the generic warp-per-word kernel."""
+    from aladin_b200 import loss as L, synth
+    Bi, Bc, S_im, S_s, d = shape
+    im, s, il, cl = synth.raw_batch(77 + S_im, Bi, Bc, S_im, S_s, d, related=0.7)
+    im[0, 1] = 0.0                                        # a zero token: norm below eps, no projection term
+    Gup = np.random.RandomState(3).standard_normal((Bi, Bc)).astype(np.float32)
+    Gup[np.random.RandomState(4).rand(Bi, Bc) < 0.3] = 0.0
+    S_ref, dim_ref, ds_ref = _autograd_reference(im, s, il, cl, agg, Gup)
+
+    def run(permuted):
+        if permuted:
+            im_t, s_t = cu(im.transpose(1, 0, 2).copy(), True), cu(s.transpose(1, 0, 2).copy(), True)
+            a, b = im_t.permute(1, 0, 2), s_t.permute(1, 0, 2)
+        else:
+            im_t, s_t = cu(im, True), cu(s, True)
+            a, b = im_t, s_t
+        crit = L.AlignmentContrastiveLoss(aggregation=agg)
+        crit.precision = "fp32"
+        S = crit(a, b, il, cl, return_loss=False, return_similarity_mat=True)
+        (S * cu(Gup)).sum().backward()
+        gi, gs = im_t.grad.cpu().numpy(), s_t.grad.cpu().numpy()
+        return S.detach().cpu().numpy(), (gi.transpose(1, 0, 2) if permuted else gi), (gs.transpose(1, 0, 2) if permuted else gs)
+
+    S_t, dim_t, ds_t = run(permuted=True)
+    assert_scores_close(S_t, S_ref, 1e-4, f"{agg} {shape}")
+    np.testing.assert_allclose(dim_t, dim_ref, rtol=2e-3, atol=2e-5)
+    np.testing.assert_allclose(ds_t, ds_ref, rtol=2e-3, atol=2e-5)
+    monkeypatch.setenv("ALAD_BWD_GENERIC", "1")
+    _, dim_g, ds_g = run(permuted=False)
+    np.testing.assert_allclose(dim_t, dim_g, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(ds_t, ds_g, rtol=1e-3, atol=1e-5)

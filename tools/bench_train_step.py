@@ -13,7 +13,7 @@ import aladin_b200  # noqa: E402
 from aladin_b200 import loss as L, synth  # noqa: E402
 
 
-def timeit(fn, iters=10, warm=3):
+def timeit(fn, iters=100, warm=10):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -26,7 +26,8 @@ def timeit(fn, iters=10, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-def train_step(B, precision):
+def make_step(B, precision):
+    """(fwd, fwd_bwd, il, cl): the three-criterion training step of alad_model.py:371-428 on synthetic features."""
     im, s, il, cl = synth.raw_batch(9, B, B, 35, 53, 1024, related=0.6)
     r = np.random.RandomState(1)
     icls = r.standard_normal((B, 1024)).astype(np.float32)
@@ -52,11 +53,26 @@ def train_step(B, precision):
             t.grad = None
         fwd().backward()
 
+    return fwd, fwd_bwd, il, cl
+
+
+def train_step(B, precision):
+    fwd, fwd_bwd, il, cl = make_step(B, precision)
     with torch.no_grad():
         t_f = timeit(fwd)
     t_fb = timeit(fwd_bwd)
+    # host enqueue time per step: wall clock of the Python side with an empty launch queue
+    import time
+    host = []
+    for _ in range(20):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fwd_bwd()
+        host.append(time.perf_counter() - t0)
+        torch.cuda.synchronize()
+    t_host = 1e3 * sorted(host)[len(host) // 2]
     flop = 2.0 * sum(l - 1 for l in il) * sum(l - 3 for l in cl) * 1024
-    return {"B": B, "precision": precision, "fwd_ms": t_f, "fwd_bwd_ms": t_fb, "pairs_per_s_fwd": B * B / t_f * 1e3,
+    return {"B": B, "precision": precision, "fwd_ms": t_f, "fwd_bwd_ms": t_fb, "fwd_bwd_host_enqueue_ms": t_host, "pairs_per_s_fwd": B * B / t_f * 1e3,
             "pairs_per_s_fwd_bwd": B * B / t_fb * 1e3, "fwd_algorithmic_tflops": flop / t_f / 1e9}
 
 
@@ -72,6 +88,30 @@ def loss_kernels(B):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "profile":      # ncu launch list: 1 warm-up + 1 profiled step
+        _, step, _, _ = make_step(int(sys.argv[2]), sys.argv[3] if len(sys.argv) > 3 else "bf16")
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[1] == "hostprof":     # where the host time of a step goes (cProfile, no sync inside)
+        import cProfile
+        import pstats
+        _, step, _, _ = make_step(int(sys.argv[2]), "bf16")
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(50):
+            step()
+            torch.cuda.synchronize()        # empty launch queue: host time is not back-pressure from the device
+        pr.disable()
+        pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+        sys.exit(0)
     out = {"train_step": [train_step(B, p) for B in (128, 512) for p in ("bf16", "fp32")],
            "loss_kernels": [loss_kernels(B) for B in (512, 8192)]}
     print(json.dumps(out, indent=1))
