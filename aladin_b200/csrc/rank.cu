@@ -168,14 +168,22 @@ __device__ __forceinline__ void heap_sift_down(float* bs, int* bi, int k, int la
   bi[j * 32 + lane] = vi;
 }
 
+// col_list / n_list (optional): the kernel visits only the listed columns (the overflow columns of the
+// threshold-select path below); CTAs beyond the list exit at once.
 __global__ void __launch_bounds__(32)
 col_topk_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int k, int img_off, int splits,
-                float* __restrict__ cand_score, int* __restrict__ cand_idx) {
+                float* __restrict__ cand_score, int* __restrict__ cand_idx, const int* __restrict__ col_list,
+                const int* __restrict__ n_list) {
   extern __shared__ uint8_t topk_smem[];
   float* bs = reinterpret_cast<float*>(topk_smem);       // [k][32]
   int* bi = reinterpret_cast<int*>(bs + k * 32);           // [k][32]
   const int lane = threadIdx.x;
-  const int c = blockIdx.x * 32 + lane;
+  int c = blockIdx.x * 32 + lane;
+  if (col_list) {
+    const int n = *n_list;
+    if ((int)blockIdx.x * 32 >= n) return;
+    c = c < n ? col_list[c] : Nc;
+  }
   const int split = blockIdx.y;
   const int per = (Ni + splits - 1) / splits;
   const int r_begin = split * per;
@@ -212,6 +220,190 @@ col_topk_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int 
     const float ls = bs[(n - 1) * 32 + lane];
     const int li = bi[(n - 1) * 32 + lane];
     if (n > 1) heap_sift_down(bs, bi, n - 1, lane, ls, li);
+  }
+}
+
+// ------------------------------------------------------------------ t2i step 3, threshold-select variant
+// Exact top-k per caption in two HBM sweeps of S instead of k-entry heaps:
+//   (1) col_groupmax: the rows are cut into G >= k groups; gmax[g][c] = max of column c over group g.
+//   (2) col_threshold: tau[c] = k-th largest of the G group maxima (radix select on order-preserving keys).
+//       At least k entries of the column are >= tau[c] (one per qualifying group), so every top-k entry is.
+//   (3) col_collect: second sweep; entries >= tau[c] are appended to a per-caption candidate list
+//       (expected ~1.3 k entries for G = 2.5 k groups, capacity `cap`).
+//   (4) col_select: one warp per caption ranks its candidates under the total order (score desc, index
+//       desc) and writes the k best in order.  Captions whose list overflowed (mass ties, e.g. an all-zero
+//       column) are queued for the heap kernel above -- exact in every case.
+constexpr int SEL_ROWS = 8;           // row slices per CTA (threadIdx.y)
+constexpr int SEL_CHUNK = 512;        // rows per collect CTA
+constexpr int SEL_MAX_G = 352;        // group-maxima tile [G][33] floats stays under 48 KB
+constexpr int SEL_MAX_CAP = 512;
+
+__device__ __forceinline__ uint32_t order_key(float v) {       // monotone float -> uint (-0 == +0)
+  const uint32_t u = __float_as_uint(v + 0.f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t key) {
+  return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
+
+__global__ void __launch_bounds__(32 * SEL_ROWS)
+col_groupmax_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int rows_per_group, int G,
+                    float* __restrict__ gmax) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int g = blockIdx.y * SEL_ROWS + threadIdx.y;
+  if (c >= Nc || g >= G) return;
+  const int r0 = g * rows_per_group;
+  const int r1 = min(Ni, r0 + rows_per_group);
+  const float* col = S + c;
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    m0 = fmaxf(m0, __ldg(col + (long long)(r + 0) * ldS));
+    m1 = fmaxf(m1, __ldg(col + (long long)(r + 1) * ldS));
+    m2 = fmaxf(m2, __ldg(col + (long long)(r + 2) * ldS));
+    m3 = fmaxf(m3, __ldg(col + (long long)(r + 3) * ldS));
+  }
+  for (; r < r1; ++r) m0 = fmaxf(m0, __ldg(col + (long long)r * ldS));
+  gmax[(long long)g * Nc + c] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// 8 warps per CTA, 32 captions per CTA (4 per warp); the [G][32] tile of group maxima goes through shared
+// memory so that the global reads stay coalesced
+template <int PER_LANE>                                        // keys per lane: ceil(G / 32) rounded up to 4, 8 or 11
+__global__ void __launch_bounds__(256)
+col_threshold_kernel(const float* __restrict__ gmax, int Nc, int G, int k, float* __restrict__ tau) {
+  extern __shared__ float tile[];                              // [G][33]
+  const int c0 = blockIdx.x * 32;
+  for (int e = threadIdx.x; e < G * 32; e += 256) {
+    const int g = e >> 5, x = e & 31;
+    tile[g * 33 + x] = (c0 + x < Nc) ? __ldg(gmax + (long long)g * Nc + c0 + x) : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = 0; q < 4; ++q) {
+    const int x = warp * 4 + q;
+    if (c0 + x >= Nc) break;                                   // warp-uniform
+    uint32_t key[PER_LANE];
+#pragma unroll
+    for (int j = 0; j < PER_LANE; ++j) {
+      const int g = lane + 32 * j;
+      key[j] = g < G ? order_key(tile[g * 33 + x]) : 0u;       // 0 is below every real key
+    }
+    uint32_t T = 0;                                            // largest T with #{key >= T} >= k  ==  k-th largest key
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int n = 0;
+#pragma unroll
+      for (int j = 0; j < PER_LANE; ++j) n += key[j] >= cand ? 1 : 0;
+      n = __reduce_add_sync(0xffffffffu, n);
+      if (n >= k) T = cand;
+    }
+    if (lane == 0) tau[c0 + x] = key_to_float(T);
+  }
+}
+
+constexpr int SEL_LOCAL = 24;         // CTA-local list entries per column (expected ~6 per 512-row chunk)
+__global__ void __launch_bounds__(32 * SEL_ROWS)
+col_collect_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int img_off,
+                   const float* __restrict__ tau, int cap, int* __restrict__ cnt, float* __restrict__ cand_s,
+                   int* __restrict__ cand_i) {
+  // Candidates are first appended to CTA-local lists (shared-memory atomics), then every column reserves its
+  // range of the global list with ONE global atomic per CTA; entries beyond the local capacity go to the
+  // global list directly.
+  __shared__ float ls[SEL_LOCAL][32];
+  __shared__ int li[SEL_LOCAL][32];
+  __shared__ int lcnt[32];
+  __shared__ int lbase[32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  if (ty == 0) lcnt[tx] = 0;
+  __syncthreads();
+  const int r_begin = blockIdx.y * SEL_CHUNK;
+  const int r_end = min(Ni, r_begin + SEL_CHUNK);
+  const bool col_ok = c < Nc;
+  const float t = (tau && col_ok) ? __ldg(tau + c) : -INFINITY;   // no threshold: every entry is a candidate
+  const float* col = S + (col_ok ? c : 0);
+  float* out_s = cand_s + (long long)c * cap;
+  int* out_i = cand_i + (long long)c * cap;
+  if (col_ok) {
+    for (int r = r_begin + ty; r < r_end; r += 4 * SEL_ROWS) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (r + u * SEL_ROWS < r_end) ? __ldg(col + (long long)(r + u * SEL_ROWS) * ldS) : -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * SEL_ROWS < r_end && v[u] >= t) {
+          const int lp = atomicAdd(&lcnt[tx], 1);
+          if (lp < SEL_LOCAL) {
+            ls[lp][tx] = v[u];
+            li[lp][tx] = img_off + r + u * SEL_ROWS;
+          } else {
+            const int pos = atomicAdd(cnt + c, 1);
+            if (pos < cap) {
+              out_s[pos] = v[u];
+              out_i[pos] = img_off + r + u * SEL_ROWS;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int n_loc = min(lcnt[tx], SEL_LOCAL);
+  if (ty == 0 && col_ok && n_loc > 0) lbase[tx] = atomicAdd(cnt + c, n_loc);
+  __syncthreads();
+  if (col_ok) {
+    const int base = lbase[tx];
+    for (int e = ty; e < n_loc; e += SEL_ROWS) {
+      if (base + e < cap) {
+        out_s[base + e] = ls[e][tx];
+        out_i[base + e] = li[e][tx];
+      }
+    }
+  }
+}
+
+// one warp per caption: rank of every candidate = number of candidates ahead of it (strict total order,
+// so the ranks are a permutation and the output does not depend on the order the atomics filled the list in)
+constexpr int SELECT_WARPS = 8;
+__global__ void __launch_bounds__(32 * SELECT_WARPS)
+col_select_kernel(const int* __restrict__ cnt, const float* __restrict__ cand_s, const int* __restrict__ cand_i, int Nc,
+                  int k, int cap, float* __restrict__ out_score, int* __restrict__ out_idx, int* __restrict__ ovf_list,
+                  int* __restrict__ ovf_n) {
+  extern __shared__ float2 sel_smem[];                         // [SELECT_WARPS][cap] (score, index bits)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * SELECT_WARPS + warp;
+  if (c >= Nc) return;
+  const int n = __ldg(cnt + c);
+  if (n > cap) {                                               // list overflowed: exact heap path for this caption
+    if (lane == 0) ovf_list[atomicAdd(ovf_n, 1)] = c;
+    return;
+  }
+  float2* mine = sel_smem + warp * cap;
+  const float* cs = cand_s + (long long)c * cap;
+  const int* ci = cand_i + (long long)c * cap;
+  for (int e = lane; e < n; e += 32) mine[e] = make_float2(__ldg(cs + e), __int_as_float(__ldg(ci + e)));
+  __syncwarp();
+  float* os = out_score + (long long)c * k;
+  int* oi = out_idx + (long long)c * k;
+  for (int e = lane; e < n; e += 32) {
+    const float v = mine[e].x;
+    const int vi = __float_as_int(mine[e].y);
+    int rank = 0;
+#pragma unroll 4
+    for (int o = 0; o < n; ++o) {
+      const float2 w = mine[o];                                // broadcast read
+      rank += ahead(w.x, __float_as_int(w.y), v, vi) ? 1 : 0;
+    }
+    if (rank < k) {
+      os[rank] = v;
+      oi[rank] = vi;
+    }
+  }
+  for (int e = n + lane; e < k; e += 32) {                     // fewer than k gallery images
+    os[e] = -INFINITY;
+    oi[e] = -1;
   }
 }
 
@@ -344,7 +536,96 @@ extern "C" int alad_col_topk(const float* S, int64_t ldS, int32_t Ni, int32_t Nc
     smem_set = smem;
   }
   dim3 grid((Nc + 31) / 32, splits);
-  col_topk_kernel<<<grid, 32, smem, as_stream(stream)>>>(S, ldS, Ni, Nc, k, img_off, splits, cand_score, cand_idx);
+  col_topk_kernel<<<grid, 32, smem, as_stream(stream)>>>(S, ldS, Ni, Nc, k, img_off, splits, cand_score, cand_idx,
+                                                         nullptr, nullptr);
+  ALAD_CUDA(cudaGetLastError());
+  return ALAD_OK;
+}
+
+namespace alad {
+struct SelectPlan {
+  bool select;          // threshold-select path (else: heaps over all columns)
+  bool threshold;       // group maxima + tau (else every entry is a candidate: Ni <= cap)
+  int cap, rows_per_group, G;
+  size_t off_tau, off_cnt, off_ovf, off_cs, off_ci, off_gmax, bytes;
+};
+static SelectPlan select_plan(int Ni, int Nc, int k) {
+  SelectPlan p = {};
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  int cap = 2 * k < 256 ? 256 : (2 * k + 31) / 32 * 32;
+  p.cap = cap;
+  p.select = k <= SEL_MAX_G / 2 && cap <= SEL_MAX_CAP && Ni > 0;
+  if (p.select && Ni > cap) {
+    int g_target = (5 * k / 2 + 31) / 32 * 32;
+    g_target = g_target < 128 ? 128 : (g_target > SEL_MAX_G ? SEL_MAX_G : g_target);
+    p.rows_per_group = (Ni + g_target - 1) / g_target;
+    p.G = (Ni + p.rows_per_group - 1) / p.rows_per_group;
+    p.threshold = true;
+    if (p.G < k || p.G > SEL_MAX_G) p.select = false;         // cannot happen for k <= SEL_MAX_G / 2; be safe
+  }
+  size_t o = 0;
+  p.off_tau = o;  o += up(sizeof(float) * (size_t)Nc);
+  p.off_cnt = o;  o += up(sizeof(int) * ((size_t)Nc + 1));    // cnt[Nc] + overflow counter: one memset
+  p.off_ovf = o;  o += up(sizeof(int) * (size_t)Nc);
+  if (p.select) {
+    p.off_cs = o;   o += up(sizeof(float) * (size_t)Nc * cap);
+    p.off_ci = o;   o += up(sizeof(int) * (size_t)Nc * cap);
+    p.off_gmax = o; o += up(sizeof(float) * (size_t)Nc * (p.threshold ? p.G : 0));
+  }
+  p.bytes = o + 256;
+  return p;
+}
+}  // namespace alad
+
+extern "C" int64_t alad_col_topk_select_workspace_bytes(int32_t Ni, int32_t Nc, int32_t k) {
+  if (Ni < 0 || Nc < 0 || k <= 0) return 0;
+  return (int64_t)alad::select_plan(Ni, Nc, k).bytes;
+}
+
+extern "C" int alad_col_topk_select(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t k, int32_t img_off,
+                                    float* out_score, int32_t* out_idx, void* workspace, void* stream) {
+  using namespace alad;
+  ALAD_REQUIRE(Ni >= 0 && Nc >= 0 && ldS >= Nc, "alad_col_topk_select: bad shape");
+  ALAD_REQUIRE(k > 0 && k <= 256, "alad_col_topk_select: k=%d out of range", k);
+  if (Nc == 0) return ALAD_OK;
+  ALAD_REQUIRE(out_score && out_idx && (S || Ni == 0), "alad_col_topk_select: NULL pointer");
+  const SelectPlan pl = select_plan(Ni, Nc, k);
+  if (!pl.select)      // large k or an empty gallery: the heap kernel over all columns (one row slice)
+    return alad_col_topk(S, ldS, Ni, Nc, k, img_off, 1, out_score, out_idx, stream);
+  ALAD_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "alad_col_topk_select: bad workspace");
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  float* tau = reinterpret_cast<float*>(w + pl.off_tau);
+  int* cnt = reinterpret_cast<int*>(w + pl.off_cnt);
+  int* ovf_n = cnt + Nc;
+  int* ovf_list = reinterpret_cast<int*>(w + pl.off_ovf);
+  float* cs = reinterpret_cast<float*>(w + pl.off_cs);
+  int* ci = reinterpret_cast<int*>(w + pl.off_ci);
+  float* gmax = reinterpret_cast<float*>(w + pl.off_gmax);
+  ALAD_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)Nc + 1), st));
+  const unsigned col_blocks = (unsigned)((Nc + 31) / 32);
+  if (pl.threshold) {
+    dim3 g1(col_blocks, (unsigned)((pl.G + SEL_ROWS - 1) / SEL_ROWS)), b1(32, SEL_ROWS);
+    col_groupmax_kernel<<<g1, b1, 0, st>>>(S, ldS, Ni, Nc, pl.rows_per_group, pl.G, gmax);
+    const size_t tile_bytes = (size_t)pl.G * 33 * sizeof(float);
+    if (pl.G <= 128)      col_threshold_kernel<4><<<col_blocks, 256, tile_bytes, st>>>(gmax, Nc, pl.G, k, tau);
+    else if (pl.G <= 256) col_threshold_kernel<8><<<col_blocks, 256, tile_bytes, st>>>(gmax, Nc, pl.G, k, tau);
+    else                  col_threshold_kernel<SEL_MAX_G / 32><<<col_blocks, 256, tile_bytes, st>>>(gmax, Nc, pl.G, k, tau);
+  }
+  dim3 g3(col_blocks, (unsigned)((Ni + SEL_CHUNK - 1) / SEL_CHUNK)), b3(32, SEL_ROWS);
+  col_collect_kernel<<<g3, b3, 0, st>>>(S, ldS, Ni, Nc, img_off, pl.threshold ? tau : nullptr, pl.cap, cnt, cs, ci);
+  const size_t sel_smem = (size_t)SELECT_WARPS * pl.cap * sizeof(float2);
+  col_select_kernel<<<(unsigned)((Nc + SELECT_WARPS - 1) / SELECT_WARPS), 32 * SELECT_WARPS, sel_smem, st>>>(
+      cnt, cs, ci, Nc, k, pl.cap, out_score, out_idx, ovf_list, ovf_n);
+  // overflowed captions (normally none): per-caption heaps; CTAs beyond the queue exit immediately
+  const size_t heap_smem = (size_t)k * 32 * 8;
+  static thread_local size_t heap_set = 0;
+  if (heap_smem > 48 * 1024 && heap_smem > heap_set) {
+    ALAD_CUDA(cudaFuncSetAttribute(col_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heap_smem));
+    heap_set = heap_smem;
+  }
+  col_topk_kernel<<<dim3(col_blocks, 1), 32, heap_smem, st>>>(S, ldS, Ni, Nc, k, img_off, 1, out_score, out_idx, ovf_list,
+                                                              ovf_n);
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;
 }

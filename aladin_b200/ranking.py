@@ -39,9 +39,21 @@ def col_count(S, gt, group=5, img_off=0):
     return count
 
 
-def col_topk(S, k, img_off=0, splits=8):
-    """t2i: sorted per-caption candidates (score[splits,Nc,k], global image idx[splits,Nc,k])."""
+def col_topk(S, k, img_off=0, splits=None):
+    """t2i: sorted per-caption candidates (score[P,Nc,k], global image idx[P,Nc,k]).
+
+    Default (splits=None): the threshold-select kernels -- two sweeps of S, P = 1, already final for this
+    shard.  An explicit `splits` runs the shared-memory heap kernel over that many row slices (P = splits
+    lists to be merged with topk_merge); kept for A/B and as the overflow path of the default."""
     Ni, Nc, ld = _check_S(S)
+    if splits is None:
+        cs = torch.empty((1, Nc, k), dtype=torch.float32, device=S.device)
+        ci = torch.empty((1, Nc, k), dtype=torch.int32, device=S.device)
+        nbytes = _cabi.lib().alad_col_topk_select_workspace_bytes(Ni, Nc, k)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=S.device)
+        _cabi.check(_cabi.lib().alad_col_topk_select(S.data_ptr(), ld, Ni, Nc, k, img_off, cs.data_ptr(), ci.data_ptr(),
+                                                      ws.data_ptr(), _cabi.stream_ptr()), "alad_col_topk_select")
+        return cs, ci
     splits = max(1, min(splits, (Ni + 63) // 64))
     cs = torch.empty((splits, Nc, k), dtype=torch.float32, device=S.device)
     ci = torch.empty((splits, Nc, k), dtype=torch.int32, device=S.device)
@@ -53,6 +65,8 @@ def col_topk(S, k, img_off=0, splits=8):
 def topk_merge(cand_score, cand_idx):
     """Merge P sorted candidate lists per caption: [P,Nc,k] -> ([Nc,k], [Nc,k])."""
     P, Nc, k = cand_score.shape
+    if P == 1:                                   # a single sorted list per caption is already the result
+        return cand_score[0], cand_idx[0]
     assert cand_score.is_contiguous() and cand_idx.is_contiguous() and cand_idx.shape == cand_score.shape
     os_ = torch.empty((Nc, k), dtype=torch.float32, device=cand_score.device)
     oi = torch.empty((Nc, k), dtype=torch.int32, device=cand_score.device)

@@ -199,7 +199,13 @@ class AlignmentGallery:
             # one rank owns all captions: score chunk k while chunk k+1 is uploaded (host sources)
             on_cpu = not self.captions.is_cuda
             chunk = self.caption_chunk if on_cpu else self.Nc
-            bounds = [(c0, min(self.Nc, c0 + chunk)) for c0 in range(0, self.Nc, chunk)]
+            # host sources: the first chunks are small (chunk/8, /4, /2) so that scoring starts after a few ms of
+            # PCIe traffic instead of a whole chunk's worth; the copies stay ahead of the scoring from then on
+            bounds, c0, size = [], 0, min(chunk, max(chunk // 8, 256)) if on_cpu else chunk
+            while c0 < self.Nc:
+                bounds.append((c0, min(self.Nc, c0 + size)))
+                c0 += size
+                size = min(chunk, 2 * size)
             main = torch.cuda.current_stream()
             if on_cpu:
                 Lw_max = 1 + int(nw.max())

@@ -283,6 +283,15 @@ int alad_col_count(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t 
  * cand_score/cand_idx are [splits, Nc, k], sorted, idx = global image index (-1 = empty). */
 int alad_col_topk(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t k, int32_t img_off, int32_t splits,
                   float* cand_score, int32_t* cand_idx, void* stream);
+/* t2i step 3, threshold-select variant (the default of the drop-ins): exact, sorted top-k of every caption
+ * over this shard's images in two sweeps of S -- group maxima -> per-caption threshold = k-th largest group
+ * maximum -> candidates >= threshold -> rank among the candidates; captions whose candidate list overflows
+ * (mass ties) fall back to the heaps of alad_col_topk.  out_score/out_idx are [Nc, k], idx = global image
+ * index (-1 = fewer than k images).  Same order as numpy.argsort(...)[::-1][:k] on a stable sort
+ * (alad/evaluation.py:303-308).  Workspace: alad_col_topk_select_workspace_bytes, 16-byte aligned. */
+int64_t alad_col_topk_select_workspace_bytes(int32_t Ni, int32_t Nc, int32_t k);
+int alad_col_topk_select(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t k, int32_t img_off,
+                         float* out_score, int32_t* out_idx, void* workspace, void* stream);
 /* merge P sorted candidate lists per caption (after the all-gather across shards). */
 int alad_topk_merge(const float* cand_score, const int32_t* cand_idx, int32_t P, int32_t Nc, int32_t k,
                     float* out_score, int32_t* out_idx, void* stream);

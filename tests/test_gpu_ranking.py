@@ -73,10 +73,68 @@ def test_sharded_ranking_equals_single_shard():
     for g in range(G):
         ranking.col_gt(shards[g], gt, 5, g * per)                # stands in for the all-gather
     counts = sum(ranking.col_count(shards[g], gt, 5, g * per) for g in range(G))
-    cands = [ranking.col_topk(shards[g], k, g * per, splits=2) for g in range(G)]
+    cands = [ranking.col_topk(shards[g], k, g * per, splits=2 if g % 2 else None) for g in range(G)]
     cs = torch.cat([c[0] for c in cands]); ci = torch.cat([c[1] for c in cands])
     _, merged = ranking.topk_merge(cs, ci)
     ranks = torch.cat([ranking.rank_rows(shards[g], 5, g * per)[0] for g in range(G)])
     assert torch.equal(ranks, full_rank)
     assert torch.equal(counts.int(), full_count)
     assert torch.equal(merged, full_topk)
+
+
+def _expected_topk(S, k, img_off=0):
+    """numpy restatement of the documented order: stable argsort reversed (score desc, index desc on ties)."""
+    Ni, Nc = S.shape
+    out = np.full((Nc, k), -1, np.int64)
+    for c in range(Nc):
+        inds = _stable_desc_order(S[:, c])[:k]
+        out[c, :inds.size] = inds + img_off
+    return out
+
+
+@pytest.mark.parametrize("Ni,Nc,k,kind", [
+    (700, 300, 50, "random"),         # threshold path (Ni > 256 candidates capacity), several row groups
+    (2600, 200, 50, "random"),        # many rows per group
+    (625, 1000, 50, "ties"),          # heavy exact ties inside the top-k: still ranked by index
+    (900, 96, 50, "constant"),        # every column constant -> candidate lists overflow -> heap fallback
+    (900, 130, 50, "mixed"),          # constant, -inf-padded and random columns side by side
+    (200, 77, 50, "random"),          # Ni <= capacity: no threshold, everything is a candidate
+    (30, 40, 50, "random"),           # fewer images than k: tail filled with -1
+    (1500, 64, 100, "random"),        # the two-stage shortlist size
+    (3000, 33, 200, "random"),        # k above the select limit: heaps over all columns
+])
+def test_col_topk_select_matches_stable_argsort(Ni, Nc, k, kind):
+    from aladin_b200 import ranking
+    r = np.random.RandomState(Ni + Nc + k)
+    S = r.standard_normal((Ni, Nc)).astype(np.float32)
+    if kind == "ties":
+        S = np.round(S * 2) / 2
+    elif kind == "constant":
+        S[:] = r.standard_normal(Nc).astype(np.float32)[None, :]
+        S[:, ::3] = 0.0
+    elif kind == "mixed":
+        S[:, 0::4] = 0.0                                            # all-zero captions (no scored words)
+        keep = r.rand(Ni, Nc) < 0.05
+        S[:, 1::4] = np.where(keep[:, 1::4], S[:, 1::4], -np.inf)   # two-stage style: -inf outside the shortlist
+        S[:, 2::4] = np.where(S[:, 2::4] > 0, S[:, 2::4], -0.0)     # signed zeros compare equal
+    Sd = torch.from_numpy(S).cuda()
+    cs, ci = ranking.col_topk(Sd, k, img_off=7)
+    assert cs.shape == (1, Nc, k)
+    exp = _expected_topk(S, k, img_off=7)
+    got = ci[0].cpu().numpy()
+    np.testing.assert_array_equal(got, exp)
+    valid = exp >= 0
+    np.testing.assert_array_equal(cs[0].cpu().numpy()[valid], S[(exp - 7)[valid], np.nonzero(valid)[0]])
+    # and the heap kernel (explicit row slices + merge) agrees entry for entry
+    hs, hi = ranking.topk_merge(*ranking.col_topk(Sd, k, img_off=7, splits=3))
+    np.testing.assert_array_equal(hi.cpu().numpy(), exp)
+
+
+def test_col_topk_select_strided_view():
+    """Column slices of a wider matrix (ldS > Nc), as rank_both_directions passes them."""
+    from aladin_b200 import ranking
+    r = np.random.RandomState(3)
+    S = r.standard_normal((640, 500)).astype(np.float32)
+    Sd = torch.from_numpy(S).cuda()
+    _, ci = ranking.col_topk(Sd[:, :333], 50)
+    np.testing.assert_array_equal(ci[0].cpu().numpy(), _expected_topk(S[:, :333], 50))
