@@ -1,49 +1,80 @@
-"""Summarise an .ncu-rep (read here, no GPU): key raw metrics + top stall sites.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--top N]"""
+"""Turn an `ncu --csv --log-file` launch list (metrics gpu__time_duration.sum and, optionally,
+dram__bytes_read.sum / dram__bytes_write.sum) into the summaries kept under profiles/:
+    python tools/ncu_summary.py launches.csv --shares  > profiles/rNN_launches_*.csv     (kernel, launches, total ms, share)
+    python tools/ncu_summary.py launches.csv --hbm [--only alad] [--peak 6544.3]         (markdown table, one row per launch)"""
+import argparse
 import csv
 import io
-import subprocess
+import re
 import sys
+from collections import OrderedDict
 
-KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg ", "sm__cycles_elapsed.avg.per_second",
-        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum ",
-        "dram__bytes_write.sum ", "dram__bytes_read.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread ",
-        "launch__grid_size", "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum ",
-        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
-        "lts__t_bytes.sum ", "lts__t_sectors_srcunit_tex_op_read.sum "]
+UNIT = {"nsecond": 1e-9, "ns": 1e-9, "usecond": 1e-6, "us": 1e-6, "msecond": 1e-3, "ms": 1e-3, "second": 1.0, "s": 1.0,
+        "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
-def run(args):
-    return subprocess.run(["ncu", "-i"] + args, capture_output=True, text=True).stdout
+def launches(path):
+    """-> list of dicts {name, time_s, rd, wr} in launch order."""
+    with open(path, newline="") as f:
+        text = f.read()
+    start = text.find('"ID"')
+    if start < 0:
+        raise SystemExit(f"{path}: no ncu CSV header found")
+    rows = OrderedDict()
+    for r in csv.DictReader(io.StringIO(text[start:])):
+        try:
+            val = float(r["Metric Value"].replace(",", ""))
+        except (ValueError, KeyError, TypeError):
+            continue
+        e = rows.setdefault(r["ID"], {"name": r["Kernel Name"], "time_s": 0.0, "rd": None, "wr": None})
+        scale = UNIT.get(r.get("Metric Unit", ""), 1.0)
+        m = r["Metric Name"]
+        if m.startswith("gpu__time_duration"):
+            e["time_s"] = val * scale
+        elif m.startswith("dram__bytes_read"):
+            e["rd"] = val * scale
+        elif m.startswith("dram__bytes_write"):
+            e["wr"] = val * scale
+    return list(rows.values())
+
+
+def short(name):
+    name = re.sub(r"\(.*$", "", name)
+    return name[:110]
 
 
 def main():
-    rep = sys.argv[1]
-    top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 25
-    raw = list(csv.reader(io.StringIO(run([rep, "--page", "raw", "--csv"]))))
-    hdr, units = raw[0], raw[1]
-    for k, launch in enumerate(raw[2:]):
-        print(f"== launch {k}: {launch[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else ''}")
-        for h, u, v in zip(hdr, units, launch):
-            if any((h + ' ').startswith(key) or h == key.strip() for key in KEYS):
-                print(f"  {h} [{u}] = {v}")
-    src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
-    h = src[1]
-    ix = {n: i for i, n in enumerate(h)}
-    rows = src[2:]
-
-    def g(r, k):
-        try:
-            return float(r[ix[k]])
-        except Exception:
-            return 0.0
-    tot = sum(g(r, "# Samples") for r in rows)
-    print(f"== source: {len(rows)} SASS instructions, {int(tot)} stall samples; top {top}:")
-    for r in sorted(rows, key=lambda r: -g(r, "# Samples"))[:top]:
-        print(f"  {100 * g(r, '# Samples') / max(tot, 1):5.1f}%  exec={int(g(r, 'Instructions Executed')):>11d}  {r[ix['Source']][:90]}")
+    ap = argparse.ArgumentParser()
+    ap.add_argument("csv")
+    ap.add_argument("--shares", action="store_true")
+    ap.add_argument("--hbm", action="store_true")
+    ap.add_argument("--only", default=None, help="substring filter on kernel names")
+    ap.add_argument("--peak", type=float, default=6544.3, help="HBM copy peak, GB/s (MEASURED_PEAKS.json)")
+    a = ap.parse_args()
+    L = launches(a.csv)
+    if a.only:
+        L = [l for l in L if a.only in l["name"]]
+    if a.shares:
+        agg = OrderedDict()
+        for l in L:
+            e = agg.setdefault(short(l["name"]), [0, 0.0])
+            e[0] += 1
+            e[1] += l["time_s"]
+        total = sum(e[1] for e in agg.values())
+        print(f"# total device time of listed launches: {1e3 * total:.1f} ms")
+        print("kernel,launches,total_ms,share")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"{k},{n},{1e3 * t:.3f},{t / total:.4f}")
+    if a.hbm:
+        print("| kernel | duration | DRAM read | DRAM write | achieved GB/s | of measured HBM peak |")
+        print("|---|---|---|---|---|---|")
+        for l in L:
+            if l["rd"] is None:
+                continue
+            gbs = (l["rd"] + l["wr"]) / l["time_s"] / 1e9 if l["time_s"] > 0 else 0.0
+            print(f"| `{short(l['name'])}` | {1e6 * l['time_s']:.1f} us | {l['rd'] / 1e6:.1f} MB | {l['wr'] / 1e6:.1f} MB | "
+                  f"{gbs:.0f} | {gbs / a.peak:.2f} |")
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())
