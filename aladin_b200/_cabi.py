@@ -45,6 +45,27 @@ class ScoresFusedArgs(C.Structure):
     ]
 
 
+class TrainLossesArgs(C.Structure):
+    """struct alad_train_losses_args (include/alad_b200.h)."""
+    _fields_ = [
+        ("im_cls", C.c_void_p), ("ld_im_cls", C.c_int64), ("s_cls", C.c_void_p), ("ld_s_cls", C.c_int64),
+        ("im_set", C.c_void_p), ("im_stride_b", C.c_int64), ("im_stride_s", C.c_int64),
+        ("s_seq", C.c_void_p), ("s_stride_b", C.c_int64), ("s_stride_s", C.c_int64),
+        ("B", C.c_int32), ("S_im", C.c_int32), ("S_s", C.c_int32), ("d", C.c_int32),
+        ("nr", C.c_void_p), ("nw", C.c_void_p), ("clamp", C.c_void_p),
+        ("precision", C.c_int32), ("precision_m", C.c_int32),
+        ("margin_m", C.c_float), ("max_violation_m", C.c_int32), ("margin_a", C.c_float), ("max_violation_a", C.c_int32),
+        ("with_distill", C.c_int32), ("temperature", C.c_float), ("listnet_eps", C.c_float), ("want_grad", C.c_int32),
+        ("losses", C.c_void_p), ("M", C.c_void_p), ("S", C.c_void_p),
+        ("G_m", C.c_void_p), ("G_a", C.c_void_p), ("dM", C.c_void_p),
+        ("g", C.c_void_p), ("has_g_m", C.c_int32), ("has_g_a", C.c_int32), ("has_g_d", C.c_int32),
+        ("d_im_cls", C.c_void_p), ("d_s_cls", C.c_void_p),
+        ("d_im_set", C.c_void_p), ("d_im_stride_b", C.c_int64), ("d_im_stride_s", C.c_int64),
+        ("d_s_seq", C.c_void_p), ("d_s_stride_b", C.c_int64), ("d_s_stride_s", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 class MrswBwdArgs(C.Structure):
     _fields_ = [
         ("im", C.c_void_p), ("im_stride_b", C.c_int64), ("im_stride_s", C.c_int64),
@@ -78,6 +99,9 @@ PROTOTYPES = {
     "alad_loss_workspace_bytes": (C.c_int64, [_I32]),
     "alad_triplet_fwd_bwd": (C.c_int, [_P, _I64, _I32, C.c_float, _I32, _P, _P, _I64, _P, _P, _P, _P]),
     "alad_listnet_fwd_bwd": (C.c_int, [_P, _I64, _P, _I64, _I32, C.c_float, C.c_float, _P, _P, _I64, _P, _P]),
+    "alad_train_losses_workspace_bytes": (C.c_int64, [_I32, _I32, _I32, _I32, _I32, _I32]),
+    "alad_train_losses_fwd": (C.c_int, [C.POINTER(TrainLossesArgs), _P]),
+    "alad_train_losses_bwd": (C.c_int, [C.POINTER(TrainLossesArgs), _P]),
     "alad_distill_workspace_bytes": (C.c_int64, [_I32, _I32]),
     "alad_distill_mse_fwd_bwd": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _P, _P, _P]),
     "alad_distill_contrastive_fwd_bwd": (C.c_int, [_P, _I64, _P, _I64, _I32, C.c_float, _I32, _P, _P, _I64, _P, _P]),
@@ -126,6 +150,7 @@ KERNELS_PER_CALL = {
     "alad_triplet_fwd_bwd": 2, "alad_listnet_fwd_bwd": 3, "alad_rank_rows": 1, "alad_col_gt": 1,
     "alad_col_count": 1, "alad_col_topk": 1, "alad_col_topk_select": 5, "alad_topk_merge": 1, "alad_shortlist_scatter": 2,
     "alad_distill_mse_fwd_bwd": 1, "alad_distill_contrastive_fwd_bwd": 2, "alad_distill_ordinal_fwd_bwd": 2,
+    "alad_train_losses_fwd": 13, "alad_train_losses_bwd": 16,
     "alad_order_scores": 1, "alad_order_scores_bwd": 1, "alad_normalize_bwd": 1, "alad_pool_tokens_bwd": 1,
 }
 launch_count = {"kernels": 0}

@@ -7,11 +7,12 @@
 //   M (TMEM lanes, 128 / tile)   = densely packed valid WORD rows of all captions
 //   N (TMEM columns, 240 / tile) = densely packed valid REGION rows, whole images per tile
 //   K                            = feature dim (bf16, or 3x for the split-precision mode)
-// One persistent CTA per SM, 6 warps:
-//   warps 0-3  epilogue: tcgen05.ld -> per-thread max over each image's columns ->
-//              smem -> ordered per-caption row sums -> <= 2 atomic addends per S entry
-//   warp 4     TMA producer (4-stage smem ring, 128B swizzle)
-//   warp 5     tcgen05.mma issuer (one lane), 2 accumulator stages in TMEM
+// Persistent kernel, 6 warps per CTA; default variant = CTA PAIRS (tcgen05 cta_group::2, one 256 x 240 tile per pair
+// and iteration, 74 pairs on 148 SMs), single-CTA variant (128 x 240) kept for A/B:
+//   warps 0-3  epilogue: tcgen05.ld windows -> FMNMX3 max over each image's columns -> smem -> ordered
+//              per-caption row sums -> <= 2 atomic addends per S entry (bit-reproducible)
+//   warp 4     TMA producer (6-stage smem ring for pairs / 4-stage single, 128B swizzle, L2 prefetch of the next word rows)
+//   warp 5     tcgen05.mma issuer (one lane of the leader CTA), 2 accumulator stages in TMEM
 #include <math.h>
 #include <stdlib.h>
 

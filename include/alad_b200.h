@@ -218,6 +218,56 @@ int alad_listnet_fwd_bwd(const float* teacher, int64_t ldT, const float* student
                          void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * alad_train_losses_fwd / alad_train_losses_bwd -- the loss stack of ALADModel.forward_loss
+ * (alad/alad_model.py:371-428: matching_criterion :380, alignment_criterion :386, distillation_loss :405) in ONE
+ * native call per direction, for the configuration every shipped config selects (measure 'dot', aggregation
+ * 'MrSw', distillation 'listnet').  Pure composition of alad_scores_fused, alad_triplet_fwd_bwd,
+ * alad_listnet_fwd_bwd and alad_mrsw_scores_bwd on the caller's stream (plus a scaled-sum/transpose helper
+ * kernel for the matching head's backward GEMM operands): at B <= 512 the step is bound by the host cost of
+ * its ~35 launches, not by the device.
+ *   fwd: M = im_cls @ s_cls.T, losses[0] = hinge(M); S = MrSw(im_set, s_seq), losses[1] = hinge(S);
+ *        losses[2] = ListNet(teacher = S, student = M) (0 when !with_distill); with want_grad the dense
+ *        gradients G_m = dlosses[0]/dM, G_a = dlosses[1]/dS, dM = dlosses[2]/dM are kept for the backward call.
+ *   bwd: g = DEVICE [3] upstream gradients of the three losses (has_g_* = 0: that loss got no gradient);
+ *        d im_cls = (g0 G_m + g2 dM) @ s_cls, d s_cls = (g0 G_m + g2 dM).T @ im_cls (split-precision GEMMs),
+ *        (d im_set, d s_seq) = sparse MrSw backward of g1 G_a.  Output pointers may be NULL (not needed).
+ * nr / nw / clamp are HOST arrays (valid scored counts per image / caption, "has masked slots" flags);
+ * M, S, G_m, G_a, dM are contiguous [B, B]; d im_cls / d s_cls contiguous [B, d]; workspace 256-byte aligned,
+ * alad_train_losses_workspace_bytes(..., backward = 0 | 1).
+ * ------------------------------------------------------------------------------- */
+typedef struct alad_train_losses_args {
+  const float* im_cls;  int64_t ld_im_cls;       /* [B, d] matching-head vectors (normalised by the model) */
+  const float* s_cls;   int64_t ld_s_cls;
+  const float* im_set;  int64_t im_stride_b, im_stride_s;   /* [B, S_im, d] raw tokens, innermost stride 1 */
+  const float* s_seq;   int64_t s_stride_b, s_stride_s;     /* [B, S_s, d]                                 */
+  int32_t B, S_im, S_s, d;
+  const int32_t* nr;             /* HOST [B] */
+  const int32_t* nw;             /* HOST [B] */
+  const uint8_t* clamp;          /* HOST [B] or NULL */
+  int32_t precision;             /* alignment score kernel: 0 = bf16 operands, 1 = split hi/lo */
+  int32_t precision_m;           /* matching GEMM (forward) likewise */
+  float margin_m;  int32_t max_violation_m;      /* matching_criterion  */
+  float margin_a;  int32_t max_violation_a;      /* alignment_criterion */
+  int32_t with_distill;
+  float temperature, listnet_eps;                /* 6.0, 1e-10 (alad/loss.py:430-443) */
+  int32_t want_grad;
+  float* losses;                 /* [3] matching, alignment, distillation */
+  float* M;  float* S;           /* [B, B] score matrices */
+  float* G_m;  float* G_a;  float* dM;
+  const float* g;                /* backward: [3] upstream gradients */
+  int32_t has_g_m, has_g_a, has_g_d;
+  float* d_im_cls;  float* d_s_cls;
+  float* d_im_set;  int64_t d_im_stride_b, d_im_stride_s;   /* element strides, 0 = contiguous [B, S, d] */
+  float* d_s_seq;   int64_t d_s_stride_b, d_s_stride_s;
+  void* workspace;
+  int64_t workspace_bytes;
+} alad_train_losses_args;
+int64_t alad_train_losses_workspace_bytes(int32_t B, int32_t S_im, int32_t S_s, int32_t d, int32_t precision,
+                                          int32_t backward);
+int alad_train_losses_fwd(const alad_train_losses_args* a, void* stream);
+int alad_train_losses_bwd(const alad_train_losses_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * The remaining DistillationLoss modes (alad/loss.py:371-425), forward + gradient in one call;
  * workspace: alad_distill_workspace_bytes(B, mode) with mode 0 = mse, 1 = contrastive, 2 = ordinal.
  * alad_distill_mse_fwd_bwd -- 'mse' (loss.py:371-373): loss = mean((student*wb[0] + wb[1] - teacher)^2);

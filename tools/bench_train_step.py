@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, ".")
 import aladin_b200  # noqa: E402
-from aladin_b200 import loss as L, synth  # noqa: E402
+from aladin_b200 import alad_model as AM, loss as L, synth  # noqa: E402
 
 
 def timeit(fn, iters=100, warm=10):
@@ -26,7 +26,7 @@ def timeit(fn, iters=100, warm=10):
     return e0.elapsed_time(e1) / iters
 
 
-def make_step(B, precision):
+def make_step(B, precision, fused=False):
     """(fwd, fwd_bwd, il, cl): the three-criterion training step of alad_model.py:371-428 on synthetic features."""
     im, s, il, cl = synth.raw_batch(9, B, B, 35, 53, 1024, related=0.6)
     r = np.random.RandomState(1)
@@ -44,6 +44,10 @@ def make_step(B, precision):
     aladin_b200.set_precision(precision)
 
     def fwd():
+        if fused:       # aladin_b200.alad_model: one native call per direction (the forward_loss call site)
+            ml, al, d, _, _ = AM.train_losses(img_cls, cap_cls, img_set.permute(1, 0, 2), cap_seq.permute(1, 0, 2), il, cl,
+                                              margin=0.2, max_violation=True)
+            return al + d + 0.1 * ml
         ml, mm = mc(img_cls, cap_cls, return_similarity_mat=True)
         al, ts = ac(img_set.permute(1, 0, 2), cap_seq.permute(1, 0, 2), il, cl, return_similarity_mat=True)
         return al + dl(ts, mm) + 0.1 * ml
@@ -56,8 +60,8 @@ def make_step(B, precision):
     return fwd, fwd_bwd, il, cl
 
 
-def train_step(B, precision):
-    fwd, fwd_bwd, il, cl = make_step(B, precision)
+def train_step(B, precision, fused=False):
+    fwd, fwd_bwd, il, cl = make_step(B, precision, fused)
     with torch.no_grad():
         t_f = timeit(fwd)
     t_fb = timeit(fwd_bwd)
@@ -72,7 +76,7 @@ def train_step(B, precision):
         torch.cuda.synchronize()
     t_host = 1e3 * sorted(host)[len(host) // 2]
     flop = 2.0 * sum(l - 1 for l in il) * sum(l - 3 for l in cl) * 1024
-    return {"B": B, "precision": precision, "fwd_ms": t_f, "fwd_bwd_ms": t_fb, "fwd_bwd_host_enqueue_ms": t_host, "pairs_per_s_fwd": B * B / t_f * 1e3,
+    return {"B": B, "precision": precision, "path": "fused forward_loss" if fused else "per-criterion drop-ins", "fwd_ms": t_f, "fwd_bwd_ms": t_fb, "fwd_bwd_host_enqueue_ms": t_host, "pairs_per_s_fwd": B * B / t_f * 1e3,
             "pairs_per_s_fwd_bwd": B * B / t_fb * 1e3, "fwd_algorithmic_tflops": flop / t_f / 1e9}
 
 
@@ -89,7 +93,7 @@ def loss_kernels(B):
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "profile":      # ncu launch list: 1 warm-up + 1 profiled step
-        _, step, _, _ = make_step(int(sys.argv[2]), sys.argv[3] if len(sys.argv) > 3 else "bf16")
+        _, step, _, _ = make_step(int(sys.argv[2]), sys.argv[3] if len(sys.argv) > 3 else "bf16", fused=len(sys.argv) > 4)
         step()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
@@ -100,7 +104,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "hostprof":     # where the host time of a step goes (cProfile, no sync inside)
         import cProfile
         import pstats
-        _, step, _, _ = make_step(int(sys.argv[2]), "bf16")
+        _, step, _, _ = make_step(int(sys.argv[2]), "bf16", fused=len(sys.argv) > 3)
         for _ in range(5):
             step()
         torch.cuda.synchronize()
@@ -112,6 +116,6 @@ if __name__ == "__main__":
         pr.disable()
         pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
         sys.exit(0)
-    out = {"train_step": [train_step(B, p) for B in (128, 512) for p in ("bf16", "fp32")],
+    out = {"train_step": [train_step(B, p, f) for B in (128, 512) for p in ("bf16", "fp32") for f in (False, True)],
            "loss_kernels": [loss_kernels(B) for B in (512, 8192)]}
     print(json.dumps(out, indent=1))
