@@ -24,7 +24,7 @@ int sm_count() {
 
 }  // namespace alad
 
-extern "C" int alad_abi_version(void) { return 2; }
+extern "C" int alad_abi_version(void) { return 3; }
 extern "C" const char* alad_last_error(void) { return alad::error_buffer(); }
 
 extern "C" int alad_h2d_2d(void* dst, int64_t dst_pitch, const void* src_host, int64_t src_pitch, int64_t width_bytes,

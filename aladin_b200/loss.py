@@ -10,7 +10,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import _cabi, scoring
+from . import _cabi, scan, scoring
 
 
 def _ws(nbytes, device):
@@ -438,9 +438,11 @@ class Contrastive(nn.Module):
 
 class AlignmentContrastiveLoss(Contrastive):
     """alad/loss.py:70-159.  'MrSw' (every shipped config), 'MrAVGw', 'MwSr', 'symm' run the fused
-    tcgen05 kernel; 'sum' / 'mean' collapse to one GEMM of pooled token sums (forward only)."""
+    tcgen05 kernel; 'sum' / 'mean' collapse to one GEMM of pooled token sums; 'scan-sentences'
+    (loss.py:136-149) is a plain GEMM of the unit token rows plus the per-pair attention kernels of
+    csrc/scan_pool.cu (aladin_b200/scan.py)."""
 
-    SUPPORTED = scoring.AGGREGATIONS
+    SUPPORTED = scoring.AGGREGATIONS + ("scan-sentences",)
 
     def __init__(self, margin=0, measure=False, max_violation=False, aggregation='sum-max-sentences'):
         super().__init__(margin, measure, max_violation)
@@ -449,14 +451,17 @@ class AlignmentContrastiveLoss(Contrastive):
 
     def forward(self, im_set, s_seq, im_len, s_len, return_loss=True, return_similarity_mat=False):
         if self.aggregation not in self.SUPPORTED:
-            raise NotImplementedError(
-                f"aggregation {self.aggregation!r} is not ported ('scan-sentences' is a different algorithm, "
-                "alad/loss.py:136-149); supported: " + ", ".join(self.SUPPORTED))
+            # the reference leaves `aggr_similarity` unbound for an unknown mode (alad/loss.py:120-151)
+            raise UnboundLocalError(f"aggregation {self.aggregation!r} is not one of " + ", ".join(self.SUPPORTED))
         out_dev = im_set.device
-        loss, S = _AlignmentFn.apply(im_set, s_seq, list(im_len), list(s_len), self.margin, self.max_violation,
-                                     bool(return_loss), self.precision, self.aggregation)
+        if self.aggregation == "scan-sentences":
+            S = scan.ScanScoresFn.apply(im_set, s_seq, list(im_len), list(s_len), self.precision)
+            loss = self.compute_contrastive_loss(S) if return_loss else None
+        else:
+            loss, S = _AlignmentFn.apply(im_set, s_seq, list(im_len), list(s_len), self.margin, self.max_violation,
+                                         bool(return_loss), self.precision, self.aggregation)
         if out_dev.type != "cuda":
-            loss, S = loss.to(out_dev), S.to(out_dev)
+            loss, S = (loss.to(out_dev) if loss is not None else None), S.to(out_dev)
         if return_loss and return_similarity_mat:
             return loss, S
         elif return_loss:

@@ -315,6 +315,35 @@ int alad_pool_tokens_bwd(const float* src, int64_t stride_b, int64_t stride_s, i
                          void* stream);
 
 /* ---------------------------------------------------------------------------------
+ * Aggregation 'scan-sentences' of AlignmentContrastiveLoss.forward (alad/loss.py:136-149): relu of the masked
+ * region x word cosines, L2 normalisation over the regions, softmax over the unmasked words, attended word
+ * vector per region, cosine of region and attended vector, sum over the unmasked regions.  The reference
+ * materialises B x B x R x W x d tensors (loss.py:143-146); here <x_r, att_r> = sum_w alpha[r,w] C[r,w] and
+ * ||att_r||^2 = alpha_r' K_j alpha_r, so a pair needs only its cosine block C (a plain GEMM of the unit token rows
+ * on the tcgen05 kernel: alad_scores_fused, epilogue 1) and the Gram matrix K_j of the caption's unit word rows.
+ *   yh  [Bc*W, d]   unit word rows, caption j = rows j*W .. j*W+W-1 (slots 1 .. W of the caption container)
+ *   C   [Bi*R, ldC] cosines: row i*R + r, column j*W + w
+ *   nr / nw         DEVICE valid scored counts per image / caption; max_nr / max_nw = host upper bounds of them
+ *                   (shared-memory extents; at most 128 each)
+ * alad_scan_gram      K [Bc, W, W] (entries outside the valid nw x nw block are 0)
+ * alad_scan_pool_fwd  S[i, j]; 0 for an image without valid regions, NaN for a caption without valid words
+ *                     (softmax over an all -inf row, loss.py:139-140), like the reference
+ * alad_scan_pool_bwd  dC [Bi*R, lddC] = dL/dC for dL/dS = G (zeroed inside, dense: feeds the two backward GEMMs)
+ *                     and dK [Bc, W, W] += dL/dK (the CALLER zeroes dK before the first image chunk); pairs with
+ *                     G = 0 are skipped.  Masked regions get a zero gradient (the reference yields NaN there).
+ * alad_scan_gram_bwd  d_yh [Bc*W, d] += 2 dK yh (dK is symmetric by construction)
+ * ------------------------------------------------------------------------------- */
+int alad_scan_gram(const float* yh, int32_t Bc, int32_t W, int32_t d, const int32_t* nw, float* K, void* stream);
+int alad_scan_gram_bwd(const float* yh, int32_t Bc, int32_t W, int32_t d, const int32_t* nw, const float* dK,
+                       float* d_yh, void* stream);
+int alad_scan_pool_fwd(const float* C, int64_t ldC, int32_t Bi, int32_t R, int32_t Bc, int32_t W, const int32_t* nr,
+                       const int32_t* nw, int32_t max_nr, int32_t max_nw, const float* K, float* S, int64_t ldS,
+                       void* stream);
+int alad_scan_pool_bwd(const float* C, int64_t ldC, int32_t Bi, int32_t R, int32_t Bc, int32_t W, const int32_t* nr,
+                       const int32_t* nw, int32_t max_nr, int32_t max_nw, const float* K, const float* G, int64_t ldG,
+                       float* dC, int64_t lddC, float* dK, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Ranking -- replaces numpy.argsort + numpy.where of alad/evaluation.py:213-223,303-308
  * and alad/recall_auxiliary.py:34-56.  Order = score descending, index descending on
  * exact ties (= stable argsort reversed).  S is image-major [Ni, ldS]; ground truth of

@@ -452,6 +452,111 @@ def mrsw_backward(im_set, s_seq, im_len, s_len, G):
 
 
 # --------------------------------------------------------------------------------------
+# aggregation 'scan-sentences' (alad/loss.py:136-149): attention of every region over the words
+# --------------------------------------------------------------------------------------
+
+
+def _scan_pair_forward(C, K):
+    """One (image, caption) pair on its VALID tokens.  C[nr,nw] = region x word cosines, K[nw,nw] = Gram matrix of
+    the caption's unit word vectors.  Follows alad/loss.py:137-147: relu, L2-normalise over the regions (dim=2,
+    eps 1e-12), softmax over the unmasked words (masked logits are -inf), attended word vector per region, cosine
+    of region and attended vector (eps 1e-8; <x, att> = alpha.C and ||att||^2 = alpha' K alpha).  Returns the
+    intermediates needed by the backward."""
+    P = np.maximum(C, 0.0)
+    n = np.sqrt((P * P).sum(axis=0))                                   # [nw] norm over the regions
+    inv_n = 1.0 / np.maximum(n, 1e-12)
+    Q = P * inv_n[None, :]
+    E = np.exp(Q - Q.max(axis=1, keepdims=True))
+    alpha = E / E.sum(axis=1, keepdims=True)                           # [nr,nw]
+    T = alpha @ K                                                      # [nr,nw]  (K symmetric)
+    u = (alpha * C).sum(axis=1)
+    v = (alpha * T).sum(axis=1)
+    b = np.sqrt(np.maximum(v, 0.0))
+    new = u / np.maximum(b, 1e-8)
+    return dict(P=P, n=n, inv_n=inv_n, Q=Q, alpha=alpha, T=T, u=u, v=v, b=b, new=new)
+
+
+def _scan_pair_backward(C, K, g):
+    """(dL/dC [nr,nw], dL/dK [nw,nw]) of one pair for dL/dS = g (autograd through alad/loss.py:137-149)."""
+    f = _scan_pair_forward(C, K)
+    alpha, T, u, b = f["alpha"], f["T"], f["u"], f["b"]
+    live = b > 1e-8                                                   # clamp of F.cosine_similarity inactive
+    cu = np.where(live, g / np.maximum(b, 1e-300), g / 1e-8)          # g * d new / d u
+    cv = np.where(live, -0.5 * g * u / np.maximum(b, 1e-300) ** 3, 0.0)   # g * d new / d v
+    d_alpha = cu[:, None] * C + 2.0 * cv[:, None] * T
+    dQ = alpha * (d_alpha - (alpha * d_alpha).sum(axis=1, keepdims=True))
+    dot = (f["Q"] * dQ).sum(axis=0)
+    dP = np.where(f["n"][None, :] > 1e-12, (dQ - f["Q"] * dot[None, :]) * f["inv_n"][None, :], dQ * 1e12)
+    dC = dP * (C > 0.0) + cu[:, None] * alpha
+    return dC, (alpha * cv[:, None]).T @ alpha
+
+
+def scan_scores(im_set, s_seq, im_len, s_len, acc64: bool = True):
+    """Scores of aggregation 'scan-sentences' (alad/loss.py:136-149) without the 4-D tensors.
+    Masked regions contribute 0 (loss.py:147); a caption without valid words gives NaN for every image that
+    has valid regions (softmax over an all -inf row, loss.py:139-140), like the reference."""
+    dt = np.float64 if acc64 else F32
+    imh = l2_normalize(im_set).astype(dt)
+    sh = l2_normalize(s_seq).astype(dt)
+    R, W, nr, nw = scored_extents(im_set.shape, s_seq.shape, im_len, s_len)
+    if W == 0:
+        raise IndexError("scan-sentences indexes word 0 of the mask (alad/loss.py:147): empty word extent")
+    Bi, Bc = imh.shape[0], sh.shape[0]
+    S = np.zeros((Bi, Bc), dtype=dt)
+    for j in range(Bc):
+        Y = sh[j, 1:1 + nw[j]]
+        K = Y @ Y.T
+        for i in range(Bi):
+            if nr[i] == 0:
+                continue
+            if nw[j] == 0:
+                S[i, j] = np.nan
+                continue
+            X = imh[i, 1:1 + nr[i]]
+            S[i, j] = _scan_pair_forward(X @ Y.T, K)["new"].sum()
+    return S.astype(F32)
+
+
+def scan_backward(im_set, s_seq, im_len, s_len, G):
+    """Gradient of sum(G * S) for aggregation 'scan-sentences' w.r.t. the raw inputs, fp64 internally
+    (autograd through alad/loss.py:80-81, 137-149).  Pairs with nw = 0 are skipped (the reference yields NaN)."""
+    im_raw = np.asarray(im_set, dtype=np.float64)
+    s_raw = np.asarray(s_seq, dtype=np.float64)
+    G = np.asarray(G, dtype=np.float64)
+    R, W, nr, nw = scored_extents(im_raw.shape, s_raw.shape, im_len, s_len)
+
+    def norm(x):
+        n = np.maximum(np.sqrt((x * x).sum(-1, keepdims=True)), 1e-12)
+        return x / n, n
+
+    imh, imn = norm(im_raw)
+    sh, sn = norm(s_raw)
+    d_imh = np.zeros_like(imh)
+    d_sh = np.zeros_like(sh)
+    for j in range(sh.shape[0]):
+        if nw[j] == 0:
+            continue
+        Y = sh[j, 1:1 + nw[j]]
+        K = Y @ Y.T
+        dK = np.zeros_like(K)
+        for i in range(imh.shape[0]):
+            g = G[i, j]
+            if g == 0.0 or nr[i] == 0:
+                continue
+            X = imh[i, 1:1 + nr[i]]
+            dC, dKp = _scan_pair_backward(X @ Y.T, K, g)
+            dK += dKp
+            d_imh[i, 1:1 + nr[i]] += dC @ Y
+            d_sh[j, 1:1 + nw[j]] += dC.T @ X
+        d_sh[j, 1:1 + nw[j]] += (dK + dK.T) @ Y
+
+    def norm_bwd(xh, n, dxh):
+        return (dxh - xh * (xh * dxh).sum(-1, keepdims=True)) / n
+
+    return norm_bwd(imh, imn, d_imh).astype(F32), norm_bwd(sh, sn, d_sh).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
 # a6-a8: ranking (alad/evaluation.py:213-235, 303-320; alad/recall_auxiliary.py:34-64)
 # --------------------------------------------------------------------------------------
 

@@ -13,6 +13,8 @@ Reference entry points exercised (mesnico/ALADIN @ d1bd7bf):
   alad/loss.py:359-447  DistillationLoss          (listnet)
   alad/evaluation.py:158-327  i2t / t2i           (alignment callback and slot-0 path)
   alad/recall_auxiliary.py:133-149  compute_recall
+
+Optional arguments select single generators (e.g. `make_golden.py scan_sentences`).
 """
 import contextlib
 import io
@@ -331,12 +333,79 @@ def golden_pooled_grads():
     save("pooled_grads", **out)
 
 
+# ---------------------------------------------------------------------------------------
+# 9. aggregation 'scan-sentences' (alad/loss.py:136-149): scores, hinge loss and gradients
+# ---------------------------------------------------------------------------------------
+def golden_scan_sentences():
+    r = rs(23)
+    out = {}
+    # (a) rectangular, ragged, dense upstream gradient
+    Bi, Bc, S_im, S_s, d = 5, 6, 8, 10, 24
+    im = r.standard_normal((Bi, S_im, d)).astype(np.float32) * 1.3
+    s = r.standard_normal((Bc, S_s, d)).astype(np.float32) * 0.8
+    im_len = [8, 3, 5, 8, 2]
+    s_len = [10, 5, 4, 10, 7, 6]
+    Gup = r.standard_normal((Bi, Bc)).astype(np.float32)
+    im_t, s_t = t(im, True), t(s, True)
+    crit = rloss.AlignmentContrastiveLoss(aggregation="scan-sentences")
+    S = crit(im_t, s_t, im_len, s_len, return_loss=False, return_similarity_mat=True)
+    (S * t(Gup)).sum().backward()
+    out.update(a_im=im, a_s=s, a_im_len=np.array(im_len), a_s_len=np.array(s_len), a_Gup=Gup, a_S=S.detach().numpy(),
+               a_dim=im_t.grad.numpy(), a_ds=s_t.grad.numpy())
+    # (b) square batch in the training layout ([S,B,d] permuted like alad_model.py:377-378), hinge loss with
+    #     hardest negatives (sparse dL/dS) and with the plain sums
+    B, S_im, S_s, d = 7, 9, 12, 32
+    base = r.standard_normal((B, d)).astype(np.float32)
+    im = (r.standard_normal((S_im, B, d)) + 0.8 * base[None]).astype(np.float32)
+    s = (r.standard_normal((S_s, B, d)) + 0.8 * base[None]).astype(np.float32)
+    im_len = [9, 9, 4, 6, 9, 2, 7]
+    s_len = [12, 7, 12, 5, 9, 12, 4]
+    out.update(b_im=im, b_s=s, b_im_len=np.array(im_len), b_s_len=np.array(s_len))
+    for tag, mv in (("mv", True), ("sum", False)):
+        im_t, s_t = t(im, True), t(s, True)
+        crit = rloss.AlignmentContrastiveLoss(margin=0.2, max_violation=mv, aggregation="scan-sentences")
+        loss, S = crit(im_t.permute(1, 0, 2), s_t.permute(1, 0, 2), im_len, s_len, return_loss=True,
+                       return_similarity_mat=True)
+        loss.backward()
+        out.update({f"b_S": S.detach().numpy(), f"b_loss_{tag}": loss.detach().numpy(),
+                    f"b_dim_{tag}": im_t.grad.numpy(), f"b_ds_{tag}": s_t.grad.numpy()})
+    # (c) degenerate lengths: a caption without valid words (NaN column), an image without valid regions (0 row)
+    Bi, Bc, S_im, S_s, d = 3, 4, 6, 8, 16
+    im = r.standard_normal((Bi, S_im, d)).astype(np.float32)
+    s = r.standard_normal((Bc, S_s, d)).astype(np.float32)
+    im_len = [6, 1, 4]
+    s_len = [8, 3, 5, 2]
+    crit = rloss.AlignmentContrastiveLoss(aggregation="scan-sentences")
+    with torch.no_grad():
+        S = crit(t(im), t(s), im_len, s_len, return_loss=False, return_similarity_mat=True)
+    out.update(c_im=im, c_s=s, c_im_len=np.array(im_len), c_s_len=np.array(s_len), c_S=S.numpy())
+    # (d) every image full length (the only case in which the reference's gradient is finite: a masked region
+    #     makes the softmax row all -inf, loss.py:139-140, and NaN * 0 reaches every scored word slot), ragged
+    #     captions, dense upstream gradient, plus the hinge loss with hardest negatives
+    B, S_im, S_s, d = 6, 7, 11, 40
+    base = r.standard_normal((B, d)).astype(np.float32)
+    im = (r.standard_normal((B, S_im, d)) + 0.1 * base[:, None]).astype(np.float32)
+    s = (r.standard_normal((B, S_s, d)) + 0.1 * base[:, None]).astype(np.float32)
+    im_len = [S_im] * B
+    s_len = [11, 6, 4, 11, 8, 5]
+    Gup = r.standard_normal((B, B)).astype(np.float32)
+    im_t, s_t = t(im, True), t(s, True)
+    crit = rloss.AlignmentContrastiveLoss(margin=0.2, max_violation=True, aggregation="scan-sentences")
+    S = crit(im_t, s_t, im_len, s_len, return_loss=False, return_similarity_mat=True)
+    (S * t(Gup)).sum().backward()
+    out.update(d_im=im, d_s=s, d_im_len=np.array(im_len), d_s_len=np.array(s_len), d_Gup=Gup, d_S=S.detach().numpy(),
+               d_dim=im_t.grad.numpy(), d_ds=s_t.grad.numpy())
+    im_t, s_t = t(im, True), t(s, True)
+    loss = crit(im_t, s_t, im_len, s_len)
+    loss.backward()
+    out.update(d_loss=loss.detach().numpy(), d_dim_loss=im_t.grad.numpy(), d_ds_loss=s_t.grad.numpy())
+    assert all(np.isfinite(out[k]).all() for k in ("d_dim", "d_ds", "d_dim_loss", "d_ds_loss")) and float(loss) > 0
+    save("scan_sentences", **out)
+
+
 if __name__ == "__main__":
-    golden_alignment_scores()
-    golden_alignment_loss()
-    golden_matching()
-    golden_triplet_listnet()
-    golden_retrieval()
-    golden_train_step()
-    golden_distill_modes()
-    golden_pooled_grads()
+    only = sys.argv[1:]
+    for fn in (golden_alignment_scores, golden_alignment_loss, golden_matching, golden_triplet_listnet, golden_retrieval,
+               golden_train_step, golden_distill_modes, golden_pooled_grads, golden_scan_sentences):
+        if not only or fn.__name__ in only or fn.__name__.replace("golden_", "") in only:
+            fn()

@@ -224,3 +224,42 @@ def test_torch_port_matches_reference_golden():
     np.testing.assert_array_equal(top50, r["top50"])
     np.testing.assert_allclose(m_i[:5], r["m_i2t"][:5])
     np.testing.assert_allclose(m_t[:5], r["m_t2i"][:5])
+
+
+def test_scan_sentences_scores_match_reference():
+    """aggregation 'scan-sentences' (alad/loss.py:136-149): ragged, training layout, degenerate lengths."""
+    g = load_golden("scan_sentences")
+    S = O.scan_scores(g["a_im"], g["a_s"], g["a_im_len"].tolist(), g["a_s_len"].tolist())
+    np.testing.assert_allclose(S, g["a_S"], rtol=2e-5, atol=2e-6)
+    im, s = np.transpose(g["b_im"], (1, 0, 2)), np.transpose(g["b_s"], (1, 0, 2))
+    S = O.scan_scores(im, s, g["b_im_len"].tolist(), g["b_s_len"].tolist())
+    np.testing.assert_allclose(S, g["b_S"], rtol=2e-5, atol=2e-6)
+    for key, mv in (("mv", True), ("sum", False)):
+        np.testing.assert_allclose(O.triplet_loss(S, 0.2, mv), g[f"b_loss_{key}"], rtol=1e-5)
+    # an image without valid regions scores 0, a caption without valid words NaN (reference: softmax of -inf)
+    S = O.scan_scores(g["c_im"], g["c_s"], g["c_im_len"].tolist(), g["c_s_len"].tolist(), acc64=False)
+    ref = g["c_S"]
+    assert np.array_equal(np.isnan(S), np.isnan(ref)) and np.isnan(ref[0, 1]) and np.all(ref[1] == 0)
+    np.testing.assert_allclose(S, ref, rtol=2e-5, atol=2e-6, equal_nan=True)
+
+
+def test_scan_sentences_backward_matches_reference_where_it_is_finite():
+    g = load_golden("scan_sentences")
+    il, sl = g["d_im_len"].tolist(), g["d_s_len"].tolist()
+    np.testing.assert_allclose(O.scan_scores(g["d_im"], g["d_s"], il, sl), g["d_S"], rtol=2e-5, atol=2e-6)
+    d_im, d_s = O.scan_backward(g["d_im"], g["d_s"], il, sl, g["d_Gup"])
+    np.testing.assert_allclose(d_im, g["d_dim"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(d_s, g["d_ds"], rtol=1e-4, atol=2e-6)
+    G = O.triplet_grad(g["d_S"], 0.2, True)
+    d_im, d_s = O.scan_backward(g["d_im"], g["d_s"], il, sl, G)
+    np.testing.assert_allclose(d_im, g["d_dim_loss"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(d_s, g["d_ds_loss"], rtol=1e-4, atol=2e-6)
+    # ragged images: the reference's gradient is NaN on every scored word slot and on the masked region slots;
+    # where it is finite (images without masked slots) it equals the oracle's
+    il, sl = g["a_im_len"].tolist(), g["a_s_len"].tolist()
+    d_im, d_s = O.scan_backward(g["a_im"], g["a_s"], il, sl, g["a_Gup"])
+    ref = g["a_dim"]
+    assert np.isnan(g["a_ds"][:, 1:-2]).all() and np.isfinite(d_im).all() and np.isfinite(d_s).all()
+    full = [i for i, l in enumerate(il) if l == g["a_im"].shape[1]]
+    assert full and np.isfinite(ref[full]).all()
+    np.testing.assert_allclose(d_im[full], ref[full], rtol=1e-4, atol=2e-6)
