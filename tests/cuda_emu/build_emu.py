@@ -11,7 +11,7 @@ CSRC = os.path.join(ROOT, "aladin_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 
 _LAUNCH = re.compile(r"(\b[\w:]+(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\);", re.S)
-_DYN_SMEM = re.compile(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];")
+_DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];")
 
 
 def translate(src):

@@ -109,8 +109,71 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   return out;
 }
 template <class T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+  using namespace cuda_emu;
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  cta->xchg[tid] = raw;
+  warp_barrier();
+  raw = cta->xchg[(tid & ~31) | (src_lane & 31)];
+  warp_barrier();
+  T out;
+  memcpy(&out, &raw, sizeof(T));
+  return out;
+}
+template <class T>
+inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
+  using namespace cuda_emu;
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  cta->xchg[tid] = raw;
+  warp_barrier();
+  const int src = (tid & 31) + (int)delta;
+  if (src < 32) raw = cta->xchg[(tid & ~31) | src];
+  warp_barrier();
+  T out;
+  memcpy(&out, &raw, sizeof(T));
+  return out;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+  using namespace cuda_emu;
+  cta->xchg[tid] = pred ? 1 : 0;
+  warp_barrier();
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m |= (unsigned)(cta->xchg[(tid & ~31) | l] & 1) << l;
+  warp_barrier();
+  return m;
+}
+template <class T>
+inline T __reduce_add_sync(unsigned, T v) {
+  using namespace cuda_emu;
+  cta->xchg[tid] = (uint64_t)(int64_t)v;
+  warp_barrier();
+  int64_t acc = 0;
+  for (int l = 0; l < 32; ++l) acc += (int64_t)cta->xchg[(tid & ~31) | l];
+  warp_barrier();
+  return (T)acc;
+}
+template <class T>
 inline T __ldg(const T* p) { return *p; }
+template <class T>
+inline T __ldcg(const T* p) { return *p; }
 inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __expf(float x) { return expf(x); }
+inline float __logf(float x) { return logf(x); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicMax(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline float atomicAdd(float* addr, float v) {
