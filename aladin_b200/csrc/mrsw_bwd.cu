@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(BW_THREADS) pair_generic_kernel(const BwdParam
 constexpr int PT_KC = 32;             // floats per K chunk
 constexpr int PT_PITCH = PT_KC + 4;   // shared-memory row pitch (floats): 144 B, keeps 16 B alignment
 
+#ifndef ALAD_CPU_EMU
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned int d = static_cast<unsigned int>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
@@ -155,6 +156,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+#else   // tests/cuda_emu (host threads): the copies complete at issue, the vector reduction is four scalar atomics
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  atomicAdd(addr, a); atomicAdd(addr + 1, b); atomicAdd(addr + 2, c); atomicAdd(addr + 3, d);
+}
+#endif
 
 template <int RA, int WB>
 struct PairTile {

@@ -45,7 +45,7 @@ def build(name, tsan=False):
     with open(cpp, "w") as f:
         f.write('#include "cuda_emu.h"\n' + text)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-shared", "-fPIC", "-pthread", "-w", "-Wl,-Bsymbolic", "-I", HERE, "-I", CSRC,
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-DALAD_CPU_EMU", "-shared", "-fPIC", "-pthread", "-w", "-Wl,-Bsymbolic", "-I", HERE, "-I", CSRC,
            "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, "-o", lib, cpp]
     if tsan:
         cmd.insert(1, "-fsanitize=thread")

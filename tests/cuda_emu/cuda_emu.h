@@ -198,6 +198,12 @@ cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
   return cudaSuccess;
 }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, const void*, int, size_t) { *n = 2; return cudaSuccess; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) {
+  *n = 2;
+  return cudaSuccess;
+}
+cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t width, size_t height, cudaStream_t) {
@@ -211,6 +217,6 @@ char* error_buffer() {
   static thread_local char buf[512];
   return buf;
 }
-int sm_count() { return 148; }
+int sm_count() { return 2; }              // persistent grids stay small under emulation
 }  // namespace alad
 extern "C" const char* alad_last_error(void) { return alad::error_buffer(); }

@@ -1,5 +1,5 @@
-"""CPU-only: the CUDA-core translation units of aladin_b200/csrc (losses, distill, rank, misc_sim, pack -- every
-kernel of the path that is not tcgen05 / TMA / inline PTX) compiled for the host-thread emulator of tests/cuda_emu
+"""CPU-only: the CUDA-core translation units of aladin_b200/csrc (losses, distill, rank, misc_sim, pack, mrsw_bwd --
+every kernel of the path that is not tcgen05 / TMA) compiled for the host-thread emulator of tests/cuda_emu
 and called through their C-ABI entry points on numpy buffers, against the oracle.  Same source as the GPU build;
 small sizes (one std::thread per CUDA thread).  The `-m gpu` tests remain the parity tests proper; this file
 catches index / barrier mistakes on the GPU-less box, and the ThreadSanitizer test at the end reports any
@@ -332,6 +332,83 @@ def test_pool_and_scale_emulated(pack):
     ref = Sm * np.float32(0.25) / div
     ok(pack, pack.alad_scale_scores(p(Sm), 300, 3, 300, p(div), 0.25, None))
     np.testing.assert_allclose(Sm, ref, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------- mrsw_bwd.cu
+@pytest.fixture(scope="module")
+def mrsw_bwd():
+    return load_emu("mrsw_bwd")
+
+
+def run_mrsw_bwd(lib, im, s, nr, nw, G0=None, g0_scale=None, G1=None, sbd_layout=False, region_extent=0):
+    """alad_mrsw_scores_bwd on numpy buffers; with sbd_layout the inputs and gradients use the [S,B,d] memory
+    layout of alad_model.py:377-378 (viewed as [B,S,d])."""
+    from aladin_b200._cabi import MrswBwdArgs
+    Bi, S_im, d = im.shape
+    Bc, S_s, _ = s.shape
+
+    def lay(x):
+        if not sbd_layout:
+            x = np.ascontiguousarray(x)
+            return x, x.shape[1] * d, d
+        x = np.ascontiguousarray(x.transpose(1, 0, 2))            # memory [S,B,d]
+        return x, d, x.shape[1] * d
+
+    im_m, im_sb, im_ss = lay(im)
+    s_m, s_sb, s_ss = lay(s)
+    d_im = np.full(im_m.shape, np.nan, np.float32)
+    d_s = np.full(s_m.shape, np.nan, np.float32)
+    max_pairs = max(Bi * Bc, 1)
+    nbytes = lib.alad_mrsw_bwd_workspace_bytes(Bi, S_im, Bc, S_s, max_pairs)
+    ws = workspace(nbytes)
+    nr32, nw32 = np.asarray(nr, np.int32), np.asarray(nw, np.int32)
+    scale = np.array([g0_scale], np.float32) if g0_scale is not None else None
+    a = MrswBwdArgs(im=p(im_m), im_stride_b=im_sb, im_stride_s=im_ss, s=p(s_m), s_stride_b=s_sb, s_stride_s=s_ss,
+                    Bi=Bi, S_im=S_im, Bc=Bc, S_s=S_s, d=d, nr=p(nr32), nw=p(nw32),
+                    G0=p(G0), ldG0=Bc if G0 is not None else 0, g0_scale=p(scale), G1=p(G1), ldG1=Bc if G1 is not None else 0,
+                    d_im=p(d_im), d_s=p(d_s), eps=1e-12, region_extent=region_extent, max_pairs=max_pairs,
+                    workspace=p(ws), workspace_bytes=nbytes,
+                    d_im_stride_b=im_sb if sbd_layout else 0, d_im_stride_s=im_ss if sbd_layout else 0,
+                    d_s_stride_b=s_sb if sbd_layout else 0, d_s_stride_s=s_ss if sbd_layout else 0)
+    ok(lib, lib.alad_mrsw_scores_bwd(C.byref(a), None))
+    if sbd_layout:
+        d_im, d_s = d_im.transpose(1, 0, 2), d_s.transpose(1, 0, 2)
+    return d_im, d_s
+
+
+@pytest.mark.parametrize("shape,sbd", [((6, 7, 9, 12, 64), False), ((5, 4, 35, 53, 64), True), ((3, 4, 60, 80, 32), False),
+                                      ((4, 5, 8, 11, 20), False)])
+def test_mrsw_backward_emulated(mrsw_bwd, shape, sbd):
+    """Sparse MrSw backward: the register-tiled pair kernels (d % 32 == 0: <5,2>, <9,3>) and the
+    generic kernel (d = 20), contiguous and [S,B,d] gradient layouts, hinge gradient scaled on the device plus a
+    dense upstream gradient."""
+    from aladin_b200 import synth
+    Bi, Bc, S_im, S_s, d = shape
+    im, s, il, sl = synth.raw_batch(sum(shape), Bi, Bc, S_im, S_s, d, ragged=True, related=0.5)
+    R, W, nr, nw = O.scored_extents(im.shape, s.shape, il, sl)
+    r = np.random.RandomState(2)
+    G0 = np.zeros((Bi, Bc), np.float32)
+    G0[r.rand(Bi, Bc) < 0.4] = 1.0
+    G0[0, 0] = -2.0
+    G1 = (r.standard_normal((Bi, Bc)) * (r.rand(Bi, Bc) < 0.5)).astype(np.float32)
+    d_im, d_s = run_mrsw_bwd(mrsw_bwd, im, s, nr, nw, G0=G0, g0_scale=0.75, G1=G1, sbd_layout=sbd)
+    ref_im, ref_s = O.mrsw_backward(im, s, il, sl, 0.75 * G0.astype(np.float64) + G1)
+    scale = max(np.abs(ref_im).max(), np.abs(ref_s).max())
+    assert np.isfinite(d_im).all() and np.isfinite(d_s).all()
+    assert np.abs(d_im - ref_im).max() <= 1e-4 * scale and np.abs(d_s - ref_s).max() <= 1e-4 * scale
+
+
+def test_mrsw_backward_emulated_reference_golden(mrsw_bwd):
+    from conftest import load_golden
+    g = load_golden("alignment_loss")
+    im = np.ascontiguousarray(np.transpose(g["im_sbd"], (1, 0, 2)))
+    s = np.ascontiguousarray(np.transpose(g["s_sbd"], (1, 0, 2)))
+    il, sl = g["im_len"].tolist(), g["s_len"].tolist()
+    R, W, nr, nw = O.scored_extents(im.shape, s.shape, il, sl)
+    G = O.triplet_grad(g["S_mv"], 0.2, True)
+    d_im, d_s = run_mrsw_bwd(mrsw_bwd, im, s, nr, nw, G0=np.ascontiguousarray(G, np.float32), sbd_layout=True)
+    np.testing.assert_allclose(np.transpose(d_im, (1, 0, 2)), g["dim_mv"], rtol=1e-3, atol=2e-6)
+    np.testing.assert_allclose(np.transpose(d_s, (1, 0, 2)), g["ds_mv"], rtol=1e-3, atol=2e-6)
 
 
 # ------------------------------------------------------------------------------------------------- sanitizer
