@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libalad_b200.so")
+# ALAD_B200_LIB: another build of the same C ABI (A/B runs of two kernel versions on one box)
+LIB_PATH = os.environ.get("ALAD_B200_LIB") or os.path.join(_HERE, "libalad_b200.so")
 
 TILE_M, TILE_N, TILE_K, MAX_SEG = 128, 240, 64, 32
 NTILE_WORDS = 20

@@ -55,6 +55,8 @@ def main():
     S = torch.empty((Ni, Nc), dtype=torch.float32, device="cuda")
     configs = [(mb, h) for mb in (8, 12, 16, 24, 30, 45) for h in (0,)] + [(16, 1), (30, 1), (16, 3), (30, 2)]
     if os.environ.get("SWEEP_CONFIGS"):
+        # "block:hints[:skew[:group]]" -- skew / group = ALAD_M_SKEW / ALAD_M_SKEW_GROUP (skewed M sweep: an experiment
+        # that was measured and removed from the kernel again, profiles/r01_tile_order_sweep.md section 9)
         configs = [tuple(int(x) for x in c.split(":")) for c in os.environ["SWEEP_CONFIGS"].split(",")]
     smi = Smi()
     flops = 2.0 * 34 * 50 * 1024 * Ni * Nc * (3 if split else 1)       # issued FLOP in split mode
@@ -64,7 +66,10 @@ def main():
         scoring.mrsw_scores_packed(words, regions, tiles_dev, len(table), Ni, Nc, out=S)
     torch.cuda.synchronize()
     for r in range(rounds):
-        for mb, h in configs:
+        for cfg in configs:
+            mb, h = cfg[0], cfg[1]
+            os.environ["ALAD_M_SKEW"] = str(cfg[2] if len(cfg) > 2 else 0)
+            os.environ["ALAD_M_SKEW_GROUP"] = str(cfg[3] if len(cfg) > 3 else 1)
             os.environ["ALAD_L2_BLOCK_MB"] = str(mb)
             if mb >= 1000:                                   # 1000 + n: block of n tiles
                 os.environ["ALAD_N_BLOCK"] = str(mb - 1000)
@@ -82,14 +87,15 @@ def main():
             t1 = time.perf_counter()
             ms = e0.elapsed_time(e1) / 2
             clk, pw = smi.window(t0 + 0.15, t1)
-            res[(mb, h)].append((ms, clk, pw))
+            res[cfg].append((ms, clk, pw))
     smi.p.terminate()
     out = []
-    for (mb, h), v in res.items():
+    for cfg, v in res.items():
+        mb, h = cfg[0], cfg[1]
         ms = float(np.median([x[0] for x in v]))
         clk = float(np.median([x[1] for x in v if x[1] is not None] or [0]))
         pw = float(np.median([x[2] for x in v if x[2] is not None] or [0]))
-        out.append({"l2_block_mb": mb, "hints": h, "ms": round(ms, 2), "tflops": round(flops / ms / 1e9, 1), "sm_mhz": clk,
+        out.append({"l2_block_mb": mb, "hints": h, "skew": list(cfg[2:]), "ms": round(ms, 2), "tflops": round(flops / ms / 1e9, 1), "sm_mhz": clk,
                     "power_w": pw, "all_ms": [round(x[0], 1) for x in v]})
         print(out[-1])
     print(json.dumps(out))
