@@ -27,6 +27,17 @@ def timeit(fn, iters, warm=3):
 
 def main():
     out = []
+    # `python tools/scan_probe.py one B` = one forward + backward of scan-sentences at batch B (for ncu launch lists)
+    if len(sys.argv) > 2 and sys.argv[1] == "one":
+        B = int(sys.argv[2])
+        im, s, il, cl = synth.raw_batch(9, B, B, 35, 53, 1024, related=0.6)
+        img = torch.tensor(im, device="cuda", requires_grad=True)
+        cap = torch.tensor(s, device="cuda", requires_grad=True)
+        crit = L.AlignmentContrastiveLoss(margin=0.2, measure="dot", max_violation=True, aggregation="scan-sentences")
+        crit.precision = "bf16"
+        crit(img, cap, il, cl).backward()
+        torch.cuda.synchronize()
+        return
     for B, iters in ((128, 20), (512, 5)):
         im, s, il, cl = synth.raw_batch(9, B, B, 35, 53, 1024, related=0.6)
         img = torch.tensor(im, device="cuda", requires_grad=True)
