@@ -37,8 +37,13 @@ K = np.zeros((Bc, W, W), np.float32)
 assert lib.alad_scan_gram(p(yh), Bc, W, d, p(nw32), p(K), None) == 0
 Cm = np.ascontiguousarray(xh @ yh.T)
 S = np.zeros((Bi, Bc), np.float32)
-assert lib.alad_scan_pool_fwd(p(Cm), Cm.shape[1], Bi, R, Bc, W, p(nr32), p(nw32), int(nr.max()), int(nw.max()), p(K), p(S),
-                              Bc, None) == 0
+for smem_kernel in (False, True):                          # register-resident forward kernel, then the shared-memory one
+    if smem_kernel:
+        os.environ["ALAD_SCAN_SMEM_FWD"] = "1"
+    S[:] = 0
+    assert lib.alad_scan_pool_fwd(p(Cm), Cm.shape[1], Bi, R, Bc, W, p(nr32), p(nw32), int(nr.max()), int(nw.max()), p(K),
+                                  p(S), Bc, None) == 0
+    assert np.abs(S - O.scan_scores(im, s, il, sl)).max() < 1e-5
 G = r.standard_normal((Bi, Bc)).astype(np.float32)
 dC, dK, dy = np.zeros_like(Cm), np.zeros_like(K), np.zeros_like(yh)
 assert lib.alad_scan_pool_bwd(p(Cm), Cm.shape[1], Bi, R, Bc, W, p(nr32), p(nw32), int(nr.max()), int(nw.max()), p(K), p(G),

@@ -84,8 +84,13 @@ def run_kernels(emu, im, s, im_len, s_len, G=None):
     return out
 
 
-@pytest.mark.parametrize("shape", [(5, 4, 7, 10, 40), (3, 3, 35, 53, 64), (18, 2, 5, 40, 16)])
-def test_emulated_kernels_match_oracle(emu, shape):
+@pytest.mark.parametrize("shape", [(5, 4, 7, 10, 40), (3, 3, 35, 53, 64), (18, 2, 5, 40, 16), (4, 3, 6, 80, 16),
+                                   (5, 4, 7, 10, 40, "smem")])
+def test_emulated_kernels_match_oracle(emu, shape, monkeypatch):
+    """Forward: register-resident kernel (<= 64 words), shared-memory kernel (77 words, or forced); backward."""
+    if shape[-1] == "smem":
+        monkeypatch.setenv("ALAD_SCAN_SMEM_FWD", "1")
+        shape = shape[:-1]
     Bi, Bc, S_im, S_s, d = shape
     im, s, il, sl = problem(sum(shape), Bi, Bc, S_im, S_s, d)
     r = np.random.RandomState(1)
