@@ -7,6 +7,8 @@ what alad/test.py:258-264 and alad/train.py:493-500 build -- the whole Ni x Nc s
 computed once on the GPU and both directions are ranked from it; ``sim_function=None`` is the
 global-vector path on slot 0 (evaluation.py:195-197,284-286); any other callable is invoked
 per query like the reference does, and only the ranking runs in our kernels."""
+import weakref
+
 import numpy as np
 import torch
 
@@ -76,7 +78,8 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
     mode = "global" if sim_function is None else ("fused" if scorer is not None else "callback")
     precision = getattr(scorer, "precision", None) or scoring.get_precision()
     key = _key(images, captions, img_lens, cap_lens, mode, precision) if mode != "callback" else None
-    if key is not None and _cache.get("key") == key:
+    if (key is not None and _cache.get("key") == key and _cache["refs"][0]() is images
+            and _cache["refs"][1]() is captions):
         return _cache["res"]
     Ni = images.shape[0] // 5
     world, rank, group = (1, 0, None)
@@ -102,8 +105,11 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
     ri, t1, rt, tk = retrieval.rank_both_directions(S, Ni, img_off=img_off, n_images_total=Ni, k=k, group=group)
     res = dict(S=S, img_off=img_off, world=world, ranks_i2t=ri, top1=t1, ranks_t2i=rt, top50=tk)
     if key is not None:
+        # the key holds addresses: a hit is valid only while the very same input objects are alive (a freed
+        # tensor's address, shape and version counter can all recur, e.g. the next epoch's validation embeddings)
+        refs = (weakref.ref(images), weakref.ref(captions))
         _cache.clear()
-        _cache.update(key=key, res=res)
+        _cache.update(key=key, res=res, refs=refs)
     return res
 
 
