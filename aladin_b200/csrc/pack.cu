@@ -31,9 +31,13 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 
 template <bool kVec>
 __global__ void __launch_bounds__(PACK_WARPS * 32) pack_tokens_kernel(const alad_pack_args a) {
-  const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // containers of one slot per item (the plain-GEMM operands of dot_sim / compute_recall / the backward GEMMs): one
+  // item per WARP, so that all eight warps of the CTA work; otherwise one item per CTA, its tokens over the warps
+  const bool flat = a.S == 1;
+  const int b = flat ? blockIdx.x * PACK_WARPS + warp : blockIdx.x;
+  if (b >= a.B) return;
   const int cnt = a.count[b];
   const long long row0 = a.row_off[b];
   const int d = a.d;
@@ -44,7 +48,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_tokens_kernel(const alad
   const int off_lo = (a.mode == 1) ? 2 * d : d;    // lo part
   const int used = (a.mode == 0) ? d : 3 * d;
 
-  for (int t = warp; t < cnt; t += PACK_WARPS) {
+  for (int t = flat ? 0 : warp; t < cnt; t += flat ? 1 : PACK_WARPS) {
     const float* x = a.src + (long long)b * a.stride_b + (long long)(a.slot0 + t) * a.stride_s;
     __nv_bfloat16* y = dst + (row0 + t) * (long long)Kp;
     float ss = 0.f;
@@ -172,10 +176,11 @@ extern "C" int alad_pack_tokens(const alad_pack_args* a, void* stream) {
   const bool vec = (a->d % 4 == 0) && (a->stride_b % 4 == 0) && (a->stride_s % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(a->src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a->dst) & 7) == 0);
   cudaStream_t st = as_stream(stream);
+  const unsigned grid = a->S == 1 ? (unsigned)((a->B + PACK_WARPS - 1) / PACK_WARPS) : (unsigned)a->B;
   if (vec)
-    pack_tokens_kernel<true><<<a->B, PACK_WARPS * 32, 0, st>>>(*a);
+    pack_tokens_kernel<true><<<grid, PACK_WARPS * 32, 0, st>>>(*a);
   else
-    pack_tokens_kernel<false><<<a->B, PACK_WARPS * 32, 0, st>>>(*a);
+    pack_tokens_kernel<false><<<grid, PACK_WARPS * 32, 0, st>>>(*a);
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;
 }

@@ -317,6 +317,36 @@ def test_pack_tokens_emulated(pack, d, mode):
     assert row == rows
 
 
+@pytest.mark.parametrize("B,d,mode", [(19, 96, 0), (8, 40, 2), (1, 64, 1)])
+def test_pack_single_slot_items_emulated(pack, B, d, mode):
+    """One slot per item (the plain-GEMM operands): one item per warp, B not a multiple of the 8 warps."""
+    from aladin_b200._cabi import PackArgs
+    r = np.random.RandomState(B + d)
+    x = r.standard_normal((B, 1, d)).astype(np.float32)
+    cnt = np.ones(B, np.int32)
+    cnt[B // 2] = 0 if B > 1 else 1
+    off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int64)
+    rows = int(cnt.sum())
+    Kp = -(-(d * (1 if mode == 0 else 3)) // 64) * 64
+    dst = np.full((rows, Kp), 0x7FC0, np.uint16)
+    a = PackArgs(src=p(x), stride_b=d, stride_s=d, B=B, S=1, d=d, slot0=0, count=p(cnt), row_off=p(off), dst=p(dst), Kp=Kp,
+                 mode=mode, normalize=0, eps=0.0, row_item=None, item_base=0)
+    ok(pack, pack.alad_pack_tokens(C.byref(a), None))
+    got = _bf16_to_f32(dst)
+    assert not np.isnan(got).any()
+    row = 0
+    for b in range(B):
+        if not cnt[b]:
+            continue
+        hi = got[row, :d]
+        np.testing.assert_allclose(hi, x[b, 0], rtol=2 ** -8, atol=1e-30)
+        if mode:
+            lo = got[row, 2 * d:3 * d] if mode == 1 else got[row, d:2 * d]
+            np.testing.assert_allclose(hi + lo, x[b, 0], rtol=2 ** -15, atol=1e-30)
+        row += 1
+    assert row == rows
+
+
 def test_pool_and_scale_emulated(pack):
     r = np.random.RandomState(9)
     B, S, d = 4, 7, 50
