@@ -157,4 +157,54 @@ def virtual_b200(monkeypatch):
     monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+
+    # streams and events: everything runs synchronously on the calling thread
+    class Stream:
+        cuda_stream = 0
+
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_stream(self, s):
+            pass
+
+        def wait_event(self, e):
+            pass
+
+        def synchronize(self):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    class Event:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, *a, **k):
+            pass
+
+        def wait(self, *a, **k):
+            pass
+
+        def synchronize(self):
+            pass
+
+        def query(self):
+            return True
+
+        def elapsed_time(self, other):
+            return 0.0
+
+    monkeypatch.setattr(torch.cuda, "Stream", Stream)
+    monkeypatch.setattr(torch.cuda, "Event", Event)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: Stream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: s if s is not None else Stream())
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "device_count", lambda: 1)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     return lib

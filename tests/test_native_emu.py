@@ -7,6 +7,7 @@ import pytest
 
 import test_gpu_distill_modes as TD
 import test_gpu_losses as TL
+import test_gpu_ranking as TR
 import test_gpu_scoring as TS
 import test_gpu_train_step as TT
 import test_gpu_zz_scan_sentences as TZ
@@ -31,6 +32,9 @@ CASES = [
     (TD.test_cosine_measure_gradient_golden, dict(key="cosine_mv", mv=True)),
     (TD.test_pooling_mode_gradients_golden, dict(agg="symm")),
     (TD.test_pooling_mode_gradients_golden, dict(agg="mean")),
+    (TR.test_rank_kernels_reproduce_reference_golden, {}),
+    (TR.test_sharded_ranking_equals_single_shard, {}),
+    (TR.test_col_topk_select_strided_view, {}),
     (TT.test_fused_losses_match_reference_training_step, {}),
     (TT.test_forward_only_and_partial_requires_grad, {}),
     (TZ.test_scores_golden, dict(precision="fp32")),
