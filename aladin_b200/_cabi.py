@@ -115,6 +115,7 @@ PROTOTYPES = {
     "alad_scan_gram_bwd": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "alad_scan_pool_fwd": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _I64, _P]),
     "alad_scan_pool_bwd": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _I64, _P, _I64, _P, _P]),
+    "alad_scan_apply_pairs": (C.c_int, [_P, _I64, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _P]),
     "alad_rank_rows": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "alad_col_gt": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "alad_col_count": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
@@ -157,7 +158,7 @@ KERNELS_PER_CALL = {
     "alad_distill_mse_fwd_bwd": 1, "alad_distill_contrastive_fwd_bwd": 2, "alad_distill_ordinal_fwd_bwd": 2,
     "alad_train_losses_fwd": 13, "alad_train_losses_bwd": 16,
     "alad_order_scores": 1, "alad_order_scores_bwd": 1, "alad_normalize_bwd": 1, "alad_pool_tokens_bwd": 1,
-    "alad_scan_gram": 1, "alad_scan_gram_bwd": 1, "alad_scan_pool_fwd": 1, "alad_scan_pool_bwd": 1,
+    "alad_scan_gram": 1, "alad_scan_gram_bwd": 1, "alad_scan_pool_fwd": 1, "alad_scan_pool_bwd": 1, "alad_scan_apply_pairs": 1,
 }
 launch_count = {"kernels": 0}
 

@@ -391,6 +391,44 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 3) scan_pair_fwd_reg_kernel(c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ sparse backward
+// d xhat[i, r, :] += sum_w dC[i, r, j, w] yhat[j, w, :]  and  d yhat[j, w, :] += sum_r dC[i, r, j, w] xhat[i, r, :]
+// for a LIST of (i, j) pairs: with the hardest-negative hinge dL/dS has <= 3B non-zero entries, so the two dense
+// GEMMs over all B x B blocks of dC would spend > 99 % of their work (and of the pack / transpose passes that feed
+// them) on zeros.  One CTA per pair and 256 feature columns: the pair's dC block in shared memory, one thread per
+// column, results added with float atomics (several pairs share an image or a caption).
+__global__ void __launch_bounds__(256) scan_apply_pairs_kernel(const float* __restrict__ dC, long long lddC,
+                                                               const float* __restrict__ xh, const float* __restrict__ yh,
+                                                               const int* __restrict__ pairs, int R, int W, int d,
+                                                               const int* __restrict__ nr, const int* __restrict__ nw,
+                                                               int Rcap, int Wcap, float* __restrict__ d_xh,
+                                                               float* __restrict__ d_yh) {
+  extern __shared__ float blk[];                       // [Rcap][Wp]
+  const int Wp = scan_wp(Wcap);
+  const int i = pairs[2 * blockIdx.x], j = pairs[2 * blockIdx.x + 1];
+  const int nri = min(max(nr[i], 0), Rcap), nwj = min(max(nw[j], 0), Wcap);
+  const float* src = dC + (long long)i * R * lddC + (long long)j * W;
+  for (int e = threadIdx.x; e < nri * nwj; e += blockDim.x) {
+    const int r = e / nwj, w = e % nwj;
+    blk[r * Wp + w] = __ldg(src + (long long)r * lddC + w);
+  }
+  __syncthreads();
+  const int k = blockIdx.y * blockDim.x + threadIdx.x;
+  if (k >= d) return;
+  const float* x = xh + (long long)i * R * d + k;
+  const float* y = yh + (long long)j * W * d + k;
+  for (int r = 0; r < nri; ++r) {
+    float acc = 0.f;
+    for (int w = 0; w < nwj; ++w) acc = fmaf(blk[r * Wp + w], __ldg(y + (long long)w * d), acc);
+    atomicAdd(d_xh + ((long long)i * R + r) * d + k, acc);
+  }
+  for (int w = 0; w < nwj; ++w) {
+    float acc = 0.f;
+    for (int r = 0; r < nri; ++r) acc = fmaf(blk[r * Wp + w], __ldg(x + (long long)r * d), acc);
+    atomicAdd(d_yh + ((long long)j * W + w) * d + k, acc);
+  }
+}
+
 int scan_check(const char* what, int32_t Bi, int32_t R, int32_t Bc, int32_t W, int32_t max_nr, int32_t max_nw, int64_t ldC) {
   ALAD_REQUIRE(Bi >= 0 && Bc >= 0 && R >= 0 && W >= 0, "%s: bad shape", what);
   ALAD_REQUIRE(max_nr >= 0 && max_nr <= R && max_nw >= 0 && max_nw <= W, "%s: max_nr / max_nw outside the extents", what);
@@ -487,4 +525,24 @@ extern "C" int alad_scan_pool_bwd(const float* C, int64_t ldC, int32_t Bi, int32
   p.Rcap = max_nr; p.Wcap = max_nw;
   p.nr = nr; p.nw = nw; p.K = K; p.G = G; p.ldG = ldG; p.dC = dC; p.lddC = lddC; p.dK = dK;
   return scan_launch<true>("alad_scan_pool_bwd", p, st);
+}
+
+extern "C" int alad_scan_apply_pairs(const float* dC, int64_t lddC, const float* xh, const float* yh, const int32_t* pairs,
+                                     int32_t n_pairs, int32_t Bi, int32_t R, int32_t Bc, int32_t W, int32_t d,
+                                     const int32_t* nr, const int32_t* nw, int32_t max_nr, int32_t max_nw, float* d_xh,
+                                     float* d_yh, void* stream) {
+  using namespace alad;
+  const int rc = scan_check("alad_scan_apply_pairs", Bi, R, Bc, W, max_nr, max_nw, lddC);
+  if (rc) return rc;
+  ALAD_REQUIRE(n_pairs >= 0 && d > 0, "alad_scan_apply_pairs: bad shape");
+  if (n_pairs == 0 || max_nr == 0 || max_nw == 0) return ALAD_OK;
+  ALAD_REQUIRE(dC && xh && yh && pairs && nr && nw && d_xh && d_yh, "alad_scan_apply_pairs: NULL pointer");
+  ALAD_REQUIRE((d + 255) / 256 <= 65535, "alad_scan_apply_pairs: d too large");
+  const size_t bytes = (size_t)max_nr * scan_wp(max_nw) * 4;
+  ALAD_CUDA(cudaFuncSetAttribute(scan_apply_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  dim3 grid(n_pairs, (d + 255) / 256);
+  scan_apply_pairs_kernel<<<grid, 256, bytes, as_stream(stream)>>>(dC, lddC, xh, yh, pairs, R, W, d, nr, nw, max_nr, max_nw,
+                                                                   d_xh, d_yh);
+  ALAD_CUDA(cudaGetLastError());
+  return ALAD_OK;
 }

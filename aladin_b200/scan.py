@@ -17,6 +17,7 @@ import torch
 from . import _cabi, scoring
 
 _CHUNK_BYTES = 1 << 30          # upper bound of one materialised cosine block (fp32)
+SPARSE_FRACTION = 8             # pair-list backward when at most 1 / SPARSE_FRACTION of dL/dS is non-zero
 
 
 def _unit_token_rows(x, extent):
@@ -91,7 +92,14 @@ def scan_backward(im_c, s_c, counts, G, precision=None):
     dK = torch.zeros_like(K)
     d_xh = torch.empty_like(xh)
     d_yh = torch.zeros_like(yh)
-    yh_t = yh.t().contiguous()
+    # dL/dS with few non-zero entries (the hardest-negative hinge leaves <= 3B): the products with dC run
+    # over the listed pairs only; otherwise two fp32-grade GEMMs on the tcgen05 kernel
+    nz = torch.nonzero(G)
+    sparse = nz.shape[0] * SPARSE_FRACTION <= Bi * Bc
+    if sparse:
+        d_xh.zero_()
+    else:
+        yh_t = yh.t().contiguous()
     for i0, i1 in _image_chunks(Bi, R, Bc, W):
         xh_c = xh[i0 * R:i1 * R]
         Cm = scoring.dot_scores(xh_c, yh, precision=precision)
@@ -101,9 +109,18 @@ def scan_backward(im_c, s_c, counts, G, precision=None):
                                            dC.data_ptr(), dC.stride(0), dK.data_ptr(), _cabi.stream_ptr()),
                     "alad_scan_pool_bwd")
         del Cm
-        # d xhat = dC @ yhat, d yhat += dC.T @ xhat: fp32-grade GEMMs on the tcgen05 kernel
-        scoring.dot_scores(dC, yh_t, precision="fp32", out=d_xh[i0 * R:i1 * R])
-        d_yh += scoring.dot_scores(dC.t().contiguous(), xh_c.t().contiguous(), precision="fp32")
+        if sparse:
+            sel = nz[(nz[:, 0] >= i0) & (nz[:, 0] < i1)]
+            pairs = torch.stack([sel[:, 0] - i0, sel[:, 1]], dim=1).to(torch.int32).contiguous()
+            _cabi.check(lib.alad_scan_apply_pairs(dC.data_ptr(), dC.stride(0), xh_c.data_ptr(), yh.data_ptr(),
+                                                  pairs.data_ptr(), pairs.shape[0], i1 - i0, R, Bc, W, d,
+                                                  nr_d[i0:i1].data_ptr(), nw_d.data_ptr(), max_nr, max_nw,
+                                                  d_xh[i0 * R:i1 * R].data_ptr(), d_yh.data_ptr(), _cabi.stream_ptr()),
+                        "alad_scan_apply_pairs")
+        else:
+            # d xhat = dC @ yhat, d yhat += dC.T @ xhat
+            scoring.dot_scores(dC, yh_t, precision="fp32", out=d_xh[i0 * R:i1 * R])
+            d_yh += scoring.dot_scores(dC.t().contiguous(), xh_c.t().contiguous(), precision="fp32")
         del dC
     _cabi.check(lib.alad_scan_gram_bwd(yh.data_ptr(), Bc, W, d, nw_d.data_ptr(), dK.data_ptr(), d_yh.data_ptr(),
                                        _cabi.stream_ptr()), "alad_scan_gram_bwd")

@@ -332,6 +332,10 @@ int alad_pool_tokens_bwd(const float* src, int64_t stride_b, int64_t stride_s, i
  *                     and dK [Bc, W, W] += dL/dK (the CALLER zeroes dK before the first image chunk); pairs with
  *                     G = 0 are skipped.  Masked regions get a zero gradient (the reference yields NaN there).
  * alad_scan_gram_bwd  d_yh [Bc*W, d] += 2 dK yh (dK is symmetric by construction)
+ * alad_scan_apply_pairs  for a DEVICE list of n_pairs (image, caption) index pairs (int32 [n_pairs, 2], each pair once):
+ *                     d_xh [Bi*R, d] += dC_ij yh_j and d_yh [Bc*W, d] += dC_ij' xh_i (float atomics; the caller zeroes
+ *                     both) -- the sparse form of the two backward GEMMs when dL/dS has few non-zero entries
+ *                     (<= 3B with the hardest-negative hinge)
  * ------------------------------------------------------------------------------- */
 int alad_scan_gram(const float* yh, int32_t Bc, int32_t W, int32_t d, const int32_t* nw, float* K, void* stream);
 int alad_scan_gram_bwd(const float* yh, int32_t Bc, int32_t W, int32_t d, const int32_t* nw, const float* dK,
@@ -339,6 +343,9 @@ int alad_scan_gram_bwd(const float* yh, int32_t Bc, int32_t W, int32_t d, const 
 int alad_scan_pool_fwd(const float* C, int64_t ldC, int32_t Bi, int32_t R, int32_t Bc, int32_t W, const int32_t* nr,
                        const int32_t* nw, int32_t max_nr, int32_t max_nw, const float* K, float* S, int64_t ldS,
                        void* stream);
+int alad_scan_apply_pairs(const float* dC, int64_t lddC, const float* xh, const float* yh, const int32_t* pairs,
+                          int32_t n_pairs, int32_t Bi, int32_t R, int32_t Bc, int32_t W, int32_t d, const int32_t* nr,
+                          const int32_t* nw, int32_t max_nr, int32_t max_nw, float* d_xh, float* d_yh, void* stream);
 int alad_scan_pool_bwd(const float* C, int64_t ldC, int32_t Bi, int32_t R, int32_t Bc, int32_t W, const int32_t* nr,
                        const int32_t* nw, int32_t max_nr, int32_t max_nw, const float* K, const float* G, int64_t ldG,
                        float* dC, int64_t lddC, float* dK, void* stream);

@@ -15,7 +15,7 @@ from aladin_b200 import _cabi  # noqa: E402
 from oracle import alad_oracle as O  # noqa: E402
 
 lib = C.CDLL(build_emu.build("scan_pool", tsan=True))
-for name in ("alad_scan_gram", "alad_scan_gram_bwd", "alad_scan_pool_fwd", "alad_scan_pool_bwd"):
+for name in ("alad_scan_gram", "alad_scan_gram_bwd", "alad_scan_pool_fwd", "alad_scan_pool_bwd", "alad_scan_apply_pairs"):
     getattr(lib, name).restype, getattr(lib, name).argtypes = _cabi.PROTOTYPES[name]
 
 r = np.random.RandomState(0)
@@ -49,5 +49,9 @@ dC, dK, dy = np.zeros_like(Cm), np.zeros_like(K), np.zeros_like(yh)
 assert lib.alad_scan_pool_bwd(p(Cm), Cm.shape[1], Bi, R, Bc, W, p(nr32), p(nw32), int(nr.max()), int(nw.max()), p(K), p(G),
                               Bc, p(dC), dC.shape[1], p(dK), None) == 0
 assert lib.alad_scan_gram_bwd(p(yh), Bc, W, d, p(nw32), p(dK), p(dy), None) == 0
+pairs = np.array([[0, 0], [2, 1], [8, 0], [8, 1]], np.int32)
+d_xh = np.zeros_like(xh)
+assert lib.alad_scan_apply_pairs(p(dC), dC.shape[1], p(xh), p(yh), p(pairs), len(pairs), Bi, R, Bc, W, d, p(nr32), p(nw32),
+                                 int(nr.max()), int(nw.max()), p(d_xh), p(dy), None) == 0
 assert np.abs(S - O.scan_scores(im, s, il, sl)).max() < 1e-5
 print("scan tsan ok")

@@ -45,5 +45,8 @@ CASES = [
 
 
 @pytest.mark.parametrize("fn,kwargs", CASES, ids=[f"{f.__module__}.{f.__name__}[{','.join(map(str, k.values()))}]" for f, k in CASES])
-def test_gpu_test_body_on_the_virtual_device(virtual_b200, fn, kwargs):
+def test_gpu_test_body_on_the_virtual_device(virtual_b200, monkeypatch, fn, kwargs):
+    import inspect
+    if "monkeypatch" in inspect.signature(fn).parameters:
+        kwargs = dict(kwargs, monkeypatch=monkeypatch)
     fn(**kwargs)

@@ -27,7 +27,7 @@ def emu():
     import build_emu
     from aladin_b200 import _cabi
     lib = C.CDLL(build_emu.build("scan_pool"))
-    for name in ("alad_scan_gram", "alad_scan_gram_bwd", "alad_scan_pool_fwd", "alad_scan_pool_bwd"):
+    for name in ("alad_scan_gram", "alad_scan_gram_bwd", "alad_scan_pool_fwd", "alad_scan_pool_bwd", "alad_scan_apply_pairs"):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = _cabi.PROTOTYPES[name]
     lib.alad_last_error.restype = C.c_char_p
@@ -127,6 +127,27 @@ def test_emulated_kernels_match_oracle(emu, shape, monkeypatch):
         np.testing.assert_allclose(k["d_yh_gram"].reshape(Bc, W, d)[j], ref_g, rtol=1e-4, atol=1e-6)
 
 
+def test_emulated_apply_pairs_equals_dense_products(emu):
+    """Pair-list form of d xhat = dC yhat, d yhat = dC' xhat (blocks outside the list are not touched)."""
+    r = np.random.RandomState(12)
+    Bi, Bc, R, W, d = 6, 5, 7, 9, 300                        # d not a multiple of the 256-column CTA slice
+    nr = np.array([7, 0, 3, 7, 5, 1], np.int32)
+    nw = np.array([9, 4, 0, 9, 6], np.int32)
+    xh = r.standard_normal((Bi * R, d)).astype(np.float32)
+    yh = r.standard_normal((Bc * W, d)).astype(np.float32)
+    dC = r.standard_normal((Bi * R, Bc * W)).astype(np.float32)
+    pairs = np.array([[0, 0], [0, 3], [2, 1], [3, 3], [4, 4], [5, 0], [1, 1], [2, 2]], np.int32)
+    d_xh, d_yh = np.zeros_like(xh), np.zeros_like(yh)
+    rc = emu.alad_scan_apply_pairs(ptr(dC), Bc * W, ptr(xh), ptr(yh), ptr(pairs), len(pairs), Bi, R, Bc, W, d, ptr(nr), ptr(nw),
+                                   int(nr.max()), int(nw.max()), ptr(d_xh), ptr(d_yh), None)
+    assert rc == 0, emu.alad_last_error()
+    masked = np.zeros_like(dC, dtype=np.float64)
+    for i, j in pairs:
+        masked[i * R:i * R + nr[i], j * W:j * W + nw[j]] = dC[i * R:i * R + nr[i], j * W:j * W + nw[j]]
+    np.testing.assert_allclose(d_xh, masked @ yh.astype(np.float64), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(d_yh, masked.T @ xh.astype(np.float64), rtol=1e-4, atol=1e-5)
+
+
 def test_emulated_kernels_golden_degenerate_lengths(emu):
     g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "scan_sentences.npz")))
     k = run_kernels(emu, g["c_im"], g["c_s"], g["c_im_len"].tolist(), g["c_s_len"].tolist())
@@ -185,10 +206,12 @@ def scan_on_cpu(emu, monkeypatch):
     return scan
 
 
-@pytest.mark.parametrize("chunk_images", [None, 2])
-def test_scan_host_flow_on_cpu(scan_on_cpu, monkeypatch, chunk_images):
+@pytest.mark.parametrize("chunk_images,sparse", [(None, False), (2, False), (None, True), (2, True)])
+def test_scan_host_flow_on_cpu(scan_on_cpu, monkeypatch, chunk_images, sparse):
     from aladin_b200 import scoring
     scan = scan_on_cpu
+    if sparse:
+        monkeypatch.setattr(scan, "SPARSE_FRACTION", 1)       # pair-list backward whatever the density of dL/dS
     Bi, Bc, S_im, S_s, d = 5, 4, 7, 10, 24
     im, s, il, sl = problem(11, Bi, Bc, S_im, S_s, d)
     if chunk_images:
@@ -201,6 +224,8 @@ def test_scan_host_flow_on_cpu(scan_on_cpu, monkeypatch, chunk_images):
     np.testing.assert_allclose(S.numpy(), O.scan_scores(im, s, il, sl), rtol=2e-5, atol=2e-6, equal_nan=True)
     G = np.random.RandomState(2).standard_normal((Bi, Bc)).astype(np.float32)
     G[1, 2] = 0.0
+    if sparse:
+        G[np.random.RandomState(3).rand(Bi, Bc) < 0.6] = 0.0
     d_im, d_s = scan.scan_backward(im_t, s_t, counts, torch.from_numpy(G))
     ref_im, ref_s = O.scan_backward(im, s, il, sl, G)
     np.testing.assert_allclose(d_im.numpy(), ref_im, rtol=1e-4, atol=2e-6)
