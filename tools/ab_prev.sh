@@ -1,5 +1,5 @@
 #!/bin/bash
-# Same-box A/B of two builds of the library (aladin_b200/libalad_b200_prev.so = the previous commit's kernels):
+# Same-box A/B of two builds of the library (aladin_b200/libalad_b200_prev.so = another commit, built by tools/build_prev.sh):
 # prefetch on / off at block 74, three rounds each, alternating the builds.  Usage on the box: bash tools/ab_prev.sh
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,pci.bus_id,serial --format=csv | tee gpurun_out/ab_box.txt
