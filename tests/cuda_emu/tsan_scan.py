@@ -14,7 +14,7 @@ import build_emu  # noqa: E402
 from aladin_b200 import _cabi  # noqa: E402
 from oracle import alad_oracle as O  # noqa: E402
 
-lib = C.CDLL(build_emu.build("scan_pool", tsan=True))
+lib = C.CDLL(build_emu.build_library(tsan=True))
 for name in ("alad_scan_gram", "alad_scan_gram_bwd", "alad_scan_pool_fwd", "alad_scan_pool_bwd", "alad_scan_apply_pairs"):
     getattr(lib, name).restype, getattr(lib, name).argtypes = _cabi.PROTOTYPES[name]
 

@@ -19,13 +19,20 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "cuda_emu"))
 
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+TSAN = os.environ.get("ALAD_EMU_TSAN") == "1"      # inside the sanitizer child run: same kernels, smallest shapes only
+
+
+def big(*cases):
+    """Parameter sets that only run outside the (10 x slower) sanitizer child."""
+    return [] if TSAN else list(cases)
 
 
 def load_emu(name, tsan=False):
     """ctypes handle of the emulated translation unit with the prototypes of aladin_b200/_cabi.py."""
     import build_emu
     from aladin_b200 import _cabi
-    lib = C.CDLL(build_emu.build(name, tsan=tsan or os.environ.get("ALAD_EMU_TSAN") == "1"))
+    # one emulated library with every translation unit (built once, in parallel); `name` documents the unit under test
+    lib = C.CDLL(build_emu.build_library(tsan=tsan or os.environ.get("ALAD_EMU_TSAN") == "1"))
     for sym, (res, args) in _cabi.PROTOTYPES.items():
         try:
             fn = getattr(lib, sym)
@@ -83,7 +90,7 @@ def run_triplet(lib, S, margin, mv):
     return loss[0], G
 
 
-@pytest.mark.parametrize("B", [1, 7, 45])
+@pytest.mark.parametrize("B", [1, 7] + big(45))
 @pytest.mark.parametrize("mv", [True, False])
 def test_triplet_emulated(losses, B, mv):
     r = np.random.RandomState(B)
@@ -102,7 +109,7 @@ def test_triplet_emulated_golden(losses):
         np.testing.assert_array_equal(G, g[f"G_{key}"])
 
 
-@pytest.mark.parametrize("B", [1, 9, 40])
+@pytest.mark.parametrize("B", [1, 9] + big(40))
 def test_listnet_emulated(losses, B):
     r = np.random.RandomState(B)
     T = (r.standard_normal((B, B)) * 2 + 3).astype(np.float32)
@@ -124,7 +131,7 @@ def _distill_inputs(B, seed):
     return T, M
 
 
-@pytest.mark.parametrize("B", [4, 37])
+@pytest.mark.parametrize("B", [4] + big(37))
 def test_distill_mse_emulated(distill, B):
     T, M = _distill_inputs(B, B)
     wb = np.array([0.7, -0.2], np.float32)
@@ -137,7 +144,7 @@ def test_distill_mse_emulated(distill, B):
     np.testing.assert_allclose(dwb, rdwb, rtol=1e-4)
 
 
-@pytest.mark.parametrize("B", [5, 29])
+@pytest.mark.parametrize("B", [5] + big(29))
 def test_distill_contrastive_emulated(distill, B):
     T, M = _distill_inputs(B, 100 + B)
     Tc = T.copy()
@@ -150,7 +157,7 @@ def test_distill_contrastive_emulated(distill, B):
     assert np.all(np.diag(Tc) == 0) and np.array_equal(Tc - np.diag(np.diag(Tc)), T - np.diag(np.diag(T)))
 
 
-@pytest.mark.parametrize("B,stride", [(6, 1), (29, 3)])
+@pytest.mark.parametrize("B,stride", [(6, 1)] + big((29, 3)))
 def test_distill_ordinal_emulated(distill, B, stride):
     T, M = _distill_inputs(B, 200 + B)
     loss, dM = np.zeros(1, np.float32), np.zeros((B, B), np.float32)
@@ -166,7 +173,7 @@ def _stable_desc(v):
     return np.argsort(v, kind="stable")[::-1]
 
 
-@pytest.mark.parametrize("Ni,ties,k", [(12, False, 10), (40, True, 30)])
+@pytest.mark.parametrize("Ni,ties,k", [(12, False, 10), (14, True, 10)] + big((40, True, 30)))
 def test_ranking_emulated(rank, Ni, ties, k):
     r = np.random.RandomState(Ni)
     Nc = 5 * Ni
@@ -406,8 +413,8 @@ def run_mrsw_bwd(lib, im, s, nr, nw, G0=None, g0_scale=None, G1=None, sbd_layout
     return d_im, d_s
 
 
-@pytest.mark.parametrize("shape,sbd", [((6, 7, 9, 12, 64), False), ((5, 4, 35, 53, 64), True), ((3, 4, 60, 80, 32), False),
-                                      ((4, 5, 8, 11, 20), False)])
+@pytest.mark.parametrize("shape,sbd", [((6, 7, 9, 12, 64), False), ((3, 4, 60, 80, 32), False), ((4, 5, 8, 11, 20), False)]
+                         + big(((5, 4, 35, 53, 64), True)))
 def test_mrsw_backward_emulated(mrsw_bwd, shape, sbd):
     """Sparse MrSw backward: the register-tiled pair kernels (d % 32 == 0: <5,2>, <9,3>) and the
     generic kernel (d = 20), contiguous and [S,B,d] gradient layouts, hinge gradient scaled on the device plus a
@@ -453,7 +460,7 @@ def test_cuda_core_kernels_are_race_free_under_thread_sanitizer():
     if os.environ.get("ALAD_EMU_TSAN") == "1":
         pytest.skip("already inside the sanitizer run")
     env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0", ALAD_EMU_TSAN="1")
-    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-k", "not reference_golden",
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-k", "not golden",
                           os.path.abspath(__file__)],
                          env=env, capture_output=True, text=True, timeout=2400, cwd=os.path.dirname(HERE))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

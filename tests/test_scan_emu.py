@@ -26,7 +26,7 @@ _I32, _I64, _P = C.c_int32, C.c_int64, C.c_void_p
 def emu():
     import build_emu
     from aladin_b200 import _cabi
-    lib = C.CDLL(build_emu.build("scan_pool"))
+    lib = C.CDLL(build_emu.build_library())
     for name in ("alad_scan_gram", "alad_scan_gram_bwd", "alad_scan_pool_fwd", "alad_scan_pool_bwd", "alad_scan_apply_pairs"):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = _cabi.PROTOTYPES[name]
