@@ -39,11 +39,13 @@ static_assert(NTILE_WORDS <= 32, "one lane per table word");
 
 // Per-variant geometry.  CG = 1: one CTA per 128 x 240 tile.  CG = 2: a CTA pair (cta_group::2)
 // per 256 x 240 tile -- each CTA stages its own 128 word rows and HALF of the region rows, which
-// cuts the shared-memory fill per SM from 46 KB to 31 KB per K block and leaves room for 6 stages.
+// cuts the shared-memory fill per SM from 46 KB to 31 KB per K block.  Ring depth: 4 stages cover the L2 round
+// trip; deeper rings only lower the clock the power cap allows (4 stages 322 ms, 6 stages 341 ms per COCO-5k launch
+// on the same box, profiles/r01_tile_order_sweep.md section 10).
 template <int CG>
 struct Cfg {
 #ifndef ALAD_STAGES_CG2
-#define ALAD_STAGES_CG2 6
+#define ALAD_STAGES_CG2 4
 #endif
 #ifndef ALAD_RES_KB
 #define ALAD_RES_KB 0
@@ -611,10 +613,11 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
     if ((long long)p.n_mtiles * p.n_block >= (1ll << 31)) p.n_block = 8;
     const char* eh = getenv("ALAD_L2_HINTS");
     p.l2_hints = eh ? atoi(eh) : 0;
-    // the word-row prefetch pays off only in the lock-step order (every unit on the same M unit, one region
-    // tile per unit): measured +0.6 % at 74 tiles / bf16, but -8 % at 148 tiles and -19 % at 37 tiles / 3x split
+    // the word-row prefetch (ALAD_L2_PREFETCH=1) is OFF by default: with the 6-stage ring it measured +0.6 % at
+    // 74 tiles / bf16 (-8 % at 148 tiles, -19 % at 37 tiles / 3x split), but with the 4-stage ring the same-box A/B
+    // gives 322-324 ms without it against 337 ms with it (profiles/r01_tile_order_sweep.md section 10)
     const char* ep = getenv("ALAD_L2_PREFETCH");
-    p.l2_prefetch = ep ? atoi(ep) : (p.n_block == units_in_flight ? 1 : 0);
+    p.l2_prefetch = ep ? atoi(ep) : 0;
     // resident region K blocks (compile-time Cfg<2>::RES > 0): only where a unit keeps its region tile
     const char* er = getenv("ALAD_B_RESIDENT");
     p.b_resident = er ? atoi(er) : (p.n_block > 0 && units_in_flight % p.n_block == 0 ? 1 : 0);

@@ -6,6 +6,6 @@ nvidia-smi --query-gpu=name,pci.bus_id,serial --format=csv | tee gpurun_out/ab_b
 for i in 1 2; do
   for lib in libalad_b200_prev.so libalad_b200.so; do
     echo "== $lib (pass $i)"
-    ALAD_B200_LIB=$PWD/aladin_b200/$lib SWEEP_CONFIGS="1074:4,1074:0" timeout 200 python tools/sweep_tile_order.py 3 2>&1 | tail -1
+    ALAD_B200_LIB=$PWD/aladin_b200/$lib SWEEP_CONFIGS="${AB_CONFIGS:-1074:4,1074:0}" timeout 200 python tools/sweep_tile_order.py 3 2>&1 | tail -1
   done
 done | tee gpurun_out/ab_prev.log
