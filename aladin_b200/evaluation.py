@@ -12,7 +12,7 @@ import weakref
 import numpy as np
 import torch
 
-from . import ranking, retrieval, scoring
+from . import retrieval, scoring
 
 _cache = {}
 

@@ -17,7 +17,6 @@ The nn.Module drop-ins of loss.py use torch.autograd.Function directly (they als
 inputs and move them); these ops are the traceable surface of the same kernels."""
 from typing import List, Tuple
 
-import numpy as np
 import torch
 from torch import Tensor
 

@@ -10,8 +10,6 @@ replicated.  i2t needs no exchange; t2i exchanges the ground-truth scores (all-r
 Nc floats), the per-shard counts (all-reduce of Nc ints) and the per-shard top-k candidates
 (all-gather of k (score, index) pairs per caption) through torch.distributed / NCCL.
 """
-import ctypes as C
-
 import numpy as np
 import torch
 

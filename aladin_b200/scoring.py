@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .tiling import (build_region_tiles, exclusive_cumsum, gemm_tiles, padded_rows, round_up, valid_counts)
+from .tiling import exclusive_cumsum, padded_rows, round_up, valid_counts
 
 PRECISIONS = ("bf16", "fp32")
 # bench.py sets this to a list to collect (start_event, end_event, pairs, Kp) of every scoring launch
