@@ -131,6 +131,7 @@ def virtual_b200(monkeypatch):
         def factory(*a, _orig=orig, **k):
             if "device" in k:
                 k["device"] = cpu_device(k["device"])
+            k.pop("pin_memory", None)
             t = _orig(*a, **k)
             if t.numel() and t.data_ptr() % 256:
                 # device allocations are 256-byte aligned (the C ABI checks its workspaces); CPU ones are not

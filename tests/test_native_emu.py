@@ -1,4 +1,4 @@
-"""CPU-only: the `-m gpu` parity tests of the loss / scoring drop-ins, UNCHANGED, on the "virtual B200" of
+"""CPU-only: the `-m gpu` parity tests of the loss / scoring / ranking / evaluation drop-ins, UNCHANGED, on the "virtual B200" of
 tests/conftest.py -- the Python host layer, the native compositions (alad_scores_fused, alad_train_losses_fwd/_bwd:
 host bookkeeping, tile tables, workspace layout, launch order) and every CUDA-core kernel run from their real
 sources on CPU tensors; only the tcgen05 scoring kernel is replaced by a CPU double of its documented contract
@@ -8,6 +8,7 @@ import pytest
 import test_gpu_distill_modes as TD
 import test_gpu_losses as TL
 import test_gpu_ranking as TR
+import test_gpu_retrieval as TE
 import test_gpu_scoring as TS
 import test_gpu_train_step as TT
 import test_gpu_zz_scan_sentences as TZ
@@ -39,6 +40,8 @@ CASES = [
     (TR.test_rank_kernels_reproduce_reference_golden, {}),
     (TR.test_sharded_ranking_equals_single_shard, {}),
     (TR.test_col_topk_select_strided_view, {}),
+    (TE.test_i2t_t2i_alignment_golden, dict(precision="fp32")),
+    (TE.test_arbitrary_callable_sim_function, {}),
     (TT.test_fused_losses_match_reference_training_step, {}),
     (TZ.test_scores_golden, dict(precision="fp32")),
     (TZ.test_degenerate_lengths_like_reference, {}),
