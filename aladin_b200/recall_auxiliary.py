@@ -37,10 +37,18 @@ def recall_test(img_embs, cap_embs, tot_lengths=None, model=None):
     return r1, r5, r10, r1i, r5i, r10i, r1 + r5 + r10 + r1i + r5i + r10i
 
 
+FOLD_ROWS = 5000          # rows per fold: 1000 images x 5 (alad/recall_auxiliary.py:99-100)
+
+
 def recall_1k_5fold_test(img_embs, cap_embs, tot_lengths=None, model=None):
-    folds = [recall_test(i, c) for i, c in zip(torch.split(img_embs, 5000, dim=0)[:5], torch.split(cap_embs, 5000, dim=0)[:5])]
-    for k in range(len(folds)):
-        print('Computing Test recall... chunk %s of 5' % (k + 1))
+    """alad/recall_auxiliary.py:90-130: mean of recall_test over the first five 5000-row chunks (IndexError, like
+    the reference, when there are fewer than five)."""
+    img_chunks = torch.split(img_embs, FOLD_ROWS, dim=0)
+    cap_chunks = torch.split(cap_embs, FOLD_ROWS, dim=0)
+    folds = []
+    for i in range(5):
+        print('Computing Test recall... chunk %s of 5' % (i + 1))
+        folds.append(recall_test(img_chunks[i], cap_chunks[i]))
     r1, r5, r10, r1i, r5i, r10i = (float(np.mean([f[j] for f in folds])) for j in range(6))
     rsum = r1 + r5 + r10 + r1i + r5i + r10i
     print("Test 1K 5Folds - Recall Image to text: %.2f, %.2f, %.2f" % (r1, r5, r10))

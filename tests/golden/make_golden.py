@@ -403,9 +403,72 @@ def golden_scan_sentences():
     save("scan_sentences", **out)
 
 
+# ---------------------------------------------------------------------------------------
+# 10. consumers of the ranking output: the ndcg_scorer hooks of i2t / t2i
+#     (alad/evaluation.py:225-228,310-313) and recall_1k_5fold_test (alad/recall_auxiliary.py:90-130)
+# ---------------------------------------------------------------------------------------
+class RecordingScorer:
+    """Stands in for evaluate_utils.dcg.DCG (which needs external relevance files): records what the reference
+    hands to compute_ndcg; DCG itself only reads sorted_indexes[:rank], rank = 25 (dcg.py:19-20)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def compute_ndcg(self, npts, query_id, sorted_indexes, fold_index=0, retrieval='image'):
+        self.calls.append((int(npts), int(query_id), np.asarray(sorted_indexes[:25]).astype(np.int64), int(fold_index), retrieval))
+        return {'rougeL': 0.25, 'spice': 0.5}
+
+
+def fold_embeddings(seed, n_rows, d):
+    """Global vectors [n_rows, d] for the 5-fold test, regenerated from the seed by the tests (only the
+    reference's OUTPUTS are stored): image rows repeated 5x, captions = image + noise."""
+    r = rs(seed)
+    base = r.standard_normal((n_rows // 5, d)).astype(np.float32)
+    img = np.repeat(base, 5, axis=0)
+    cap = (img + 1.5 * r.standard_normal((n_rows, d))).astype(np.float32)
+    return img, cap
+
+
+def golden_ranking_consumers():
+    g = dict(np.load(os.path.join(HERE, "retrieval.npz")))
+    images = np.repeat(g["images"], 5, axis=0)
+    captions, img_lens, cap_lens = g["captions"], g["img_lens"].tolist(), g["cap_lens"].tolist()
+    crit = rloss.AlignmentContrastiveLoss(aggregation="MrSw")
+
+    def sim_fn(img, cap, img_len, cap_len):
+        with torch.no_grad():
+            return crit(img, cap, img_len, cap_len, return_loss=False, return_similarity_mat=True)
+
+    ti, tc = torch.from_numpy(images), torch.from_numpy(captions)
+    out = {}
+    sink = io.StringIO()
+    with contextlib.redirect_stderr(sink), contextlib.redirect_stdout(sink):
+        for tag, fn, kw in (("i2t", reval.i2t, dict(cap_batches=5)), ("t2i", reval.t2i, dict(im_batches=5))):
+            sc = RecordingScorer()
+            m = fn(ti, tc, img_lens, cap_lens, ndcg_scorer=sc, fold_index=2, sim_function=sim_fn, **kw)
+            out[f"{tag}_metrics"] = np.array(m, dtype=np.float64)
+            out[f"{tag}_query"] = np.array([c[1] for c in sc.calls])
+            out[f"{tag}_order25"] = np.stack([c[2] for c in sc.calls])
+            assert all(c[0] == 60 and c[3] == 2 and c[4] == ("sentence" if tag == "i2t" else "image") for c in sc.calls)
+    # 5-fold recall: the unmodified function on 25000 rows (5 folds of 1000 images x 5000 captions), and the same
+    # protocol on 5 folds of 50 images x 250 captions through the reference's recall_test (what the CPU tests use)
+    img, cap = fold_embeddings(41, 25000, 8)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out["fold5000"] = np.array(rrec.recall_1k_5fold_test(torch.from_numpy(img), torch.from_numpy(cap)), dtype=np.float64)
+    out["fold5000_stdout"] = np.array(buf.getvalue())
+    img, cap = fold_embeddings(42, 1250, 8)
+    with contextlib.redirect_stdout(io.StringIO()):
+        folds = [rrec.recall_test(torch.from_numpy(img[k * 250:(k + 1) * 250]), torch.from_numpy(cap[k * 250:(k + 1) * 250]), None, None)
+                 for k in range(5)]
+    small = [float(np.mean([f[j] for f in folds])) for j in range(6)]
+    out["fold250"] = np.array(small + [sum(small)], dtype=np.float64)
+    save("ranking_consumers", **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for fn in (golden_alignment_scores, golden_alignment_loss, golden_matching, golden_triplet_listnet, golden_retrieval,
-               golden_train_step, golden_distill_modes, golden_pooled_grads, golden_scan_sentences):
+               golden_train_step, golden_distill_modes, golden_pooled_grads, golden_scan_sentences, golden_ranking_consumers):
         if not only or fn.__name__ in only or fn.__name__.replace("golden_", "") in only:
             fn()

@@ -1,0 +1,94 @@
+"""GPU parity tests for the consumers of the ranking output: recall_1k_5fold_test
+(alad/recall_auxiliary.py:90-130) and the ndcg_scorer hooks of i2t / t2i (alad/evaluation.py:225-228,310-313)
+against tests/golden/ranking_consumers.npz (outputs of the unmodified reference; the 5-fold inputs are
+regenerated from their seed).  Recall values may differ by single queries whose decisive scores sit within
+fp32 rounding of each other (the reference's mm vs the split-precision tcgen05 GEMM): the tolerance is two
+such queries."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_order_equal_up_to_ties, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def fold_embeddings(seed, n_rows, d):
+    """Same construction as tests/golden/make_golden.py:fold_embeddings."""
+    r = np.random.RandomState(seed)
+    base = r.standard_normal((n_rows // 5, d)).astype(np.float32)
+    img = np.repeat(base, 5, axis=0)
+    cap = (img + 1.5 * r.standard_normal((n_rows, d))).astype(np.float32)
+    return img, cap
+
+
+def check_fold_result(got, ref, queries_i2t, queries_t2i):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    tol_i = 2 * 100.0 / queries_i2t / 5 + 1e-9            # two queries in one of the five folds
+    tol_t = 2 * 100.0 / queries_t2i / 5 + 1e-9
+    assert np.all(np.abs(got[:3] - ref[:3]) <= tol_i), (got, ref)
+    assert np.all(np.abs(got[3:6] - ref[3:6]) <= tol_t), (got, ref)
+    assert abs(got[6] - got[:6].sum()) < 1e-9 and abs(got[6] - ref[6]) <= 3 * (tol_i + tol_t)
+
+
+def test_recall_1k_5fold_full_size(capsys):
+    import aladin_b200
+    from aladin_b200 import recall_auxiliary as RA
+    g = load_golden("ranking_consumers")
+    img, cap = fold_embeddings(41, 25000, 8)
+    aladin_b200.set_precision("fp32")
+    try:
+        got = RA.recall_1k_5fold_test(torch.from_numpy(img), torch.from_numpy(cap))
+    finally:
+        aladin_b200.set_precision("bf16")
+    check_fold_result(got, g["fold5000"], 1000, 5000)
+    out, ref_out = capsys.readouterr().out.splitlines(), str(g["fold5000_stdout"]).splitlines()
+    assert out[:5] == ref_out[:5] and len(out) == len(ref_out) == 8
+    assert [l.split(":")[0] for l in out[5:]] == [l.split(":")[0] for l in ref_out[5:]]
+    assert all(isinstance(v, float) for v in got)
+
+
+def test_recall_1k_5fold_small_folds_and_missing_folds(monkeypatch, capsys):
+    import aladin_b200
+    from aladin_b200 import recall_auxiliary as RA
+    g = load_golden("ranking_consumers")
+    img, cap = fold_embeddings(42, 1250, 8)
+    monkeypatch.setattr(RA, "FOLD_ROWS", 250)
+    aladin_b200.set_precision("fp32")
+    try:
+        got = RA.recall_1k_5fold_test(torch.from_numpy(img), torch.from_numpy(cap))
+        check_fold_result(got, g["fold250"], 50, 250)
+        with pytest.raises(IndexError):                     # the reference indexes chunk 4 of a 4-chunk split
+            RA.recall_1k_5fold_test(torch.from_numpy(img[:1000]), torch.from_numpy(cap[:1000]))
+    finally:
+        aladin_b200.set_precision("bf16")
+
+
+class RecordingScorer:
+    def __init__(self):
+        self.calls = []
+
+    def compute_ndcg(self, npts, query_id, sorted_indexes, fold_index=0, retrieval='image'):
+        assert sorted_indexes.dtype.kind == "i"
+        self.calls.append((int(npts), int(query_id), np.asarray(sorted_indexes[:25]).astype(np.int64), int(fold_index), retrieval))
+        return {'rougeL': 0.25, 'spice': 0.5}
+
+
+def test_ndcg_scorer_hooks_receive_the_reference_order():
+    from aladin_b200 import evaluation, loss as L
+    g, r = load_golden("ranking_consumers"), load_golden("retrieval")
+    images = torch.from_numpy(np.repeat(r["images"], 5, axis=0))
+    captions = torch.from_numpy(r["captions"])
+    img_lens, cap_lens = r["img_lens"].tolist(), r["cap_lens"].tolist()
+    crit = L.AlignmentContrastiveLoss(aggregation="MrSw")
+    crit.precision = "fp32"
+    S = r["S_full"]
+    for tag, fn, kw, scores in (("i2t", evaluation.i2t, dict(cap_batches=5), S), ("t2i", evaluation.t2i, dict(im_batches=5), S.T)):
+        sc = RecordingScorer()
+        evaluation.clear_cache()
+        m = fn(images, captions, img_lens, cap_lens, ndcg_scorer=sc, fold_index=2, sim_function=crit, **kw)
+        np.testing.assert_allclose(np.array(m, dtype=np.float64), g[f"{tag}_metrics"], rtol=0, atol=1e-12)
+        assert [c[1] for c in sc.calls] == g[f"{tag}_query"].tolist()
+        assert all(c[0] == 60 and c[3] == 2 and c[4] == ("sentence" if tag == "i2t" else "image") for c in sc.calls)
+        got = np.stack([c[2] for c in sc.calls])
+        assert_order_equal_up_to_ties(got, g[f"{tag}_order25"], scores, 1e-4, f"{tag} order handed to the scorer")

@@ -12,6 +12,7 @@ import test_gpu_retrieval as TE
 import test_gpu_scoring as TS
 import test_gpu_train_step as TT
 import test_gpu_zz_scan_sentences as TZ
+import test_gpu_zzz_ranking_consumers as TC
 
 CASES = [
     (TS.test_pack_tokens_matches_normalize, {}),
@@ -42,6 +43,8 @@ CASES = [
     (TR.test_col_topk_select_strided_view, {}),
     (TE.test_i2t_t2i_alignment_golden, dict(precision="fp32")),
     (TE.test_arbitrary_callable_sim_function, {}),
+    (TC.test_recall_1k_5fold_small_folds_and_missing_folds, {}),
+    (TC.test_ndcg_scorer_hooks_receive_the_reference_order, {}),
     (TT.test_fused_losses_match_reference_training_step, {}),
     (TZ.test_scores_golden, dict(precision="fp32")),
     (TZ.test_degenerate_lengths_like_reference, {}),
@@ -51,8 +54,10 @@ CASES = [
 
 
 @pytest.mark.parametrize("fn,kwargs", CASES, ids=[f"{f.__module__}.{f.__name__}[{','.join(map(str, k.values()))}]" for f, k in CASES])
-def test_gpu_test_body_on_the_virtual_device(virtual_b200, monkeypatch, fn, kwargs):
+def test_gpu_test_body_on_the_virtual_device(virtual_b200, monkeypatch, capsys, fn, kwargs):
     import inspect
     if "monkeypatch" in inspect.signature(fn).parameters:
         kwargs = dict(kwargs, monkeypatch=monkeypatch)
+    if "capsys" in inspect.signature(fn).parameters:
+        kwargs = dict(kwargs, capsys=capsys)
     fn(**kwargs)
