@@ -11,7 +11,7 @@
 // and iteration, 74 pairs on 148 SMs), single-CTA variant (128 x 240) kept for A/B:
 //   warps 0-3  epilogue: tcgen05.ld windows -> FMNMX3 max over each image's columns -> smem -> ordered
 //              per-caption row sums -> <= 2 atomic addends per S entry (bit-reproducible)
-//   warp 4     TMA producer (4-stage smem ring, 128B swizzle, optional L2 prefetch of the next word rows)
+//   warp 4     TMA producer (4-stage smem ring, 128B swizzle, L2 prefetch of the next word rows)
 //   warp 5     tcgen05.mma issuer (one lane of the leader CTA), 2 accumulator stages in TMEM
 #include <math.h>
 #include <stdlib.h>
