@@ -35,3 +35,25 @@ def test_kernels_are_blackwell_native(built_lib):
     assert "UTMALDG" in sass      # TMA
     assert "LDTM" in sass         # tcgen05.ld
     assert "sm_100a" in sass
+
+
+def test_scoring_kernel_resources(built_lib):
+    """The tcgen05 kernel must stay spill-free and inside the register budget of 6 warps x 1 CTA/SM; its performance is
+    sensitive to code-generation changes (profiles/r01_tile_order_sweep.md sections 9, 10), so a change in these numbers is
+    a reason to re-run the same-box A/B (tools/ab_prev.sh) before trusting a bench line."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-res-usage", built_lib], capture_output=True, text=True).stdout
+    seen = 0
+    lines = out.splitlines()
+    for i, line in enumerate(lines):
+        if "mrsw_fwd_kernel" in line and i + 1 < len(lines):
+            m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", lines[i + 1])
+            assert m, lines[i + 1]
+            reg, stack, _, local = map(int, m.groups())
+            assert stack == 0 and local == 0, f"spills in {line.strip()}"
+            assert reg <= 168, f"{reg} registers in {line.strip()}"     # 65536 / 384 threads = 170
+            seen += 1
+    assert seen == 2                                     # the single-CTA and the CTA-pair variants
