@@ -54,6 +54,6 @@ def test_scoring_kernel_resources(built_lib):
             assert m, lines[i + 1]
             reg, stack, _, local = map(int, m.groups())
             assert stack == 0 and local == 0, f"spills in {line.strip()}"
-            assert reg <= 168, f"{reg} registers in {line.strip()}"     # 65536 / 384 threads = 170
+            assert reg <= 168, f"{reg} registers in {line.strip()}"     # 135-136 today; a jump = different code generation
             seen += 1
     assert seen == 2                                     # the single-CTA and the CTA-pair variants
