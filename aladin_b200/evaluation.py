@@ -4,7 +4,8 @@ Same signatures, same return tuples (7 metrics, optionally (ranks, top1) / (rank
 float64 numpy arrays).  When ``sim_function`` is (or closes over) an
 ``aladin_b200.loss.AlignmentContrastiveLoss`` with aggregation 'MrSw' -- which is exactly
 what alad/test.py:258-264 and alad/train.py:493-500 build -- the whole Ni x Nc score block is
-computed once on the GPU and both directions are ranked from it; ``sim_function=None`` is the
+computed once on the GPU and both directions are ranked from it (the other pooling modes of the
+drop-in criterion get the same treatment through one criterion call on the whole gallery); ``sim_function=None`` is the
 global-vector path on slot 0 (evaluation.py:195-197,284-286); any other callable is invoked
 per query like the reference does, and only the ranking runs in our kernels."""
 import weakref
@@ -28,7 +29,7 @@ def _find_scorer(fn):
         except ValueError:
             pass
     for c in cands:
-        if isinstance(c, AlignmentContrastiveLoss) and c.aggregation == "MrSw":
+        if isinstance(c, AlignmentContrastiveLoss) and c.aggregation in c.SUPPORTED:
             return c
     return None
 
@@ -57,6 +58,17 @@ def _callback_scores(images, captions, img_lens, cap_lens, sim_function, cap_bat
     return S
 
 
+def _block_scores(images, captions, img_lens, cap_lens, scorer):
+    """Any pooling mode of the drop-in criterion other than 'MrSw' ('MrAVGw', 'MwSr', 'symm', 'sum', 'mean',
+    'scan-sentences'): ONE criterion call on the distinct gallery images x all captions instead of one call per
+    query and gallery chunk (evaluation.py:199-210, 288-300) -- every pair's score is independent of how the
+    calls are batched, so the block equals the matrix the per-query loop assembles."""
+    with torch.no_grad():
+        ims = images[0::5].cuda()
+        caps = captions.cuda()
+        return scorer(ims, caps, list(img_lens[0::5]), list(cap_lens), return_loss=False, return_similarity_mat=True).float()
+
+
 def clear_cache():
     """Forget the score block kept from the previous i2t/t2i call."""
     _cache.clear()
@@ -75,16 +87,20 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
     Returns dict(S, img_off, ranks_i2t, top1, ranks_t2i, top50).  Under torch.distributed
     (world > 1) the fused path shards the gallery images across ranks (retrieval.py)."""
     scorer = _find_scorer(sim_function)
-    mode = "global" if sim_function is None else ("fused" if scorer is not None else "callback")
+    mode = "global" if sim_function is None else ("callback" if scorer is None else
+                                                   "fused" if scorer.aggregation == "MrSw" else "block")
+    from .gallery import DeviceContainer
+    if mode == "block" and (_dist_state()[0] > 1 or isinstance(images, DeviceContainer)):
+        mode = "callback"                     # sharding and packed containers exist for the 'MrSw' kernel only
     precision = getattr(scorer, "precision", None) or scoring.get_precision()
-    key = _key(images, captions, img_lens, cap_lens, mode, precision) if mode != "callback" else None
+    mode_key = mode if scorer is None else f"{mode}:{scorer.aggregation}"
+    key = _key(images, captions, img_lens, cap_lens, mode_key, precision) if mode != "callback" else None
     if (key is not None and _cache.get("key") == key and _cache["refs"][0]() is images
             and _cache["refs"][1]() is captions):
         return _cache["res"]
     Ni = images.shape[0] // 5
     world, rank, group = (1, 0, None)
     img_off = 0
-    from .gallery import DeviceContainer
     if isinstance(images, DeviceContainer) and mode == "callback":
         raise TypeError("DeviceContainer galleries hold packed tokens only: pass sim_function=None or a closure over "
                         "aladin_b200.loss.AlignmentContrastiveLoss('MrSw')")
@@ -99,6 +115,8 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
                                          precision=precision, world=world, rank=rank)
         S = gal.scores(group=group)
         img_off = gal.lo
+    elif mode == "block":
+        S = _block_scores(images, captions, img_lens, cap_lens, scorer)
     else:
         S = _callback_scores(images, captions, img_lens, cap_lens, sim_function, batches)
     k = min(50, Ni)

@@ -92,3 +92,60 @@ def test_ndcg_scorer_hooks_receive_the_reference_order():
         assert all(c[0] == 60 and c[3] == 2 and c[4] == ("sentence" if tag == "i2t" else "image") for c in sc.calls)
         got = np.stack([c[2] for c in sc.calls])
         assert_order_equal_up_to_ties(got, g[f"{tag}_order25"], scores, 1e-4, f"{tag} order handed to the scorer")
+
+
+class _Opaque:
+    """A callable that hides the criterion from evaluation._find_scorer -> the per-query callback path."""
+
+    def __init__(self, registry, key):
+        self.registry, self.key = registry, key
+
+    def __call__(self, img, cap, img_len, cap_len):
+        return self.registry[self.key](img, cap, img_len, cap_len, return_loss=False, return_similarity_mat=True)
+
+
+@pytest.mark.parametrize("agg", ["symm", "mean", "scan-sentences"])
+def test_other_pooling_modes_one_block_equals_per_query_callbacks(agg):
+    """A closure over the drop-in criterion with a pooling mode other than 'MrSw' is scored with ONE criterion call
+    on the whole gallery; the result must be what the reference-style per-query loop assembles, and two modes on
+    the same tensors must not share a cached block."""
+    from aladin_b200 import evaluation, loss as L
+    from conftest import assert_ranks_equal_up_to_ties
+    r = load_golden("retrieval")
+    images = torch.from_numpy(np.repeat(r["images"], 5, axis=0))
+    captions = torch.from_numpy(r["captions"])
+    il, cl = r["img_lens"].tolist(), r["cap_lens"].tolist()
+    crit = L.AlignmentContrastiveLoss(aggregation=agg)
+    crit.precision = "fp32"
+
+    def sim_fn(img, cap, img_len, cap_len):
+        return crit(img, cap, img_len, cap_len, return_loss=False, return_similarity_mat=True)
+
+    calls = []
+    orig = crit.forward
+    crit.forward = lambda *a, **k: (calls.append(a[0].shape[0]), orig(*a, **k))[1]
+    evaluation.clear_cache()
+    mi, (ri, t1) = evaluation.i2t(images, captions, il, cl, return_ranks=True, sim_function=sim_fn, cap_batches=5)
+    mt, (rt, t50) = evaluation.t2i(images, captions, il, cl, return_ranks=True, sim_function=sim_fn, im_batches=5)
+    assert calls == [60]                                   # one call, shared by both directions
+    S = evaluation._cache["res"]["S"].cpu().numpy()
+    other = L.AlignmentContrastiveLoss(aggregation="MrSw" if agg != "MrSw" else "symm")
+    m_other = evaluation.i2t(images, captions, il, cl, sim_function=other)
+    assert evaluation._cache["key"][-2].endswith(other.aggregation) and len(m_other) == 7
+    opaque = _Opaque({"c": crit}, "c")
+    calls.clear()
+    mi2, (ri2, t12) = evaluation.i2t(images, captions, il, cl, return_ranks=True, sim_function=opaque, cap_batches=5)
+    assert len(calls) == 60 * 5                            # reference-style loop: one call per query and gallery chunk
+    gt = np.array([5 * i + int(np.argmax(S[i, 5 * i:5 * i + 5])) for i in range(60)])
+    assert_ranks_equal_up_to_ties(ri, ri2, S, gt, 1e-5, f"{agg}: block vs per-query i2t ranks")
+    from oracle import alad_oracle as O
+    if agg != "scan-sentences":
+        ref = O.alignment_scores_small(r["images"], r["captions"], il[0::5], cl, agg)
+    else:
+        ref = O.scan_scores(r["images"], r["captions"], il[0::5], cl)
+    ok = ~np.isnan(ref)
+    assert np.array_equal(np.isnan(S), np.isnan(ref))
+    scale = max(np.abs(ref[ok]).max(), 1e-30)
+    assert np.abs(S[ok] - ref[ok]).max() <= 1e-4 * scale
+    if ok.all():
+        assert_ranks_equal_up_to_ties(rt, O.t2i_ranks(ref)[0], ref.T, np.arange(300) // 5, 1e-4, f"{agg}: t2i ranks vs oracle")

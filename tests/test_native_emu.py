@@ -61,3 +61,31 @@ def test_gpu_test_body_on_the_virtual_device(virtual_b200, monkeypatch, capsys, 
     if "capsys" in inspect.signature(fn).parameters:
         kwargs = dict(kwargs, capsys=capsys)
     fn(**kwargs)
+
+
+@pytest.mark.parametrize("agg", ["symm", "scan-sentences"])
+def test_block_mode_of_i2t_on_a_small_gallery(virtual_b200, agg):
+    """evaluation.i2t with a closure over the drop-in criterion in a pooling mode other than 'MrSw': one criterion
+    call on the whole gallery (the GPU test of the same path also runs the per-query loop, which is too slow for
+    the emulator); scores and ranks against the oracle."""
+    import numpy as np
+    import torch
+    from aladin_b200 import evaluation, loss as L, synth
+    from oracle import alad_oracle as O
+    images, captions, il, cl = synth.eval_containers(3, 8, 14, 32, max_regions=9, max_words=10)
+    crit = L.AlignmentContrastiveLoss(aggregation=agg)
+    crit.precision = "fp32"
+    calls = []
+    orig = crit.forward
+    crit.forward = lambda *a, **k: (calls.append(a[0].shape[0]), orig(*a, **k))[1]
+    evaluation.clear_cache()
+    m, (ranks, top1) = evaluation.i2t(torch.from_numpy(images), torch.from_numpy(captions), il, cl, return_ranks=True,
+                                      sim_function=lambda im, cap, a, b: crit(im, cap, a, b, return_loss=False,
+                                                                              return_similarity_mat=True), cap_batches=2)
+    assert calls == [8]
+    ref = (O.alignment_scores_small(images[0::5], captions, il[0::5], cl, agg) if agg != "scan-sentences"
+           else O.scan_scores(images[0::5], captions, il[0::5], cl))
+    S = evaluation._cache["res"]["S"].numpy()
+    np.testing.assert_allclose(S, ref, rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(ranks, O.i2t_ranks(ref)[0])
+    assert evaluation._cache["key"][-2] == f"block:{agg}"
