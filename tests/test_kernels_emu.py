@@ -463,5 +463,7 @@ def test_cuda_core_kernels_are_race_free_under_thread_sanitizer():
     res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-k", "not golden",
                           os.path.abspath(__file__)],
                          env=env, capture_output=True, text=True, timeout=2400, cwd=os.path.dirname(HERE))
+    if "FATAL: ThreadSanitizer" in res.stderr:           # the sanitizer runtime cannot start here (e.g. address-space layout)
+        pytest.skip("ThreadSanitizer runtime unavailable: " + res.stderr.strip().splitlines()[0][:200])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "ThreadSanitizer: data race" not in res.stderr, res.stderr[:6000]

@@ -265,5 +265,7 @@ def test_scan_kernels_are_race_free_under_thread_sanitizer():
     env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0")
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emu", "tsan_scan.py")
     res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=900)
+    if "FATAL: ThreadSanitizer" in res.stderr:           # the sanitizer runtime cannot start here (e.g. address-space layout)
+        pytest.skip("ThreadSanitizer runtime unavailable: " + res.stderr.strip().splitlines()[0][:200])
     assert "scan tsan ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
     assert "ThreadSanitizer: data race" not in res.stderr, res.stderr[:4000]
