@@ -517,6 +517,28 @@ def scan_scores(im_set, s_seq, im_len, s_len, acc64: bool = True):
     return S.astype(F32)
 
 
+def scan_fragile_pairs(im_set, s_seq, im_len, s_len, tol=3e-5, floor=1e-3):
+    """bool [Bi,Bc]: pairs on which 'scan-sentences' is DISCONTINUOUS in the cosines.  alad/loss.py:137-138 feeds
+    relu(cos) through F.normalize over the regions: when every other region of a word column is <= 0 (column norm
+    without it < floor) and one cosine sits within `tol` of 0, that entry normalises to 0 or to 1 depending on its
+    sign, so two fp32-grade GEMMs (the reference's own CPU and GPU matmuls included) legitimately disagree there.
+    Parity tests assert the tight bound on all other pairs and a loose one (|dS| <= 1, one region's cosine) here."""
+    imh = l2_normalize(im_set).astype(np.float64)
+    sh = l2_normalize(s_seq).astype(np.float64)
+    _, _, nr, nw = scored_extents(im_set.shape, s_seq.shape, im_len, s_len)
+    out = np.zeros((imh.shape[0], sh.shape[0]), dtype=bool)
+    for j in range(sh.shape[0]):
+        Y = sh[j, 1:1 + nw[j]]
+        for i in range(imh.shape[0]):
+            if nr[i] == 0 or nw[j] == 0:
+                continue
+            C = imh[i, 1:1 + nr[i]] @ Y.T
+            near = np.abs(C) < tol
+            rest = np.sqrt((np.where(near, 0.0, np.maximum(C, 0.0)) ** 2).sum(axis=0))
+            out[i, j] = bool((near.any(axis=0) & (rest < floor)).any())
+    return out
+
+
 def scan_backward(im_set, s_seq, im_len, s_len, G):
     """Gradient of sum(G * S) for aggregation 'scan-sentences' w.r.t. the raw inputs, fp64 internally
     (autograd through alad/loss.py:80-81, 137-149).  Pairs with nw = 0 are skipped (the reference yields NaN)."""

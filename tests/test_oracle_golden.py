@@ -263,3 +263,13 @@ def test_scan_sentences_backward_matches_reference_where_it_is_finite():
     full = [i for i, l in enumerate(il) if l == g["a_im"].shape[1]]
     assert full and np.isfinite(ref[full]).all()
     np.testing.assert_allclose(d_im[full], ref[full], rtol=1e-4, atol=2e-6)
+
+
+def test_scan_fragile_pairs_flags_the_discontinuity_of_the_reference_op():
+    """relu -> F.normalize over the regions (alad/loss.py:137-138): the golden gallery has exactly three pairs with a
+    word column whose only non-negative cosine is ~0; perturbing the cosines at the 1e-5 level (what separates two
+    fp32-grade GEMMs) moves one of them by 2.5e-2 and every other pair by < 2e-5."""
+    g = load_golden("retrieval")
+    il, cl = g["img_lens"].tolist()[0::5], g["cap_lens"].tolist()
+    fr = O.scan_fragile_pairs(g["images"], g["captions"], il, cl)
+    assert sorted(map(tuple, np.argwhere(fr).tolist())) == [(4, 45), (8, 260), (38, 122)]
