@@ -82,6 +82,30 @@ class MrswBwdArgs(C.Structure):
     ]
 
 
+PTILE_SLOTS, PTILE_WORDS = 8, 24
+
+
+class PairtileArgs(C.Structure):
+    """struct alad_pairtile_args (include/alad_b200.h)."""
+    _fields_ = [
+        ("n_groups", C.c_int32), ("group_row0", C.c_void_p), ("group_cap_lo", C.c_void_p), ("cap_group", C.c_void_p),
+        ("Nc", C.c_int32), ("lists_t2i", C.c_void_p), ("k_t2i", C.c_int32), ("lists_i2t", C.c_void_p), ("k_i2t", C.c_int32),
+        ("img_off", C.c_int32), ("n_loc", C.c_int32), ("region_row", C.c_void_p), ("nr", C.c_void_p), ("clamp", C.c_void_p),
+        ("slot_rows", C.c_int32), ("ptiles", C.c_void_p), ("capacity", C.c_int32), ("n_ptiles", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
+class MrswPairsArgs(C.Structure):
+    """struct alad_mrsw_pairs_args (include/alad_b200.h)."""
+    _fields_ = [
+        ("words", C.c_void_p), ("n_word_rows", C.c_int64), ("regions", C.c_void_p), ("n_region_rows", C.c_int64),
+        ("Kp", C.c_int32), ("row_cap", C.c_void_p), ("ptiles", C.c_void_p), ("n_ptiles", C.c_void_p),
+        ("max_ptiles", C.c_int32), ("slot_rows", C.c_int32), ("S", C.c_void_p), ("ldS", C.c_int64),
+        ("Ni", C.c_int32), ("Nc", C.c_int32), ("transpose_out", C.c_int32), ("num_ctas", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/alad_b200.h one to one
 _I32, _I64, _P = C.c_int32, C.c_int64, C.c_void_p
 PROTOTYPES = {
@@ -124,6 +148,12 @@ PROTOTYPES = {
     "alad_col_topk_select": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "alad_topk_merge": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "alad_shortlist_scatter": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P]),
+    "alad_caption_groups": (C.c_int, [_P, _I32, _P, _P, _P]),
+    "alad_pairtile_workspace_bytes": (C.c_int64, [_I32, _I32]),
+    "alad_pairtile_build": (C.c_int, [C.POINTER(PairtileArgs), _P]),
+    "alad_mrsw_scores_pairs": (C.c_int, [C.POINTER(MrswPairsArgs), _P]),
+    "alad_gather_list_scores": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "alad_list_rerank": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
 }
 
 _lib = None
@@ -158,6 +188,7 @@ KERNELS_PER_CALL = {
     "alad_distill_mse_fwd_bwd": 1, "alad_distill_contrastive_fwd_bwd": 2, "alad_distill_ordinal_fwd_bwd": 2,
     "alad_train_losses_fwd": 13, "alad_train_losses_bwd": 16,
     "alad_order_scores": 1, "alad_order_scores_bwd": 1, "alad_normalize_bwd": 1, "alad_pool_tokens_bwd": 1,
+    "alad_pairtile_build": 5, "alad_mrsw_scores_pairs": 1, "alad_gather_list_scores": 1, "alad_list_rerank": 1,
     "alad_scan_gram": 1, "alad_scan_gram_bwd": 1, "alad_scan_pool_fwd": 1, "alad_scan_pool_bwd": 1, "alad_scan_apply_pairs": 1,
 }
 launch_count = {"kernels": 0}

@@ -36,6 +36,11 @@ constexpr int ACC_COLS = 256;                 // column stride between accumulat
 constexpr int TMEM_COLS = 512;
 constexpr int NTILE_WORDS = sizeof(alad_ntile) / 4;   // 20
 static_assert(NTILE_WORDS <= 32, "one lane per table word");
+constexpr int PTILE_WORDS = sizeof(alad_ptile) / 4;   // 24
+static_assert(PTILE_WORDS <= 32 && ALAD_PTILE_SLOTS == 8, "one lane per table word; slot fields are unrolled by 8");
+// word offsets inside alad_ptile
+constexpr int PT_ROW0 = 0, PT_CAP_LO = 1, PT_CAP_HI = 2, PT_NSEG = 3, PT_CLAMP = 4, PT_SLOT_ROW = 5, PT_SLOT_IMG = 13,
+              PT_SLOT_W = 21;
 
 // Per-variant geometry.  CG = 1: one CTA per 128 x 240 tile.  CG = 2: a CTA pair (cta_group::2)
 // per 256 x 240 tile -- each CTA stages its own 128 word rows and HALF of the region rows, which
@@ -89,6 +94,12 @@ struct MrswParams {
   int l2_hints;     // TMA L2 policies: bit 0 = words evict_first, bit 1 = region block evict_last
   int l2_prefetch;  // 1: the CTAs cooperatively prefetch the next M unit's word rows into L2
   int b_resident;   // 1: keep the first Cfg::RES K blocks of the unit's region tile resident in shared memory
+  // pair-list mode (LIST = true, alad_mrsw_scores_pairs): tiles come from a device table instead of the dense
+  // (word tile, region tile) enumeration; every tile names its own word rows and up to 8 gathered image slots
+  const alad_ptile* ptiles;
+  const int32_t* n_ptiles;   // device scalar
+  int max_ptiles;
+  int slot_rows;
 };
 
 // full = the tile lies in a complete block of n_block region tiles (the last block may be shorter)
@@ -106,10 +117,11 @@ __device__ __forceinline__ void tile_coord(int t, int n_mtiles, int n_ntiles, in
   tile_coord(t, n_mtiles, n_ntiles, n_block, mt, nt, full);
 }
 
-template <int CG>
+template <int CG, bool LIST>
 __global__ void __launch_bounds__(THREADS, 1)
 mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_constant__ CUtensorMap map_regions,
                 const MrswParams p) {
+  static_assert(!LIST || CG == 1, "the pair-list mode runs single-CTA tiles (one or two captions per 128 word rows)");
   using C = Cfg<CG>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -134,7 +146,8 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
   const int unit = blockIdx.x / CG;                  // work unit: a CTA (CG=1) or a CTA pair (CG=2)
   const int n_units = gridDim.x / CG;
   const int n_munits = (p.n_mtiles + CG - 1) / CG;   // M tiles are consumed CG at a time
-  const int total_tiles = n_munits * p.n_ntiles;
+  int total_tiles = n_munits * p.n_ntiles;
+  if constexpr (LIST) total_tiles = min(__ldg(p.n_ptiles), p.max_ptiles);
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_words);
@@ -177,6 +190,31 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
       const uint64_t pol_words = (p.l2_hints & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
       const uint64_t pol_regions = (p.l2_hints & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
       for (int t = unit; t < total_tiles; t += n_units) {
+        if constexpr (LIST) {
+          // pair-list tile: 128 word rows from m_row0, one TMA box of slot_rows region rows per image slot
+          const int32_t* rec = reinterpret_cast<const int32_t*>(&p.ptiles[t]);
+          const int m_row0 = __ldg(rec + PT_ROW0);
+          const int nseg = __ldg(rec + PT_NSEG);
+          int srow[ALAD_PTILE_SLOTS];
+#pragma unroll
+          for (int s_i = 0; s_i < ALAD_PTILE_SLOTS; ++s_i) srow[s_i] = __ldg(rec + PT_SLOT_ROW + s_i);
+          const uint32_t slot_bytes = static_cast<uint32_t>(p.slot_rows) * (BK * 2);
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + C::OFF_A + stage * A_BYTES;
+            uint8_t* sb = smem + C::OFF_B + stage * C::B_BYTES;
+            mbar_expect_tx(&full_bar[stage], A_BYTES + static_cast<uint32_t>(nseg) * slot_bytes);
+            tma_load_2d(sa, &map_words, &full_bar[stage], kb * BK, m_row0);
+#pragma unroll
+            for (int s_i = 0; s_i < ALAD_PTILE_SLOTS; ++s_i)
+              if (s_i < nseg) tma_load_2d(sb + s_i * slot_bytes, &map_regions, &full_bar[stage], kb * BK, srow[s_i]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          continue;
+        }
         int mu, nt;
         bool full_block;
         tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt, full_block);
@@ -311,6 +349,13 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
     uint32_t nx_tab = 0;
     int nx_cap = 0, nx_above = 0;
     auto fetch_meta = [&](int t) {
+      if constexpr (LIST) {
+        if (lane < PTILE_WORDS) nx_tab = __ldg(reinterpret_cast<const uint32_t*>(&p.ptiles[t]) + lane);
+        const long long mrow = static_cast<long long>(__shfl_sync(0xffffffffu, static_cast<int>(nx_tab), PT_ROW0)) + row;
+        nx_cap = mrow < p.n_word_rows ? __ldg(&p.row_cap[mrow]) : -1;
+        nx_above = (row > 0 && lane == 0 && mrow - 1 < p.n_word_rows) ? __ldg(&p.row_cap[mrow - 1]) : -1;
+        return;
+      }
       int mu, nt;
       tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt);
       const int mt = mu * CG + cta_rank;
@@ -325,15 +370,15 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
 
     int it = 0;
     for (int t = unit; t < total_tiles; t += n_units, ++it) {
-      int mu, nt;
-      tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt);
+      int mu = 0, nt = 0;
+      if constexpr (!LIST) tile_coord(t, n_munits, p.n_ntiles, p.n_block, mu, nt);
       const int mt = mu * CG + cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int buf = it & 1;
       const long long mrow = static_cast<long long>(mt) * BM + row;
       const int mycap = nx_cap;
-      if (lane < NTILE_WORDS) tab[lane] = nx_tab;
+      if (lane < (LIST ? PTILE_WORDS : NTILE_WORDS)) tab[lane] = nx_tab;
       if (mrsw) {
         // caption runs of this M tile: a row starts a run when its caption differs from the row above
         int above = __shfl_up_sync(0xffffffffu, mycap, 1);
@@ -346,9 +391,21 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
       __syncwarp();
       const int n_row0 = static_cast<int>(tab[0]);
       const int img0 = static_cast<int>(tab[1]);
-      const int nseg = __shfl_sync(0xffffffffu, static_cast<int>(tab[2]), 0);      // shfl => provably warp-uniform
-      const uint32_t clamp = tab[3];
-      const uint32_t mydesc = (tab[4 + (lane >> 1)] >> ((lane & 1) * 16)) & 0xffffu;  // descriptor of image `lane`
+      // shfl => provably warp-uniform
+      const int nseg = __shfl_sync(0xffffffffu, static_cast<int>(tab[LIST ? PT_NSEG : 2]), 0);
+      const uint32_t clamp = tab[LIST ? PT_CLAMP : 3];
+      uint32_t mydesc;                                                                // descriptor of image `lane`
+      int cap_lo = 0, cap_hi = 0x7fffffff, my_img = img0 + lane;
+      if constexpr (LIST) {
+        const int sl = lane & (ALAD_PTILE_SLOTS - 1);
+        const uint32_t w = (tab[PT_SLOT_W + (sl >> 2)] >> ((sl & 3) * 8)) & 0xffu;
+        mydesc = static_cast<uint32_t>(sl * p.slot_rows) | (w << 8);
+        cap_lo = static_cast<int>(tab[PT_CAP_LO]);
+        cap_hi = static_cast<int>(tab[PT_CAP_HI]);
+        my_img = static_cast<int>(tab[PT_SLOT_IMG + sl]);
+      } else {
+        mydesc = (tab[4 + (lane >> 1)] >> ((lane & 1) * 16)) & 0xffffu;
+      }
       // prefetch the next tile's metadata while this one is processed
       if (t + n_units < total_tiles) fetch_meta(t + n_units);
 
@@ -419,7 +476,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
         const float* Vcol = V + buf * (BM * V_STRIDE) + lane;
         const bool active = lane < nseg;
         const float floor_v = ((clamp >> lane) & 1u) ? 0.f : -INFINITY;   // masked slots take part in the max as 0
-        float* Sout = p.S + static_cast<long long>(img0 + lane) * p.ld_seg;
+        float* Sout = p.S + static_cast<long long>(my_img) * p.ld_seg;
         unsigned long long lo = runS[buf * EPI_WARPS + 0] | (static_cast<unsigned long long>(runS[buf * EPI_WARPS + 1]) << 32);
         unsigned long long hi = runS[buf * EPI_WARPS + 2] | (static_cast<unsigned long long>(runS[buf * EPI_WARPS + 3]) << 32);
         auto pop_start = [&]() -> int {                    // next run start (128 when exhausted)
@@ -441,7 +498,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
           const int end = pop_start();
           if ((ord & 3) == warp) {
             const int cap = caps[start];
-            if (cap >= 0 && active) {
+            if (cap >= cap_lo && cap < cap_hi && active) {
               float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
               int r = start;
               for (; r + 4 <= end; r += 4) {
@@ -451,7 +508,8 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
                 s3 += fmaxf(Vcol[(r + 3) * V_STRIDE], floor_v);
               }
               for (; r < end; ++r) s0 += fmaxf(Vcol[r * V_STRIDE], floor_v);
-              atomicAdd(Sout + cap * p.ld_row, (s0 + s1) + (s2 + s3));
+              if constexpr (LIST) Sout[cap * p.ld_row] = (s0 + s1) + (s2 + s3);   // every listed pair lives in ONE tile
+              else atomicAdd(Sout + cap * p.ld_row, (s0 + s1) + (s2 + s3));
             }
           }
           start = end;
@@ -549,7 +607,7 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   ALAD_REQUIRE((reinterpret_cast<uintptr_t>(a->words) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->regions) & 15) == 0,
                "alad_mrsw_scores_fwd: operands must be 16-byte aligned");
 
-  MrswParams p;
+  MrswParams p = {};
   p.row_cap = a->row_cap;
   p.ntiles = a->ntiles;
   p.S = a->S;
@@ -635,14 +693,71 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (cg == 2) {
-    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
     cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
-    ALAD_CUDA(cudaLaunchKernelEx(&cfg, mrsw_fwd_kernel<2>, map_w, map_r, p));
+    ALAD_CUDA(cudaLaunchKernelEx(&cfg, mrsw_fwd_kernel<2, false>, map_w, map_r, p));
   } else {
-    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
     cfg.dynamicSmemBytes = Cfg<1>::SMEM_BYTES;
-    ALAD_CUDA(cudaLaunchKernelEx(&cfg, mrsw_fwd_kernel<1>, map_w, map_r, p));
+    ALAD_CUDA(cudaLaunchKernelEx(&cfg, mrsw_fwd_kernel<1, false>, map_w, map_r, p));
   }
+  ALAD_CUDA(cudaGetLastError());
+  return ALAD_OK;
+}
+
+// Pair-list scoring (two-stage retrieval, stage 2): same mainloop and epilogue, tiles from a device table.
+extern "C" int alad_mrsw_scores_pairs(const alad_mrsw_pairs_args* a, void* stream) {
+  using namespace alad;
+  ALAD_REQUIRE(a != nullptr, "alad_mrsw_scores_pairs: NULL args");
+  const int out_cols = a->transpose_out ? a->Ni : a->Nc;
+  ALAD_REQUIRE(a->Ni >= 0 && a->Nc >= 0 && a->ldS >= out_cols, "alad_mrsw_scores_pairs: bad output");
+  ALAD_REQUIRE(a->Kp > 0 && a->Kp % BK == 0, "alad_mrsw_scores_pairs: Kp=%d must be a positive multiple of %d", a->Kp, BK);
+  ALAD_REQUIRE(a->n_word_rows >= 0 && a->n_region_rows >= 0 && a->n_word_rows < (1ll << 31) && a->n_region_rows < (1ll << 31),
+               "alad_mrsw_scores_pairs: bad row counts");
+  ALAD_REQUIRE(a->slot_rows >= BN / ALAD_PTILE_SLOTS && a->slot_rows <= BN,
+               "alad_mrsw_scores_pairs: slot_rows=%d outside [%d, %d]", a->slot_rows, BN / ALAD_PTILE_SLOTS, BN);
+  ALAD_REQUIRE(a->max_ptiles >= 0, "alad_mrsw_scores_pairs: bad max_ptiles");
+  if (a->max_ptiles == 0 || a->n_word_rows == 0 || a->n_region_rows == 0 || a->Ni == 0 || a->Nc == 0) return ALAD_OK;
+  ALAD_REQUIRE(a->words && a->regions && a->row_cap && a->ptiles && a->n_ptiles && a->S, "alad_mrsw_scores_pairs: NULL pointer");
+  ALAD_REQUIRE((reinterpret_cast<uintptr_t>(a->words) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->regions) & 15) == 0,
+               "alad_mrsw_scores_pairs: operands must be 16-byte aligned");
+  MrswParams p = {};
+  p.row_cap = a->row_cap;
+  p.S = a->S;
+  p.ld_seg = a->transpose_out ? 1 : a->ldS;
+  p.ld_row = a->transpose_out ? a->ldS : 1;
+  p.n_word_rows = a->n_word_rows;
+  p.n_region_rows = a->n_region_rows;
+  p.n_mtiles = 1;
+  p.n_ntiles = 1;
+  p.n_block = 1;
+  p.num_kb = a->Kp / BK;
+  p.epilogue = 0;
+  p.ptiles = a->ptiles;
+  p.n_ptiles = a->n_ptiles;
+  p.max_ptiles = a->max_ptiles;
+  p.slot_rows = a->slot_rows;
+  CUtensorMap map_w, map_r;
+  int rc = make_map(&map_w, a->words, a->n_word_rows, a->Kp, BM);
+  if (rc) return rc;
+  rc = make_map(&map_r, a->regions, a->n_region_rows, a->Kp, a->slot_rows);
+  if (rc) return rc;
+  int ctas = a->num_ctas > 0 ? a->num_ctas : sm_count();
+  if (ctas > a->max_ptiles) ctas = a->max_ptiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(THREADS);
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+  cfg.dynamicSmemBytes = Cfg<1>::SMEM_BYTES;
+  ALAD_CUDA(cudaLaunchKernelEx(&cfg, mrsw_fwd_kernel<1, true>, map_w, map_r, p));
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;
 }

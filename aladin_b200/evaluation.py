@@ -100,7 +100,7 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
         return _cache["res"]
     Ni = images.shape[0] // 5
     world, rank, group = (1, 0, None)
-    img_off = 0
+    img_off, bounds = 0, None
     if isinstance(images, DeviceContainer) and mode == "callback":
         raise TypeError("DeviceContainer galleries hold packed tokens only: pass sim_function=None or a closure over "
                         "aladin_b200.loss.AlignmentContrastiveLoss('MrSw')")
@@ -114,13 +114,13 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
         gal = retrieval.AlignmentGallery(images, captions, img_lens, cap_lens, n_images=Ni, img_start=0, img_step=5,
                                          precision=precision, world=world, rank=rank)
         S = gal.scores(group=group)
-        img_off = gal.lo
+        img_off, bounds = gal.lo, gal.bounds
     elif mode == "block":
         S = _block_scores(images, captions, img_lens, cap_lens, scorer)
     else:
         S = _callback_scores(images, captions, img_lens, cap_lens, sim_function, batches)
     k = min(50, Ni)
-    ri, t1, rt, tk = retrieval.rank_both_directions(S, Ni, img_off=img_off, n_images_total=Ni, k=k, group=group)
+    ri, t1, rt, tk = retrieval.rank_both_directions(S, Ni, img_off=img_off, n_images_total=Ni, k=k, group=group, bounds=bounds)
     res = dict(S=S, img_off=img_off, world=world, ranks_i2t=ri, top1=t1, ranks_t2i=rt, top50=tk)
     if key is not None:
         # the key holds addresses: a hit is valid only while the very same input objects are alive (a freed

@@ -6,10 +6,14 @@ Ni x Nc score block serves both directions, ranks come from "count ahead of the 
 truth" kernels instead of per-query numpy argsorts.
 
 Multi-GPU: gallery images are split into contiguous image blocks, captions are
-replicated.  i2t needs no exchange; t2i exchanges the ground-truth scores (all-reduce of
-Nc floats), the per-shard counts (all-reduce of Nc ints) and the per-shard top-k candidates
-(all-gather of k (score, index) pairs per caption) through torch.distributed / NCCL.
-"""
+replicated.  i2t needs no exchange.  t2i exchanges, through torch.distributed / NCCL, ONE all-gather that
+carries the ground-truth scores, the per-shard top-k candidates and the i2t results of every image block
+(the ranks meet here once per step), followed by a 100 KB all-reduce of the per-shard "images ahead" counts.
+The image blocks are sized by the measured speed of every GPU (``ShardBalancer``): under the 1 kW power cap
+the B200s of one box differ by several percent in sustained clock, and equal blocks leave the fast ones
+waiting in the collective."""
+import collections
+
 import numpy as np
 import torch
 
@@ -18,10 +22,93 @@ from .tiling import build_region_tiles
 
 
 def shard_bounds(n, world, rank):
-    """Contiguous image block of `rank`: [lo, hi)."""
+    """Contiguous image block of `rank` for equal blocks: [lo, hi)."""
     per = (n + world - 1) // world
     lo = min(n, rank * per)
     return lo, min(n, lo + per)
+
+
+class ShardBalancer:
+    """Image-block bounds proportional to the measured speed of every rank.
+
+    Every step each rank times its own scoring launches (CUDA events) and ships (images scored, milliseconds) of its
+    PREVIOUS step inside the ranking exchange; all ranks apply the same update to the same gathered numbers, so the
+    bounds stay identical everywhere without an extra collective.  Results do not depend on the partition."""
+    SMOOTH = 0.5          # weight of a new measurement
+    CLAMP = (0.75, 1.3)   # relative speed is kept inside this band
+
+    def __init__(self):
+        self.speed = {}            # world -> float64 [world], mean 1
+
+    def all_bounds(self, n, world):
+        sp = self.speed.get(world)
+        if sp is None or n < 8 * world:
+            return [shard_bounds(n, world, r) for r in range(world)]
+        cum = np.cumsum(sp) / float(np.sum(sp))
+        edges = [0] + [int(round(n * c)) for c in cum[:-1]] + [n]
+        edges = np.maximum.accumulate(np.clip(edges, 0, n))
+        return [(int(edges[r]), int(edges[r + 1])) for r in range(world)]
+
+    def bounds(self, n, world, rank):
+        return self.all_bounds(n, world)[rank]
+
+    def update(self, world, images, ms):
+        """images / ms: per-rank work and time of one earlier step (entries with ms <= 0 carry no measurement)."""
+        images, ms = np.asarray(images, np.float64), np.asarray(ms, np.float64)
+        if len(images) != world or np.any(ms <= 0) or np.any(images <= 0):
+            return
+        rate = images / ms
+        rate = rate / rate.mean()
+        old = self.speed.get(world)
+        new = rate if old is None else (1 - self.SMOOTH) * old + self.SMOOTH * rate
+        new = np.clip(new, *self.CLAMP)
+        self.speed[world] = new / new.mean()
+
+    def reset(self):
+        self.speed.clear()
+
+
+balancer = ShardBalancer()
+# this rank's last completed scoring pass: (images scored, [(start_event, end_event), ...]); read one step later
+_last_timing = {"n": 0, "events": []}
+
+
+def _take_timing():
+    """(images, ms) of this rank's previous scoring pass, (0, 0) when there is none; consumes it."""
+    n, ev = _last_timing["n"], _last_timing["events"]
+    _last_timing["n"], _last_timing["events"] = 0, []
+    if not n or not ev:
+        return 0.0, 0.0
+    try:
+        return float(n), float(sum(a.elapsed_time(b) for a, b in ev))
+    except RuntimeError:            # events not complete (no synchronisation since): no measurement
+        return 0.0, 0.0
+
+
+# Derived host arrays of a gallery (valid counts, clamp flags) are a function of the python length lists the
+# reference passes around (25 000 entries at COCO-5k: ~1 ms of list -> numpy conversion per call); memoised by content.
+_META = collections.OrderedDict()
+
+
+def _gallery_meta(img_shape1, cap_shape, img_lens, cap_lens, Ni, img_start, img_step):
+    if isinstance(img_lens, np.ndarray):
+        img_lens = img_lens.tolist()
+    if isinstance(cap_lens, np.ndarray):
+        cap_lens = cap_lens.tolist()
+    key = (len(img_lens), hash(tuple(img_lens)), len(cap_lens), hash(tuple(cap_lens)), img_shape1, tuple(cap_shape), Ni,
+           img_start, img_step)
+    hit = _META.get(key)
+    if hit is not None:
+        _META.move_to_end(key)
+        return hit
+    img_lens_g = img_lens[img_start:img_start + (Ni - 1) * img_step + 1:img_step] if Ni else []
+    if len(img_lens_g) != Ni:
+        raise ValueError("length lists do not match the batch sizes")
+    val = scoring.scored_counts((Ni, img_shape1), cap_shape, img_lens_g, cap_lens)
+    _META[key] = val
+    if len(_META) > 8:
+        _META.popitem(last=False)
+    return val
 
 
 def _upload_rows(x, row_start, row_step, n_rows, n_slots, out=None):
@@ -52,7 +139,7 @@ class AlignmentGallery:
     i2t reads row 5i, t2i rows 0::5 -- alad/evaluation.py:178,252)."""
 
     def __init__(self, images, captions, img_lens, cap_lens, n_images, img_start=0, img_step=1,
-                 precision=None, world=1, rank=0, caption_chunk=4096, caption_phases=4):
+                 precision=None, world=1, rank=0, caption_chunk=4096, caption_phases=None, bounds=None):
         if not torch.cuda.is_available():
             raise _cabi.AladError("aladin_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         from .gallery import DeviceContainer
@@ -71,12 +158,49 @@ class AlignmentGallery:
         self.Ni, self.Nc = int(n_images), int(captions.shape[0])
         self.img_start, self.img_step = img_start, img_step
         self.world, self.rank = world, rank
-        self.lo, self.hi = shard_bounds(self.Ni, world, rank)
+        # image blocks of all ranks: equal blocks for a single rank, speed-weighted ones otherwise (ShardBalancer)
+        self.bounds = bounds if bounds is not None else balancer.all_bounds(self.Ni, world)
+        self.lo, self.hi = self.bounds[rank]
         self.caption_chunk = caption_chunk
-        self.caption_phases = max(1, caption_phases)
-        img_lens_g = [img_lens[img_start + i * img_step] for i in range(self.Ni)]
-        self.R, self.W, self.nr, self.nw, self.clamp = scoring.scored_counts(
-            (self.Ni, images.shape[1]), captions.shape, img_lens_g, cap_lens)
+        self.caption_phases = caption_phases          # None: ramped phases (see _phase_bounds)
+        self.R, self.W, self.nr, self.nw, self.clamp = _gallery_meta(
+            images.shape[1], tuple(captions.shape), img_lens, cap_lens, self.Ni, img_start, img_step)
+        self._events = []
+
+    def _score(self, words, regions, tiles_dev, n_tiles, n_loc, n_caps, out):
+        """One scoring launch, bracketed by events for the shard balancer."""
+        if self.world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        scoring.mrsw_scores_packed(words, regions, tiles_dev, n_tiles, n_loc, n_caps, out=out)
+        if self.world > 1:
+            e1.record()
+            self._events.append((e0, e1))
+
+    def _done(self, n_loc):
+        if self.world > 1:
+            _last_timing["n"], _last_timing["events"] = n_loc, self._events
+            self._events = []
+
+    def _phase_bounds(self):
+        """Caption-column phases of the host-resident multi-rank path: the upload + pack + all-gather of phase p+1
+        hides behind the scoring of phase p, so only phase 0 is exposed -- it is small (Nc/64) and the phases grow
+        by 1.5x (the ratio of scoring time to PCIe time per caption on a B200 box) up to Nc/4."""
+        Nc = self.Nc
+        if self.caption_phases is not None:
+            P = max(1, self.caption_phases if Nc >= self.caption_phases * self.world * 64 else 1)
+            return [(p * Nc // P, (p + 1) * Nc // P) for p in range(P)]
+        if Nc < 64 * self.world * 16:
+            return [(0, Nc)]
+        out, c0, size = [], 0, max(Nc // 64, 64 * self.world)
+        while c0 < Nc:
+            c1 = min(Nc, c0 + int(size))
+            if Nc - c1 < size // 2:
+                c1 = Nc
+            out.append((c0, c1))
+            c0 = c1
+            size = min(size * 1.5, max(Nc // 4, 1))
+        return out
 
     def _pack_caption_range(self, c_lo, c_hi, words_buf, cap_buf, row_base, split, dev, item_origin=0):
         """Upload (if on the host) and pack captions [c_lo, c_hi) into rows row_base.. of
@@ -114,6 +238,36 @@ class AlignmentGallery:
                 freed[bsel].record(main)
         return rows
 
+    def packed_operands(self):
+        """Device-resident packed operands of this shard: (words Packed over ALL captions incl. row_item,
+        regions Packed over the image block, first packed region row of every local image [int64 numpy]).
+        Used by the pair-list (two-stage) path, which scores many small tiles from the same operands."""
+        from .tiling import exclusive_cumsum, padded_rows
+        split = self.precision == "fp32"
+        lo, hi = self.lo, self.hi
+        n_loc = hi - lo
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nr = self.nr[lo:hi]
+        row_off, _ = exclusive_cumsum(nr)
+        if self.prepacked:
+            regions, nr_loc = self.images.rows_of(lo, hi)
+            assert np.array_equal(nr_loc, nr)
+            return self.captions.packed, regions, row_off
+        d = self.captions.shape[2]
+        Kp = ((d * (3 if split else 1) + _cabi.TILE_K - 1) // _cabi.TILE_K) * _cabi.TILE_K
+        regions = None
+        if n_loc:
+            Lr = 1 + int(nr.max())
+            im_dev = _upload_rows(self.images, self.img_start + lo * self.img_step, self.img_step, n_loc, Lr)
+            regions = scoring.pack_tokens(im_dev, nr, slot0=1, mode=2 if split else 0)
+        n_rows = int(self.nw.sum())
+        words_buf = torch.empty((max(n_rows, 1), Kp), dtype=torch.bfloat16, device=dev)
+        cap_buf = torch.full((max(padded_rows(n_rows), 2 * _cabi.TILE_M),), -1, dtype=torch.int32, device=dev)
+        if self.Nc:
+            self._pack_caption_range(0, self.Nc, words_buf, cap_buf, 0, split, dev)
+        words = scoring.Packed(words_buf, n_rows, Kp, self.nw, None, cap_buf, 1 if split else 0)
+        return words, regions, row_off
+
     def scores(self, group=None):
         """S[hi-lo, Nc] fp32 on the device for this shard's image block.
 
@@ -134,7 +288,9 @@ class AlignmentGallery:
             assert np.array_equal(nr_loc, self.nr[lo:hi]) and np.array_equal(self.captions.counts, self.nw)
             _, table, _ = build_region_tiles(nr_loc, self.clamp[lo:hi])
             tiles_dev = scoring._to_dev(table.view(np.int32).reshape(-1), dev) if len(table) else None
-            return scoring.mrsw_scores_packed(self.captions.packed, regions, tiles_dev, len(table), n_loc, self.Nc, out=S)
+            self._score(self.captions.packed, regions, tiles_dev, len(table), n_loc, self.Nc, S)
+            self._done(n_loc)
+            return S
         shard_caps = (group is not None and self.world > 1 and not self.captions.is_cuda and dist.is_initialized())
         if (n_loc == 0 and not shard_caps) or self.Nc == 0:
             return S
@@ -156,8 +312,7 @@ class AlignmentGallery:
             # captions are processed in phases; inside a phase every rank uploads + packs its 1/world
             # share, the packed rows are all-gathered (NVLink) and the phase is scored while the next
             # phase is being prepared on a side stream
-            P = self.caption_phases if self.Nc >= self.caption_phases * self.world * 64 else 1
-            pb = [(p * self.Nc // P, (p + 1) * self.Nc // P) for p in range(P)]
+            pb = self._phase_bounds()
             plans = []
             for c0, c1 in pb:
                 spans = [tuple(c0 + x for x in shard_bounds(c1 - c0, self.world, r)) for r in range(self.world)]
@@ -189,9 +344,10 @@ class AlignmentGallery:
                 main.wait_event(ready)
                 if n_loc:
                     words = scoring.Packed(wa, self.world * pad, Kp, None, None, ca, 1 if split else 0)
-                    scoring.mrsw_scores_packed(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, out=S[:, c0:c1])
+                    self._score(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, S[:, c0:c1])
                 freed[b] = torch.cuda.Event()
                 freed[b].record(main)
+            self._done(n_loc)
             return S
         else:
             # one rank owns all captions: score chunk k while chunk k+1 is uploaded (host sources)
@@ -224,20 +380,22 @@ class AlignmentGallery:
                 else:
                     cap_dev = self.captions[c0:c1]
                 words = scoring.pack_tokens(cap_dev, nw[c0:c1], slot0=1, mode=1 if split else 0, want_row_item=True)
-                scoring.mrsw_scores_packed(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, out=S[:, c0:c1])
+                self._score(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, S[:, c0:c1])
                 if on_cpu:
                     freed[bsel] = torch.cuda.Event()
                     freed[bsel].record(main)
+            self._done(n_loc)
             return S
 
 
-def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=None, gather_i2t=True, ops=ranking):
-    """Exact i2t / t2i ranks and top-k from a shard's score block S[n_loc, Nc].
+def rank_device(S, npts, img_off=0, n_images_total=None, k=50, group=None, ops=ranking, bounds=None):
+    """Exact i2t / t2i ranks and top-k from a shard's score block S[n_loc, Nc], as DEVICE tensors:
+    (rank_i2t[npts] int32, top1[npts] int32, rank_t2i[ncq] int32, topk_score[ncq, k], topk_idx[ncq, k] int32,
+    timing [world, 2] float32 or None: every rank's (images, ms) of its previous scoring pass).
 
-    Returns numpy arrays shaped like the reference's (alad/evaluation.py:166-167,255-256):
-    ranks_i2t[npts], top1[npts], ranks_t2i[5*npts], topk[5*npts, k] (float64).
-    `ops` provides rank_rows / col_gt / col_count / col_topk / topk_merge (the CUDA kernels by
-    default; the gloo CPU tests plug the oracle in to exercise the exchange protocol)."""
+    `ops` provides rank_rows / col_gt / col_count / col_topk / topk_merge (the CUDA kernels by default; the gloo
+    CPU tests plug the oracle in to exercise the exchange protocol).  `bounds` = image blocks [(lo, hi)] of all
+    ranks (default: equal blocks)."""
     import torch.distributed as dist
     n_loc, Nc = S.shape
     dist_on = group is not None and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -251,33 +409,57 @@ def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=No
     Sq = S[:, :ncq]
     gt = torch.zeros(ncq, dtype=torch.float32, device=S.device)
     ops.col_gt(Sq, gt, 5, img_off)
-    if dist_on:
-        dist.all_reduce(gt, group=group)                       # every entry is owned by exactly one shard
-    count = ops.col_count(Sq, gt, 5, img_off)
     cs, ci = ops.col_topk(Sq, k, img_off)
     ts, ti = ops.topk_merge(cs, ci)
-    if dist_on:
-        world = dist.get_world_size(group)
-        # per-shard k-best lists -> every rank, then one merge of `world` sorted lists per caption
-        gs = torch.empty((world * ts.shape[0], ts.shape[1]), dtype=ts.dtype, device=S.device)
-        gi = torch.empty((world * ti.shape[0], ti.shape[1]), dtype=ti.dtype, device=S.device)
-        dist.all_gather_into_tensor(gs, ts.contiguous(), group=group)       # output = concatenation along dim 0
-        dist.all_gather_into_tensor(gi, ti.contiguous(), group=group)
-        ts, ti = ops.topk_merge(gs.view(world, *ts.shape), gi.view(world, *ti.shape))
-        # counts (summed over the shards) and the i2t results of every image block in one small gather
-        per = (Ni_total + world - 1) // world
-        small = torch.full((ncq + 2 * per,), -1, dtype=torch.int32, device=S.device)
-        small[:ncq] = count
-        small[ncq:ncq + q_loc] = rank_i
-        small[ncq + per:ncq + per + q_loc] = top1_i
-        gsm = torch.empty((world * (ncq + 2 * per),), dtype=torch.int32, device=S.device)
-        dist.all_gather_into_tensor(gsm, small, group=group)
-        gsm = gsm.view(world, ncq + 2 * per)
-        count = gsm[:, :ncq].sum(dim=0, dtype=torch.int32)
-        if gather_i2t:
-            rank_i = gsm[:, ncq:ncq + per].reshape(-1)[:npts]
-            top1_i = gsm[:, ncq + per:].reshape(-1)[:npts]
-    return _to_host_f64(rank_i, top1_i, count, ti)
+    if not dist_on:
+        count = ops.col_count(Sq, gt, 5, img_off)
+        return rank_i, top1_i, count, ts, ti, None
+    world = dist.get_world_size(group)
+    if bounds is None:
+        bounds = [shard_bounds(Ni_total, world, r) for r in range(world)]
+    per = max(hi - lo for lo, hi in bounds)
+    # ONE all-gather: ground-truth scores (every entry is owned by exactly one shard, 0 elsewhere), the shard's
+    # k best (score, image) per caption, its i2t results, and the (images, ms) of its previous scoring pass
+    t_n, t_ms = _take_timing()
+    tail = torch.full((2 * per + 2,), -1, dtype=torch.int32, device=S.device)
+    tail[:q_loc] = rank_i
+    tail[per:per + q_loc] = top1_i
+    tail[2 * per:] = torch.tensor([t_n, t_ms], dtype=torch.float32).view(torch.int32).to(S.device, non_blocking=True)
+    ts_c, ti_c = ts.contiguous(), ti.contiguous()
+    payload = torch.cat([gt.view(torch.int32), ts_c.view(torch.int32).reshape(-1), ti_c.reshape(-1), tail])
+    n_pay = payload.numel()
+    gathered = torch.empty((world * n_pay,), dtype=torch.int32, device=S.device)
+    dist.all_gather_into_tensor(gathered, payload, group=group)
+    gathered = gathered.view(world, n_pay)
+    o = 0
+    gt = gathered[:, o:o + ncq].view(torch.float32).sum(dim=0)
+    o += ncq
+    gs = gathered[:, o:o + ncq * k].view(torch.float32).reshape(world, ncq, k)
+    o += ncq * k
+    gi = gathered[:, o:o + ncq * k].reshape(world, ncq, k)
+    o += ncq * k
+    ts, ti = ops.topk_merge(gs.contiguous(), gi.contiguous())
+    g_tail = gathered[:, o:]
+    rank_i = torch.cat([g_tail[r, :bounds[r][1] - bounds[r][0]] for r in range(world)])[:npts]
+    top1_i = torch.cat([g_tail[r, per:per + bounds[r][1] - bounds[r][0]] for r in range(world)])[:npts]
+    # images ahead of the ground truth: local count against the global gt, summed over the shards
+    count = ops.col_count(Sq, gt, 5, img_off)
+    dist.all_reduce(count, group=group)
+    # the gathered (images, ms) pairs update the shard balancer identically on every rank (read with the results)
+    return rank_i, top1_i, count, ts, ti, g_tail[:, 2 * per:2 * per + 2].view(torch.float32)
+
+
+def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=None, gather_i2t=True, ops=ranking,
+                         bounds=None):
+    """rank_device + ONE device->host copy.  Returns numpy arrays shaped like the reference's
+    (alad/evaluation.py:166-167,255-256): ranks_i2t[npts], top1[npts], ranks_t2i[5*npts], topk[5*npts, k] (float64)."""
+    rank_i, top1_i, count, _, ti, timing = rank_device(S, npts, img_off, n_images_total, k, group, ops, bounds)
+    if timing is None:
+        return _to_host_f64(rank_i, top1_i, count, ti)
+    out = _to_host_f64(rank_i, top1_i, count, ti, timing.reshape(-1))
+    tm = out[4].reshape(-1, 2)
+    balancer.update(tm.shape[0], tm[:, 0], tm[:, 1])
+    return out[:4]
 
 
 def _to_host_f64(*tensors):

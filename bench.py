@@ -242,7 +242,8 @@ def main():
         gal = retrieval.AlignmentGallery(images, captions, im_len, s_len, n_images=Ni, precision=args.precision,
                                          world=world, rank=rank)
         S = gal.scores()
-        result["out"] = retrieval.rank_both_directions(S, Ni, img_off=gal.lo, n_images_total=Ni, k=50, group=group)
+        result["out"] = retrieval.rank_both_directions(S, Ni, img_off=gal.lo, n_images_total=Ni, k=50, group=group,
+                                                       bounds=gal.bounds)
 
     ms_step, timeline, launches, clocks = timed(step_resident, args.steps, args.warmup)
     value = Ni * Nc / (ms_step * 1e-3)

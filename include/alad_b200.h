@@ -382,6 +382,99 @@ int alad_col_topk_select(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, in
 int alad_topk_merge(const float* cand_score, const int32_t* cand_idx, int32_t P, int32_t Nc, int32_t k,
                     float* out_score, int32_t* out_idx, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Pair-list scoring (BASELINE config 5, stage 2 of two-stage retrieval): MrSw scores of a SPARSE set of
+ * (image, caption) pairs on the same tcgen05 mainloop as alad_mrsw_scores_fwd.  The reference pieces composed are
+ * the matching-head shortlist of alad/recall_auxiliary.py:30 and the alignment scores of alad/loss.py:97-125.
+ *
+ * A "pair tile" is 128 packed word rows starting at the first row of caption cap_lo (captions cap_lo .. cap_hi-1
+ * lie completely inside it; rows of later captions are ignored) times up to ALAD_PTILE_SLOTS image SLOTS of
+ * slot_rows packed region rows each: slot s is loaded by its own TMA box from packed region row slot_row[s], so the
+ * images of a tile need not be neighbours in the gallery.  Every listed (image, caption) pair is produced by exactly
+ * one tile and written with a plain store to S[slot_img, caption]; S is NOT zeroed and entries of unlisted pairs are
+ * left untouched.
+ *
+ * alad_pairtile_build (device-side bookkeeping, no host sync): the image set of a tile group = union over its
+ * captions of their t2i shortlist (lists_t2i[c, :], GLOBAL image ids, -1 = empty; ids outside
+ * [img_off, img_off + n_loc) are another shard's) and of the local images that shortlist the caption
+ * (lists_i2t[i, :], caption ids).  The union is a bitmap per group (workspace), compacted in ascending image order
+ * into tiles of 240 / slot_rows slots; n_ptiles (DEVICE int32) receives the tile count, clipped to `capacity`
+ * (capacity >= (entries of both lists) / slots + n_groups always suffices).
+ * ------------------------------------------------------------------------------- */
+#define ALAD_PTILE_SLOTS 8
+typedef struct alad_ptile {      /* device table entry, 96 bytes                                             */
+  int32_t m_row0;                /* first packed word row of the tile                                        */
+  int32_t cap_lo, cap_hi;        /* captions (row_cap values) whose scores this tile emits                   */
+  int32_t nseg;                  /* image slots in use                                                       */
+  uint32_t clamp_bits;           /* bit s: slot s's image has masked region slots -> max starts at 0         */
+  int32_t slot_row[ALAD_PTILE_SLOTS];   /* first packed region row of slot s                                 */
+  int32_t slot_img[ALAD_PTILE_SLOTS];   /* LOCAL image index (row of S) of slot s                            */
+  uint8_t slot_w[ALAD_PTILE_SLOTS];     /* scored regions of slot s (<= slot_rows)                           */
+  int32_t reserved;
+} alad_ptile;
+
+typedef struct alad_pairtile_args {
+  int32_t n_groups;              /* caption groups = M tiles (host-built: consecutive captions, <= 128 word rows) */
+  const int32_t* group_row0;     /* [n_groups] first packed word row                                          */
+  const int32_t* group_cap_lo;   /* [n_groups + 1] first caption of every group (last entry = Nc)             */
+  const int32_t* cap_group;      /* [Nc] group of every caption                                               */
+  int32_t Nc;
+  const int32_t* lists_t2i;      /* [Nc, k_t2i] or NULL                                                       */
+  int32_t k_t2i;
+  const int32_t* lists_i2t;      /* [n_loc, k_i2t] or NULL                                                    */
+  int32_t k_i2t;
+  int32_t img_off, n_loc;        /* this shard's image block                                                  */
+  const int32_t* region_row;     /* [n_loc] first packed region row of every local image                      */
+  const int32_t* nr;             /* [n_loc] scored regions                                                    */
+  const uint8_t* clamp;          /* [n_loc] or NULL                                                           */
+  int32_t slot_rows;             /* >= max nr, <= 240                                                         */
+  alad_ptile* ptiles;            /* [capacity] out                                                            */
+  int32_t capacity;
+  int32_t* n_ptiles;             /* DEVICE scalar out                                                         */
+  void* workspace;
+  int64_t workspace_bytes;       /* >= alad_pairtile_workspace_bytes(n_groups, n_loc)                         */
+} alad_pairtile_args;
+/* Host helper (HOST pointers, no CUDA work): greedy grouping of consecutive captions into M tiles of <= ALAD_TILE_M
+ * packed word rows.  group_row0 [>= Nc], group_cap_lo [>= Nc + 1] (n_groups + 1 entries are written), cap_group [Nc]
+ * (-1 for a caption without scored words).  Returns n_groups or a negative alad_status. */
+int alad_caption_groups(const int32_t* nw, int32_t Nc, int32_t* group_row0, int32_t* group_cap_lo, int32_t* cap_group);
+int64_t alad_pairtile_workspace_bytes(int32_t n_groups, int32_t n_loc);
+int alad_pairtile_build(const alad_pairtile_args* a, void* stream);
+
+typedef struct alad_mrsw_pairs_args {
+  const void* words;             /* [n_word_rows, Kp] bf16 packed (mode 0 or 1)                              */
+  int64_t n_word_rows;
+  const void* regions;           /* [n_region_rows, Kp] bf16 packed (mode 0 or 2)                            */
+  int64_t n_region_rows;
+  int32_t Kp;
+  const int32_t* row_cap;        /* [n_word_rows] caption of each packed word row                            */
+  const alad_ptile* ptiles;      /* device table                                                             */
+  const int32_t* n_ptiles;       /* DEVICE scalar: tiles in the table                                        */
+  int32_t max_ptiles;            /* host upper bound (sizes the grid)                                        */
+  int32_t slot_rows;
+  float* S;                      /* [Ni, ldS] (or [Nc, ldS] when transpose_out); not zeroed                   */
+  int64_t ldS;
+  int32_t Ni, Nc;
+  int32_t transpose_out;
+  int32_t num_ctas;              /* 0 = one persistent CTA per SM                                            */
+} alad_mrsw_pairs_args;
+int alad_mrsw_scores_pairs(const alad_mrsw_pairs_args* a, void* stream);
+
+/* Re-ranking of per-query candidate lists (stage 2 consumers).
+ * alad_gather_list_scores: out[q, k] = S entry of (query q, candidate ids[q, k]); by_column = 1: q is a caption
+ *   (column of S), ids are GLOBAL image ids -- candidates outside this shard's block [img_off, img_off + Ni) or with
+ *   no scored token on either side give 0, so the per-shard outputs add up (all-reduce) to the full list;
+ *   by_column = 0: q is a LOCAL image (row of S), ids are caption ids.
+ * alad_list_rerank: order[q, :] = candidate ids by (score desc, list position desc on exact ties, i.e.
+ *   numpy.argsort(scores)[::-1] of the shortlisted scores); rank[q] = position of the best
+ *   ground-truth candidate (ids gt_lo .. gt_lo + gt_n - 1 with gt_lo = (q + q_off) * gt_mul / gt_div) inside that
+ *   order, or fallback[q] when no ground-truth id is in the list (it keeps its stage-1 rank). */
+int alad_gather_list_scores(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, const int32_t* ids, int32_t Q, int32_t k,
+                            int32_t by_column, int32_t img_off, const int32_t* nr, const int32_t* nw, float* out,
+                            void* stream);
+int alad_list_rerank(const float* scores, const int32_t* ids, int32_t Q, int32_t k, int32_t q_off, int32_t gt_mul,
+                     int32_t gt_div, int32_t gt_n, const int32_t* fallback, int32_t* rank, int32_t* order, void* stream);
+
 /* Two-stage retrieval (BASELINE config 5; not in the reference): S2 = -inf everywhere except the
  * shortlisted (image, caption) pairs, which keep their alignment score.  idx is [n_lists, k];
  * by_column = 1: list q belongs to caption q and holds GLOBAL image indices (t2i shortlist),

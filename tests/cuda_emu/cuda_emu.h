@@ -174,6 +174,23 @@ inline int atomicMax(int* p, int v) {
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
   return old;
 }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+  using namespace cuda_emu;
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  cta->xchg[tid] = raw;
+  warp_barrier();
+  const int src = (tid & 31) - (int)delta;
+  if (src >= 0) raw = cta->xchg[(tid & ~31) | src];
+  warp_barrier();
+  T out;
+  memcpy(&out, &raw, sizeof(T));
+  return out;
+}
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline float atomicAdd(float* addr, float v) {

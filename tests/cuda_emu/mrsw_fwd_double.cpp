@@ -71,3 +71,45 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void*) {
   }
   return ALAD_OK;
 }
+
+// CPU double of alad_mrsw_scores_pairs: the contract of the pair-list entry point (include/alad_b200.h) -- every tile
+// scores captions cap_lo .. cap_hi-1 (rows from m_row0, 128 at most) against its image slots and stores
+// S[slot_img, caption]; rows of other captions and unlisted pairs are left untouched.
+extern "C" int alad_mrsw_scores_pairs(const alad_mrsw_pairs_args* a, void*) {
+  using namespace alad;
+  ALAD_REQUIRE(a != nullptr, "alad_mrsw_scores_pairs: NULL args");
+  ALAD_REQUIRE(a->slot_rows >= ALAD_TILE_N / ALAD_PTILE_SLOTS && a->slot_rows <= ALAD_TILE_N, "alad_mrsw_scores_pairs: bad slot_rows");
+  if (a->max_ptiles == 0 || a->n_word_rows == 0 || a->n_region_rows == 0 || a->Ni == 0 || a->Nc == 0) return ALAD_OK;
+  ALAD_REQUIRE(a->words && a->regions && a->row_cap && a->ptiles && a->n_ptiles && a->S, "alad_mrsw_scores_pairs: NULL pointer");
+  const uint16_t* words = static_cast<const uint16_t*>(a->words);
+  const uint16_t* regions = static_cast<const uint16_t*>(a->regions);
+  const long long ld_seg = a->transpose_out ? 1 : a->ldS, ld_row = a->transpose_out ? a->ldS : 1;
+  const int n_t = *a->n_ptiles < a->max_ptiles ? *a->n_ptiles : a->max_ptiles;
+  for (int t = 0; t < n_t; ++t) {
+    const alad_ptile& pt = a->ptiles[t];
+    ALAD_REQUIRE(pt.nseg >= 0 && pt.nseg <= ALAD_TILE_N / a->slot_rows, "alad_mrsw_scores_pairs: bad tile table");
+    for (int s = 0; s < pt.nseg; ++s) {
+      const int width = pt.slot_w[s];
+      if (width == 0) continue;
+      const bool clamp = (pt.clamp_bits >> s) & 1u;
+      float* Sout = a->S + (long long)pt.slot_img[s] * ld_seg;
+      int cur = -1;
+      float sum = 0.f;
+      for (int r = 0; r <= ALAD_TILE_M; ++r) {
+        const long long m = (long long)pt.m_row0 + r;
+        const int cap = (r < ALAD_TILE_M && m < a->n_word_rows) ? a->row_cap[m] : -2;
+        if (cap != cur) {
+          if (cur >= pt.cap_lo && cur < pt.cap_hi) Sout[cur * ld_row] = sum;
+          cur = cap;
+          sum = 0.f;
+        }
+        if (cap < 0) continue;
+        float best = clamp ? 0.f : -INFINITY;
+        for (int c = 0; c < width; ++c)
+          best = fmaxf(best, dot_rows(regions + (long long)(pt.slot_row[s] + c) * a->Kp, words + m * a->Kp, a->Kp));
+        sum += best;
+      }
+    }
+  }
+  return ALAD_OK;
+}

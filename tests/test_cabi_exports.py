@@ -56,4 +56,4 @@ def test_scoring_kernel_resources(built_lib):
             assert stack == 0 and local == 0, f"spills in {line.strip()}"
             assert reg <= 168, f"{reg} registers in {line.strip()}"     # 135-136 today; a jump = different code generation
             seen += 1
-    assert seen == 2                                     # the single-CTA and the CTA-pair variants
+    assert seen == 3                                     # single-CTA, CTA-pair and the pair-list (two-stage) variants

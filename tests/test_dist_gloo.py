@@ -1,6 +1,6 @@
 """CPU, world_size 2, gloo: the multi-GPU exchange protocol of the sharded retrieval
-(retrieval.rank_both_directions: gt all-reduce, count all-reduce, candidate all-gather + merge,
-i2t gather) gives the single-shard answer.  The per-shard ranking ops are supplied by the
+(retrieval.rank_both_directions: ONE all-gather of ground-truth scores + top-k candidates + i2t results + shard
+timings, merge, count all-reduce) gives the single-shard answer, with equal and with speed-weighted image blocks.  The per-shard ranking ops are supplied by the
 oracle here (tests may use it); on the GPU box the same protocol runs over NCCL with the CUDA ops."""
 import os
 import socket
@@ -79,8 +79,14 @@ def _worker(rank, world, port, S_full, out):
         lo, hi = retrieval.shard_bounds(Ni, world, rank)
         res = retrieval.rank_both_directions(S_full[lo:hi].clone(), Ni, img_off=lo, n_images_total=Ni, k=50,
                                              group=dist.group.WORLD, ops=OracleOps)
+        # speed-weighted blocks: rank 1 measured 1.5x faster -> all ranks derive the same uneven bounds
+        retrieval.balancer.update(world, [30, 31], [3.0, 2.0])
+        bounds = retrieval.balancer.all_bounds(Ni, world)
+        lo, hi = bounds[rank]
+        res2 = retrieval.rank_both_directions(S_full[lo:hi].clone(), Ni, img_off=lo, n_images_total=Ni, k=50,
+                                              group=dist.group.WORLD, ops=OracleOps, bounds=bounds)
         if rank == 0:
-            out.put([np.asarray(r) for r in res])
+            out.put([np.asarray(r) for r in res] + [np.asarray(r) for r in res2] + [np.asarray(bounds)])
     finally:
         dist.destroy_process_group()
 
@@ -103,7 +109,8 @@ def test_sharded_ranking_protocol_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(rk, 2, port, S_t, out)) for rk in range(2)]
     for p in procs:
         p.start()
-    ranks_i2t, top1, ranks_t2i, top50 = out.get(timeout=120)
+    got = out.get(timeout=120)
+    ranks_i2t, top1, ranks_t2i, top50 = got[:4]
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -113,6 +120,27 @@ def test_sharded_ranking_protocol_world2_gloo():
     np.testing.assert_array_equal(top1, t1)
     np.testing.assert_array_equal(ranks_t2i, rt)
     np.testing.assert_array_equal(top50, t50)
+    bounds = got[8]
+    assert bounds[0][1] - bounds[0][0] < bounds[1][1] - bounds[1][0] and bounds[0][0] == 0 and bounds[1][1] == Ni
+    for a, b in zip(got[4:8], (ri, t1, rt, t50)):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_shard_balancer_tracks_measured_speed():
+    from aladin_b200 import retrieval
+    b = retrieval.ShardBalancer()
+    assert b.all_bounds(5000, 4) == [retrieval.shard_bounds(5000, 4, r) for r in range(4)]
+    for _ in range(6):                                   # rank 2 is 10 % slower than the others
+        spans = b.all_bounds(5000, 4)
+        n = [hi - lo for lo, hi in spans]
+        b.update(4, n, [n[0] / 1.0, n[1] / 1.0, n[2] / 0.9, n[3] / 1.0])
+    spans = b.all_bounds(5000, 4)
+    n = np.array([hi - lo for lo, hi in spans], np.float64)
+    t = n / np.array([1.0, 1.0, 0.9, 1.0])
+    assert spans[0][0] == 0 and spans[-1][1] == 5000 and all(a[1] == c[0] for a, c in zip(spans, spans[1:]))
+    assert t.max() / t.min() < 1.01                      # equal finishing times
+    b.update(4, n, [0, 1, 1, 1])                         # a step without a measurement changes nothing
+    assert b.all_bounds(5000, 4) == spans
 
 
 def test_shard_bounds_cover_everything():
