@@ -91,7 +91,8 @@ class PairtileArgs(C.Structure):
         ("n_groups", C.c_int32), ("group_row0", C.c_void_p), ("group_cap_lo", C.c_void_p), ("cap_group", C.c_void_p),
         ("Nc", C.c_int32), ("lists_t2i", C.c_void_p), ("k_t2i", C.c_int32), ("lists_i2t", C.c_void_p), ("k_i2t", C.c_int32),
         ("img_off", C.c_int32), ("n_loc", C.c_int32), ("region_row", C.c_void_p), ("nr", C.c_void_p), ("clamp", C.c_void_p),
-        ("slot_rows", C.c_int32), ("ptiles", C.c_void_p), ("capacity", C.c_int32), ("n_ptiles", C.c_void_p),
+        ("slot_rows", C.c_int32), ("block_images", C.c_int32), ("ptiles", C.c_void_p), ("capacity", C.c_int32),
+        ("n_ptiles", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
@@ -149,7 +150,7 @@ PROTOTYPES = {
     "alad_topk_merge": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "alad_shortlist_scatter": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P]),
     "alad_caption_groups": (C.c_int, [_P, _I32, _P, _P, _P]),
-    "alad_pairtile_workspace_bytes": (C.c_int64, [_I32, _I32]),
+    "alad_pairtile_workspace_bytes": (C.c_int64, [_I32, _I32, _I32]),
     "alad_pairtile_build": (C.c_int, [C.POINTER(PairtileArgs), _P]),
     "alad_mrsw_scores_pairs": (C.c_int, [C.POINTER(MrswPairsArgs), _P]),
     "alad_gather_list_scores": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),

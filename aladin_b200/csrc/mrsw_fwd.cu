@@ -189,15 +189,28 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
       uint32_t res_loads = 0;
       const uint64_t pol_words = (p.l2_hints & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
       const uint64_t pol_regions = (p.l2_hints & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
+      // pair-list mode: the record of the NEXT tile is fetched while the current one streams (a dependent global
+      // load at the head of every tile would drain the 4-stage ring)
+      int nx_row0 = 0, nx_nseg = 0, nx_srow[ALAD_PTILE_SLOTS] = {};
+      auto fetch_rec = [&](int t) {
+        const int32_t* rec = reinterpret_cast<const int32_t*>(&p.ptiles[t]);
+        nx_row0 = __ldg(rec + PT_ROW0);
+        nx_nseg = __ldg(rec + PT_NSEG);
+#pragma unroll
+        for (int s_i = 0; s_i < ALAD_PTILE_SLOTS; ++s_i) nx_srow[s_i] = __ldg(rec + PT_SLOT_ROW + s_i);
+      };
+      if constexpr (LIST) {
+        if (unit < total_tiles) fetch_rec(unit);
+      }
       for (int t = unit; t < total_tiles; t += n_units) {
         if constexpr (LIST) {
           // pair-list tile: 128 word rows from m_row0, one TMA box of slot_rows region rows per image slot
-          const int32_t* rec = reinterpret_cast<const int32_t*>(&p.ptiles[t]);
-          const int m_row0 = __ldg(rec + PT_ROW0);
-          const int nseg = __ldg(rec + PT_NSEG);
+          const int m_row0 = nx_row0;
+          const int nseg = nx_nseg;
           int srow[ALAD_PTILE_SLOTS];
 #pragma unroll
-          for (int s_i = 0; s_i < ALAD_PTILE_SLOTS; ++s_i) srow[s_i] = __ldg(rec + PT_SLOT_ROW + s_i);
+          for (int s_i = 0; s_i < ALAD_PTILE_SLOTS; ++s_i) srow[s_i] = nx_srow[s_i];
+          if (t + n_units < total_tiles) fetch_rec(t + n_units);
           const uint32_t slot_bytes = static_cast<uint32_t>(p.slot_rows) * (BK * 2);
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);

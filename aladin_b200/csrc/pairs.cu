@@ -43,17 +43,24 @@ pairtile_mark_i2t_kernel(const int32_t* __restrict__ lists, long long n_entries,
   atomicOr(bitmap + (long long)g * bw + (l >> 5), 1u << (l & 31));
 }
 
-// one warp per group: images in the union -> tiles of `slots` images
+// Image blocks: the local images are cut into blocks of block_words * 32 images whose packed region rows fit the L2
+// (a gathered slot is re-used by ~Nc*K/Ni caption groups; with the whole gallery in play every slot load would come
+// from HBM: 200 GB per call at COCO-5k).  Tiles are emitted block-major, so one launch sweeps block after block.
+// A "virtual group" v = block * n_groups + group owns the images of its group's union that fall into its block.
+// one warp per virtual group: images in the union -> tiles of `slots` images
 __global__ void __launch_bounds__(PT_THREADS)
-pairtile_count_kernel(const uint32_t* __restrict__ bitmap, int bw, int n_groups, int slots, int32_t* __restrict__ tiles_of) {
-  const int g = blockIdx.x * (PT_THREADS / 32) + (threadIdx.x >> 5);
+pairtile_count_kernel(const uint32_t* __restrict__ bitmap, int bw, int n_groups, int n_blocks, int block_words, int slots,
+                      int32_t* __restrict__ tiles_of) {
+  const int v = blockIdx.x * (PT_THREADS / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (g >= n_groups) return;
+  if (v >= n_groups * n_blocks) return;
+  const int b = v / n_groups, g = v - b * n_groups;
+  const int w_lo = b * block_words, w_hi = min(bw, w_lo + block_words);
   int n = 0;
-  for (int w = lane; w < bw; w += 32) n += __popc(__ldg(bitmap + (long long)g * bw + w));
+  for (int w = w_lo + lane; w < w_hi; w += 32) n += __popc(__ldg(bitmap + (long long)g * bw + w));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-  if (lane == 0) tiles_of[g] = (n + slots - 1) / slots;
+  if (lane == 0) tiles_of[v] = (n + slots - 1) / slots;
 }
 
 // single CTA: exclusive prefix sum of tiles_of -> tile_off[0 .. n_groups], n_ptiles = min(total, capacity)
@@ -86,18 +93,19 @@ pairtile_scan_kernel(const int32_t* __restrict__ tiles_of, int n_groups, int cap
   }
 }
 
-// one warp per group: compact the bitmap in ascending image order into the group's tile records
+// one warp per virtual group: compact its part of the bitmap in ascending image order into its tile records
 __global__ void __launch_bounds__(PT_THREADS)
-pairtile_emit_kernel(const uint32_t* __restrict__ bitmap, int bw, int n_groups, int slots, int slot_rows,
-                     const int32_t* __restrict__ tile_off, const int32_t* __restrict__ group_row0,
+pairtile_emit_kernel(const uint32_t* __restrict__ bitmap, int bw, int n_groups, int n_blocks, int block_words, int slots,
+                     int slot_rows, const int32_t* __restrict__ tile_off, const int32_t* __restrict__ group_row0,
                      const int32_t* __restrict__ group_cap_lo, const int32_t* __restrict__ region_row,
                      const int32_t* __restrict__ nr, const uint8_t* __restrict__ clamp, int capacity,
                      alad_ptile* __restrict__ ptiles) {
-  const int g = blockIdx.x * (PT_THREADS / 32) + (threadIdx.x >> 5);
+  const int v = blockIdx.x * (PT_THREADS / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (g >= n_groups) return;
-  const int t0 = tile_off[g];
-  const int n_t = min(tile_off[g + 1], capacity) - t0;
+  if (v >= n_groups * n_blocks) return;
+  const int b = v / n_groups, g = v - b * n_groups;
+  const int t0 = tile_off[v];
+  const int n_t = min(tile_off[v + 1], capacity) - t0;
   if (n_t <= 0) return;
   // headers (and zeroed slot fields) first; the slot writers below fill them in
   const int row0 = __ldg(group_row0 + g), cap_lo = __ldg(group_cap_lo + g), cap_hi = __ldg(group_cap_lo + g + 1);
@@ -116,10 +124,11 @@ pairtile_emit_kernel(const uint32_t* __restrict__ bitmap, int bw, int n_groups, 
     rec->reserved = 0;
   }
   __syncwarp();
+  const int w_lo = b * block_words, w_hi = min(bw, w_lo + block_words);
   int base = 0;
-  for (int w0 = 0; w0 < bw; w0 += 32) {
+  for (int w0 = w_lo; w0 < w_hi; w0 += 32) {
     const int w = w0 + lane;
-    uint32_t bits = w < bw ? __ldg(bitmap + (long long)g * bw + w) : 0u;
+    uint32_t bits = w < w_hi ? __ldg(bitmap + (long long)g * bw + w) : 0u;
     const int n = __popc(bits);
     int incl = n;
 #pragma unroll
@@ -129,17 +138,17 @@ pairtile_emit_kernel(const uint32_t* __restrict__ bitmap, int bw, int n_groups, 
     }
     int idx = base + incl - n;
     while (bits) {
-      const int b = __ffs((int)bits) - 1;
+      const int bit = __ffs((int)bits) - 1;
       bits &= bits - 1;
-      const int l = w * 32 + b;
-      const int t = idx / slots, s = idx - t * slots;
+      const int l = w * 32 + bit;
+      const int t = idx / slots, s_i = idx - t * slots;
       if (t < n_t) {
         alad_ptile* rec = ptiles + t0 + t;
-        rec->slot_row[s] = __ldg(region_row + l);
-        rec->slot_img[s] = l;
-        rec->slot_w[s] = (uint8_t)min(__ldg(nr + l), slot_rows);
-        if (clamp && __ldg(clamp + l)) atomicOr(&rec->clamp_bits, 1u << s);
-        atomicMax(&rec->nseg, s + 1);
+        rec->slot_row[s_i] = __ldg(region_row + l);
+        rec->slot_img[s_i] = l;
+        rec->slot_w[s_i] = (uint8_t)min(__ldg(nr + l), slot_rows);
+        if (clamp && __ldg(clamp + l)) atomicOr(&rec->clamp_bits, 1u << s_i);
+        atomicMax(&rec->nseg, s_i + 1);
       }
       ++idx;
     }
@@ -234,14 +243,19 @@ struct PairPlan {
   int bw;
   size_t off_bitmap, off_tiles_of, off_tile_off, bytes;
 };
-PairPlan pair_plan(int n_groups, int n_loc) {
+int pair_blocks(int n_loc, int block_images) {
+  if (block_images <= 0 || block_images >= n_loc) return 1;
+  return (n_loc + block_images - 1) / block_images;
+}
+PairPlan pair_plan(int n_groups, int n_loc, int block_images) {
   PairPlan p = {};
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   p.bw = (n_loc + 31) / 32;
+  const size_t n_v = (size_t)n_groups * pair_blocks(n_loc, block_images);
   size_t o = 0;
   p.off_bitmap = o;   o += up(sizeof(uint32_t) * (size_t)n_groups * (size_t)(p.bw > 0 ? p.bw : 1));
-  p.off_tiles_of = o; o += up(sizeof(int32_t) * ((size_t)n_groups + 1));
-  p.off_tile_off = o; o += up(sizeof(int32_t) * ((size_t)n_groups + 1));
+  p.off_tiles_of = o; o += up(sizeof(int32_t) * (n_v + 1));
+  p.off_tile_off = o; o += up(sizeof(int32_t) * (n_v + 1));
   p.bytes = o + 256;
   return p;
 }
@@ -249,9 +263,9 @@ PairPlan pair_plan(int n_groups, int n_loc) {
 }  // namespace
 }  // namespace alad
 
-extern "C" int64_t alad_pairtile_workspace_bytes(int32_t n_groups, int32_t n_loc) {
-  if (n_groups < 0 || n_loc < 0) return 0;
-  return (int64_t)alad::pair_plan(n_groups, n_loc).bytes;
+extern "C" int64_t alad_pairtile_workspace_bytes(int32_t n_groups, int32_t n_loc, int32_t block_images) {
+  if (n_groups < 0 || n_loc < 0 || block_images < 0 || block_images % 32 != 0) return 0;
+  return (int64_t)alad::pair_plan(n_groups, n_loc, block_images).bytes;
 }
 
 /* Host helper (HOST pointers, no CUDA work): consecutive captions are grouped greedily into M tiles of <= 128 packed
@@ -304,7 +318,12 @@ extern "C" int alad_pairtile_build(const alad_pairtile_args* a, void* stream) {
     ALAD_CUDA(cudaMemsetAsync(a->n_ptiles, 0, sizeof(int32_t), st));
     return ALAD_OK;
   }
-  const PairPlan pl = pair_plan(a->n_groups, a->n_loc);
+  ALAD_REQUIRE(a->block_images >= 0 && a->block_images % 32 == 0, "alad_pairtile_build: block_images must be a multiple of 32");
+  const PairPlan pl = pair_plan(a->n_groups, a->n_loc, a->block_images);
+  const int n_blocks = pair_blocks(a->n_loc, a->block_images);
+  const int block_words = n_blocks == 1 ? pl.bw : a->block_images / 32;
+  ALAD_REQUIRE((long long)a->n_groups * n_blocks < (1ll << 31), "alad_pairtile_build: too many (group, block) pairs");
+  const int n_v = a->n_groups * n_blocks;
   ALAD_REQUIRE(a->workspace && a->workspace_bytes >= (int64_t)pl.bytes && (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0,
                "alad_pairtile_build: workspace too small or misaligned");
   ALAD_REQUIRE(a->group_row0 && a->group_cap_lo && a->cap_group && a->region_row && a->nr && a->ptiles,
@@ -325,11 +344,12 @@ extern "C" int alad_pairtile_build(const alad_pairtile_args* a, void* stream) {
   if (n2)
     pairtile_mark_i2t_kernel<<<(unsigned)((n2 + PT_THREADS - 1) / PT_THREADS), PT_THREADS, 0, st>>>(
         a->lists_i2t, n2, a->k_i2t, a->cap_group, a->Nc, a->nr, pl.bw, bitmap);
-  const unsigned gblocks = (unsigned)((a->n_groups + PT_THREADS / 32 - 1) / (PT_THREADS / 32));
-  pairtile_count_kernel<<<gblocks, PT_THREADS, 0, st>>>(bitmap, pl.bw, a->n_groups, slots, tiles_of);
-  pairtile_scan_kernel<<<1, 1024, 0, st>>>(tiles_of, a->n_groups, a->capacity, tile_off, a->n_ptiles);
-  pairtile_emit_kernel<<<gblocks, PT_THREADS, 0, st>>>(bitmap, pl.bw, a->n_groups, slots, a->slot_rows, tile_off, a->group_row0,
-                                                      a->group_cap_lo, a->region_row, a->nr, a->clamp, a->capacity, a->ptiles);
+  const unsigned gblocks = (unsigned)((n_v + PT_THREADS / 32 - 1) / (PT_THREADS / 32));
+  pairtile_count_kernel<<<gblocks, PT_THREADS, 0, st>>>(bitmap, pl.bw, a->n_groups, n_blocks, block_words, slots, tiles_of);
+  pairtile_scan_kernel<<<1, 1024, 0, st>>>(tiles_of, n_v, a->capacity, tile_off, a->n_ptiles);
+  pairtile_emit_kernel<<<gblocks, PT_THREADS, 0, st>>>(bitmap, pl.bw, a->n_groups, n_blocks, block_words, slots, a->slot_rows,
+                                                      tile_off, a->group_row0, a->group_cap_lo, a->region_row, a->nr, a->clamp,
+                                                      a->capacity, a->ptiles);
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;
 }

@@ -20,11 +20,14 @@ import torch
 
 from . import _cabi, ranking, retrieval, scoring
 
-# Region rows per image slot = max scored regions of the shard, rounded up to SLOT_ALIGN.  8 keeps every slot on a
-# whole 1024-byte swizzle atom of the shared-memory operand tile (TMA's 128-byte swizzle is a function of the
-# shared-memory address, so an unaligned box start would also be consistent with the MMA descriptor; 8 is the
-# layout every other TMA load of the kernel uses).
-SLOT_ALIGN = 8
+# Region rows per image slot = max scored regions of the shard, rounded up to SLOT_ALIGN.  TMA's 128-byte swizzle is a
+# function of the shared-memory ADDRESS, so a slot box that starts between two 1024-byte swizzle atoms lands exactly
+# where the MMA descriptor of the whole operand tile expects its rows (checked on hardware for both settings,
+# tests/test_gpu_two_stage.py): no rounding, 7 slots of 34 rows per tile at COCO shape instead of 6 of 40.
+SLOT_ALIGN = 1
+# Packed region bytes per image block of the pair-list pass (see alad_pairtile_args.block_images): a gathered slot is
+# re-used by ~Nc*K/Ni caption groups, so the block being swept has to stay in the 126 MB L2 next to the streamed words.
+L2_BLOCK_BYTES = 48 << 20
 _GROUPS = {}
 
 
@@ -69,19 +72,27 @@ def pair_scores(words, regions, region_row_off, nr, clamp, nw, lists_t2i, lists_
     slots = _cabi.TILE_N // slot_rows
     k1 = lists_t2i.shape[1] if lists_t2i is not None else 0
     k2 = lists_i2t.shape[1] if lists_i2t is not None else 0
-    capacity = (Nc * k1 + n_loc * k2) // slots + n_g + 1
+    block = 0
+    row_bytes = words.Kp * 2
+    if regions.n_rows * row_bytes > L2_BLOCK_BYTES:
+        per_image = max(regions.n_rows / n_loc * row_bytes, 1.0)
+        block = max(32, int(L2_BLOCK_BYTES / per_image) // 32 * 32)
+        if block >= n_loc:
+            block = 0
+    n_blocks = 1 if block == 0 else (n_loc + block - 1) // block
+    capacity = (Nc * k1 + n_loc * k2) // slots + n_g * n_blocks + 1
     row0_d, cap_lo_d, cap_group_d, rr_d, nr_d, clamp_d = scoring._to_dev_group(
         [row0, cap_lo, cap_group, np.asarray(region_row_off, np.int32), np.asarray(nr, np.int32),
          np.asarray(clamp, np.uint8)], dev)
     ptiles = torch.empty((capacity, _cabi.PTILE_WORDS), dtype=torch.int32, device=dev)
     n_ptiles = torch.zeros(1, dtype=torch.int32, device=dev)
-    nbytes = int(lib.alad_pairtile_workspace_bytes(n_g, n_loc))
+    nbytes = int(lib.alad_pairtile_workspace_bytes(n_g, n_loc, block))
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
     a = _cabi.PairtileArgs(
         n_groups=n_g, group_row0=row0_d.data_ptr(), group_cap_lo=cap_lo_d.data_ptr(), cap_group=cap_group_d.data_ptr(), Nc=Nc,
         lists_t2i=lists_t2i.data_ptr() if k1 else None, k_t2i=k1, lists_i2t=lists_i2t.data_ptr() if k2 else None, k_i2t=k2,
         img_off=img_off, n_loc=n_loc, region_row=rr_d.data_ptr(), nr=nr_d.data_ptr(), clamp=clamp_d.data_ptr(),
-        slot_rows=slot_rows, ptiles=ptiles.data_ptr(), capacity=capacity, n_ptiles=n_ptiles.data_ptr(),
+        slot_rows=slot_rows, block_images=block, ptiles=ptiles.data_ptr(), capacity=capacity, n_ptiles=n_ptiles.data_ptr(),
         workspace=ws.data_ptr(), workspace_bytes=nbytes)
     _cabi.check(lib.alad_pairtile_build(C.byref(a), _cabi.stream_ptr()), "alad_pairtile_build")
     b = _cabi.MrswPairsArgs(

@@ -399,7 +399,7 @@ int alad_topk_merge(const float* cand_score, const int32_t* cand_idx, int32_t P,
  * [img_off, img_off + n_loc) are another shard's) and of the local images that shortlist the caption
  * (lists_i2t[i, :], caption ids).  The union is a bitmap per group (workspace), compacted in ascending image order
  * into tiles of 240 / slot_rows slots; n_ptiles (DEVICE int32) receives the tile count, clipped to `capacity`
- * (capacity >= (entries of both lists) / slots + n_groups always suffices).
+ * (capacity >= (entries of both lists) / slots + n_groups * n_blocks always suffices).
  * ------------------------------------------------------------------------------- */
 #define ALAD_PTILE_SLOTS 8
 typedef struct alad_ptile {      /* device table entry, 96 bytes                                             */
@@ -428,17 +428,20 @@ typedef struct alad_pairtile_args {
   const int32_t* nr;             /* [n_loc] scored regions                                                    */
   const uint8_t* clamp;          /* [n_loc] or NULL                                                           */
   int32_t slot_rows;             /* >= max nr, <= 240                                                         */
+  int32_t block_images;          /* 0 = one block; else a multiple of 32: the local images are processed in blocks
+                                    of this many (tiles are emitted block-major) so that a block's packed region
+                                    rows stay L2-resident while the caption groups stream past                */
   alad_ptile* ptiles;            /* [capacity] out                                                            */
   int32_t capacity;
   int32_t* n_ptiles;             /* DEVICE scalar out                                                         */
   void* workspace;
-  int64_t workspace_bytes;       /* >= alad_pairtile_workspace_bytes(n_groups, n_loc)                         */
+  int64_t workspace_bytes;       /* >= alad_pairtile_workspace_bytes(n_groups, n_loc, block_images)           */
 } alad_pairtile_args;
 /* Host helper (HOST pointers, no CUDA work): greedy grouping of consecutive captions into M tiles of <= ALAD_TILE_M
  * packed word rows.  group_row0 [>= Nc], group_cap_lo [>= Nc + 1] (n_groups + 1 entries are written), cap_group [Nc]
  * (-1 for a caption without scored words).  Returns n_groups or a negative alad_status. */
 int alad_caption_groups(const int32_t* nw, int32_t Nc, int32_t* group_row0, int32_t* group_cap_lo, int32_t* cap_group);
-int64_t alad_pairtile_workspace_bytes(int32_t n_groups, int32_t n_loc);
+int64_t alad_pairtile_workspace_bytes(int32_t n_groups, int32_t n_loc, int32_t block_images);
 int alad_pairtile_build(const alad_pairtile_args* a, void* stream);
 
 typedef struct alad_mrsw_pairs_args {

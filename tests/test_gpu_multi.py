@@ -18,3 +18,12 @@ def test_sharded_equals_unsharded_over_nccl():
            "--master-port", "29533", os.path.join(ROOT, "tools", "dist_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0 and "dist_check ok" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_two_stage_sharded_equals_unsharded_over_nccl():
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tools", "two_stage_dist_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "two_stage_dist_check ok" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

@@ -48,15 +48,16 @@ def test_two_stage_matches_oracle_composition(K):
     np.testing.assert_allclose(m_t2i, O.recall_metrics(et))
 
 
-@pytest.mark.parametrize("align", [8, 1])
+@pytest.mark.parametrize("align,l2_bytes", [(8, 48 << 20), (1, 48 << 20), (1, 1 << 18)])
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
-def test_pair_list_scores_equal_the_dense_pass(align, precision, monkeypatch):
+def test_pair_list_scores_equal_the_dense_pass(align, l2_bytes, precision, monkeypatch):
     """Stage 2 on its own: the pair-list kernel (gathered image slots, caption-aligned word tiles) must reproduce the
     dense kernel's scores on every listed pair -- ragged lengths, images without regions, captions without words,
     lists that reach into other shards' blocks (ignored) and empty entries.  align = 1 packs the slots without
-    rounding the slot height to the 8-row swizzle atom."""
+    rounding the slot height to the 8-row swizzle atom; the small L2 budget forces the block-major tile order."""
     from aladin_b200 import retrieval, synth, two_stage
     monkeypatch.setattr(two_stage, "SLOT_ALIGN", align)
+    monkeypatch.setattr(two_stage, "L2_BLOCK_BYTES", l2_bytes)      # 256 KB: the 250 local images go in blocks of 32
     Ni, d = 333, 192
     images, captions, il, cl = synth.eval_containers(47, Ni, 40, d, max_regions=36, max_words=38, alpha=0.3)
     for i in (3, 200):
@@ -90,7 +91,7 @@ def test_pair_list_scores_equal_the_dense_pass(align, precision, monkeypatch):
     assert np.abs(Sp[want] - Sd[want]).max() <= (2e-5 * max(np.abs(Sd).max(), 1.0))   # same operands, same MMA: only the fp32 sum order differs
     assert tol > 0
     slots = 240 // two_stage.slot_rows_for(nr)
-    assert 0 < int(n_tiles.item()) <= (want.sum() // slots) + len(nw)
+    assert 0 < int(n_tiles.item()) <= (want.sum() // slots) + len(nw) * (8 if l2_bytes < (1 << 20) else 1)
     # nothing outside the union of a tile's captions x images is written: untouched entries stay NaN
     assert np.isnan(Sp).sum() > 0
 
@@ -116,26 +117,43 @@ def test_two_stage_at_coco1k_shape_matches_dense_composition():
     # stage-2 scores of the lists = dense scores
     np.testing.assert_allclose(det["scores_t2i"].cpu().numpy(), np.take_along_axis(S.T, short_t, axis=1), atol=2e-4)
     np.testing.assert_allclose(det["scores_i2t"].cpu().numpy(), np.take_along_axis(S, short_i, axis=1), atol=2e-4)
-    # ranks: re-rank rule applied to the dense scores
-    rt = np.zeros(5 * Ni)
+    # ranks: re-rank rule applied to the dense scores.  The two kernels sum a caption's words in a different order
+    # (one tile vs <= 2 tiles), so their scores differ in the last bits: the rank must lie between the counts taken
+    # with the ground-truth score moved by +-eps, and be exact wherever no candidate sits within eps of it.
+    eps = 1e-3
+    eps1 = 3e-5 * np.abs(M).max()                        # the matching scores are not normalised here (|M| ~ 40)
+
+    def bounds(sc, p):
+        exact = np.sum((sc > sc[p]) | ((sc == sc[p]) & (np.arange(len(sc)) > p)))
+        return np.sum(sc > sc[p] + eps), exact, np.sum(sc >= sc[p] - eps) - 1
+
+    def check(got, cands):
+        lo = min(c[0] for c in cands)
+        hi = min(c[2] for c in cands)
+        exact = min(c[1] for c in cands)
+        assert lo <= got <= hi, (got, cands)
+        return got == exact
+
+    n_exact = 0
     for c in range(5 * Ni):
         g = c // 5
         pos = np.nonzero(short_t[c] == g)[0]
         if len(pos):
-            sc = S[short_t[c], c]
-            p = pos[0]
-            rt[c] = np.sum((sc > sc[p]) | ((sc == sc[p]) & (np.arange(K) > p)))
-        else:
-            rt[c] = np.sum(M[:, c] > M[g, c])
-    ri = np.zeros(Ni)
+            n_exact += check(det["ranks_t2i"][c], [bounds(S[short_t[c], c], pos[0])])
+        else:                                            # stage-1 rank (fp32-grade GEMM vs float64 here: same eps rule)
+            lo1, hi1 = np.sum(M[:, c] > M[g, c] + eps1), np.sum(M[:, c] >= M[g, c] - eps1) - 1
+            assert lo1 <= det["ranks_t2i"][c] <= hi1
+            n_exact += det["ranks_t2i"][c] == np.sum(M[:, c] > M[g, c])
+    assert n_exact >= 0.98 * 5 * Ni
+    n_exact = 0
     for i in range(Ni):
         inl = np.nonzero((short_i[i] >= 5 * i) & (short_i[i] < 5 * i + 5))[0]
         if len(inl):
             sc = S[i, short_i[i]]
-            ri[i] = min(np.sum((sc > sc[p]) | ((sc == sc[p]) & (np.arange(K) > p))) for p in inl)
+            n_exact += check(det["ranks_i2t"][i], [bounds(sc, p) for p in inl])
         else:
-            ri[i] = min(np.sum(M[i] > M[i, g]) for g in range(5 * i, 5 * i + 5))
-    # scores from the two kernels differ in the last bits: allow rank changes only between near-tied candidates
-    assert np.mean(det["ranks_t2i"] != rt) < 2e-3 and np.abs(det["ranks_t2i"] - rt).max() <= 1
-    assert np.mean(det["ranks_i2t"] != ri) < 5e-3 and np.abs(det["ranks_i2t"] - ri).max() <= 1
+            gs = M[i, 5 * i:5 * i + 5].max()
+            assert np.sum(M[i] > gs + eps1) <= det["ranks_i2t"][i] <= np.sum(M[i] >= gs - eps1) - 1
+            n_exact += det["ranks_i2t"][i] == np.sum(M[i] > gs)
+    assert n_exact >= 0.97 * Ni
     assert out[0][0] > 20 and out[1][0] > 10             # the re-rank finds the ground truth

@@ -13,9 +13,10 @@ def _tiles(details, slots):
     return n
 
 
-@pytest.mark.parametrize("K", [7, 100])
-def test_two_stage_pair_list_path_on_the_emulator(virtual_b200, K):
+@pytest.mark.parametrize("K,l2_bytes", [(7, 48 << 20), (100, 48 << 20), (12, 1 << 13)])
+def test_two_stage_pair_list_path_on_the_emulator(virtual_b200, K, l2_bytes, monkeypatch):
     from aladin_b200 import synth, two_stage
+    monkeypatch.setattr(two_stage, "L2_BLOCK_BYTES", l2_bytes)      # 8 KB: the 36 images go in two blocks of 32
     images, captions, il, cl = synth.eval_containers(43, 36, 14, 32, max_regions=9, max_words=12, alpha=0.3)
     il[5:10] = [1] * 5                      # an image without scored regions: its scores are 0
     cl[7] = 3                               # a caption without scored words: its column is 0
