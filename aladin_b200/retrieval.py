@@ -350,40 +350,52 @@ class AlignmentGallery:
             self._done(n_loc)
             return S
         else:
-            # one rank owns all captions: score chunk k while chunk k+1 is uploaded (host sources)
+            # one rank prepares all captions, in column phases: phase k is scored while phase k+1 is uploaded (host
+            # sources) and packed on a side stream, so only the first, small phase is exposed
+            from .tiling import padded_rows
             on_cpu = not self.captions.is_cuda
-            chunk = self.caption_chunk if on_cpu else self.Nc
-            # host sources: the first chunks are small (chunk/8, /4, /2) so that scoring starts after a few ms of
-            # PCIe traffic instead of a whole chunk's worth; the copies stay ahead of the scoring from then on
-            bounds, c0, size = [], 0, min(chunk, max(chunk // 8, 256)) if on_cpu else chunk
-            while c0 < self.Nc:
-                bounds.append((c0, min(self.Nc, c0 + size)))
-                c0 += size
-                size = min(chunk, 2 * size)
-            main = torch.cuda.current_stream()
             if on_cpu:
-                Lw_max = 1 + int(nw.max())
-                stage = [torch.empty((chunk, Lw_max, d), dtype=torch.float32, device=dev) for _ in range(2)]
-                copy_stream = torch.cuda.Stream()
-                copy_stream.wait_stream(main)
-                ready = [torch.cuda.Event() for _ in bounds]
-                freed = [None, None]
+                # the first phases are small (chunk/8, /4, /2) so that scoring starts after a few ms of PCIe traffic
+                # instead of a whole chunk's worth; the copies stay ahead of the scoring from then on
+                chunk = self.caption_chunk
+                bounds, c0, size = [], 0, min(chunk, max(chunk // 8, 256))
+                while c0 < self.Nc:
+                    bounds.append((c0, min(self.Nc, c0 + size)))
+                    c0 += size
+                    size = min(chunk, 2 * size)
+            elif self.Nc >= 4096:
+                bounds = [(0, self.Nc // 16), (self.Nc // 16, self.Nc)]   # packing is HBM-bound: 6 % exposed, the rest hidden
+            else:
+                bounds = [(0, self.Nc)]
+            if len(bounds) == 1 and not on_cpu:
+                words = scoring.pack_tokens(self.captions, nw, slot0=1, mode=1 if split else 0, want_row_item=True)
+                self._score(words, regions, tiles_dev, n_tiles, n_loc, self.Nc, S)
+                self._done(n_loc)
+                return S
+            csum = np.concatenate([[0], np.cumsum(nw, dtype=np.int64)])
+            rows_max = max(int(csum[c1] - csum[c0]) for c0, c1 in bounds)
+            n_buf = 2 if len(bounds) > 1 else 1
+            words_buf = [torch.empty((max(rows_max, 1), Kp), dtype=torch.bfloat16, device=dev) for _ in range(n_buf)]
+            cap_buf = [torch.empty((max(padded_rows(rows_max), 2 * _cabi.TILE_M),), dtype=torch.int32, device=dev)
+                       for _ in range(n_buf)]
+            main = torch.cuda.current_stream()
+            prep = torch.cuda.Stream()
+            prep.wait_stream(main)
+            freed = [None] * n_buf
             for k, (c0, c1) in enumerate(bounds):
-                if on_cpu:
-                    bsel = k & 1
-                    with torch.cuda.stream(copy_stream):
-                        if freed[bsel] is not None:
-                            copy_stream.wait_event(freed[bsel])
-                        cap_dev = _upload_rows(self.captions, c0, 1, c1 - c0, Lw_max, out=stage[bsel])
-                        ready[k].record(copy_stream)
-                    main.wait_event(ready[k])
-                else:
-                    cap_dev = self.captions[c0:c1]
-                words = scoring.pack_tokens(cap_dev, nw[c0:c1], slot0=1, mode=1 if split else 0, want_row_item=True)
+                b = k % n_buf
+                with torch.cuda.stream(prep):
+                    if freed[b] is not None:
+                        prep.wait_event(freed[b])
+                    cap_buf[b].fill_(-1)
+                    rows = self._pack_caption_range(c0, c1, words_buf[b], cap_buf[b], 0, split, dev, item_origin=c0)
+                    ready = torch.cuda.Event()
+                    ready.record(prep)
+                main.wait_event(ready)
+                words = scoring.Packed(words_buf[b], rows, Kp, None, None, cap_buf[b], 1 if split else 0)
                 self._score(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, S[:, c0:c1])
-                if on_cpu:
-                    freed[bsel] = torch.cuda.Event()
-                    freed[bsel].record(main)
+                freed[b] = torch.cuda.Event()
+                freed[b].record(main)
             self._done(n_loc)
             return S
 

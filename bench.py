@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the `also` block (BASELINE configs 1, 2, 4, 5 and fp32 mode)")
     ap.add_argument("--no-cublas-probe", action="store_true",
                     help="skip the same-box cuBLAS bf16 sustained-GEMM probe reported beside the roofline (context only)")
     return ap.parse_args()
@@ -99,36 +100,47 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path (per-query loops, alad/evaluation.py:175-223)
+# CPU arm: the reference's own evaluation loops (alad/evaluation.py:158-327) on the host cores
 # ------------------------------------------------------------------------------------------
 def cpu_baseline_sample(images_np, captions_np, img_lens, cap_lens, budget_s):
     """Times the reference algorithm on the host cores on a bounded sample: q query images through
     i2t (each against ALL captions, cap_batches=5) and q caption groups through t2i (each against
-    ALL images, im_batches=5).  The code timed is oracle/alad_torch_port.py: the reference's own op
-    sequence (F.normalize, batched matmul on expanded operands, masked_fill_, max, sum, numpy argsort)
-    in torch CPU ops with all host threads -- within ~1.3x of the unmodified reference on the same
-    cores, whereas the numpy oracle is 4-8x slower.  Returns (pairs_per_s, description, cores)."""
+    ALL images, im_batches=5), all host threads.
+
+    kind "reference": the UNMODIFIED alad/evaluation.py + alad/loss.py copied into oracle/_ref by
+    oracle/make_ref.py (run by __graft_entry__.build() where /root/reference exists), driven through
+    their public API with the sim_function closure of alad/test.py:259-263 and `.cuda()` as the identity.
+    kind "port": oracle/alad_torch_port.py (the same op sequence restated; ~1.3x slower) when the copy is absent.
+    Returns (pairs_per_s, description, cores, kind)."""
     import torch
-    from oracle import alad_torch_port as TP
+    from oracle import ref_runner as RR
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     Ni = images_np.shape[0] // 5
     Nc = captions_np.shape[0]
     images_t, captions_t = torch.from_numpy(images_np), torch.from_numpy(captions_np)
+    if RR.available():
+        kind, what = "reference", "unmodified alad.evaluation.i2t/t2i + alad.loss.AlignmentContrastiveLoss('MrSw') from oracle/_ref"
 
-    def run(q):
-        t0 = time.perf_counter()
-        TP.i2t(images_t, captions_t, img_lens, cap_lens, npts=q, cap_batches=5)
-        TP.t2i(images_t, captions_t, img_lens, cap_lens, npts=q, im_batches=5)
-        return time.perf_counter() - t0
+        def run(q):
+            return RR.run_sample(images_t, captions_t, img_lens, cap_lens, q, batches=5)[0]
+    else:
+        from oracle import alad_torch_port as TP
+        kind, what = "port", "torch-CPU port of the reference loops (oracle/alad_torch_port.py; oracle/_ref absent)"
+
+        def run(q):
+            t0 = time.perf_counter()
+            TP.i2t(images_t, captions_t, img_lens, cap_lens, npts=q, cap_batches=5)
+            TP.t2i(images_t, captions_t, img_lens, cap_lens, npts=q, im_batches=5)
+            return time.perf_counter() - t0
 
     t1 = run(1)                                            # also the warm-up
     q = int(max(1, min(Ni, budget_s / max(t1, 1e-3))))
     t = run(q) if q > 1 else t1
     pairs = q * Nc + 5 * q * Ni
-    desc = (f"torch-CPU port of the reference loops: i2t for {q} query images x {Nc} captions (cap_batches=5) + t2i for "
-            f"{q} caption groups ({5 * q} captions) x {Ni} images (im_batches=5), fp32, {torch.get_num_threads()} threads, {t:.1f} s")
-    return pairs / t, desc, torch.get_num_threads()
+    desc = (f"{what}: i2t for {q} query images x {Nc} captions (cap_batches=5) + t2i for {q} caption groups "
+            f"({5 * q} captions) x {Ni} images (im_batches=5), fp32, {torch.get_num_threads()} threads, {t:.1f} s")
+    return pairs / t, desc, torch.get_num_threads(), kind
 
 
 def host_layout(images_dev, captions_dev, pinned=True):
@@ -169,12 +181,12 @@ def main():
         del images, captions
         img_lens5 = [l for l in im_len for _ in range(5)]
         vals = []
-        desc = cores = None
+        desc = cores = kind = None
         # every step is a bounded sample; the whole --steps/--warmup run stays within a few minutes
         per_step = min(args.cpu_seconds, 150.0 / max(args.steps + args.warmup, 1))
         for it in range(args.warmup + args.steps):
             budget = per_step if it >= args.warmup else min(per_step, 5.0)
-            v, desc, cores = cpu_baseline_sample(imgs_h.numpy(), caps_h.numpy(), img_lens5, s_len, budget)
+            v, desc, cores, kind = cpu_baseline_sample(imgs_h.numpy(), caps_h.numpy(), img_lens5, s_len, budget)
             if it >= args.warmup:
                 vals.append(v)
         value = float(np.mean(vals))
@@ -183,7 +195,7 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * pairs / value,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "gpu_launches": 0,
-                "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc},
+                "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": desc},
                 "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "ms_per_step is the sample rate extrapolated to the full workload (queries are independent)"}
         print(json.dumps(line))
@@ -290,7 +302,7 @@ def main():
             result["t2i"] = evaluation.t2i(imgs_h, caps_h, img_lens5, s_len, sim_function=alignment_sim_fn, im_batches=5)
 
         ms_e2e, _, _, _ = timed(step_e2e, max(2, min(args.steps, 3)), 3)
-        lo, hi = retrieval.shard_bounds(Ni, world, rank)
+        lo, hi = retrieval.balancer.bounds(Ni, world, rank)
         h2d = (hi - lo) * (regions + 1) * d * 4 + Nc * (words + 1) * d * 4
         d2h = (Ni + Nc + Ni + Nc * 50) * 4
         e2e = {"value": Ni * Nc / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
@@ -305,8 +317,8 @@ def main():
         if args.no_e2e:
             imgs_h, caps_h = host_layout(images, captions, pinned=False)
             img_lens5 = [l for l in im_len for _ in range(5)]
-        v, desc, cores = cpu_baseline_sample(imgs_h.numpy(), caps_h.numpy(), img_lens5, s_len, args.cpu_seconds)
-        cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc}
+        v, desc, cores, kind = cpu_baseline_sample(imgs_h.numpy(), caps_h.numpy(), img_lens5, s_len, args.cpu_seconds)
+        cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": desc}
 
     # ---- context for the roofline: cuBLAS bf16 GEMM sustained on THIS box (after all timed regions)
     if rank == 0 and world == 1 and not args.no_cublas_probe:
@@ -319,12 +331,37 @@ def main():
         except Exception as e:      # the probe is context, never a reason to lose the bench line
             roofline["same_box_cublas_bf16_tflops_sustained"] = f"probe failed: {e}"
 
+    # ---- e2e once more from PAGEABLE host tensors (what the reference's encode_data hands over)
+    if e2e is not None and rank == 0 and world == 1 and not args.no_also:
+        imgs_p, caps_p = host_layout(images, captions, pinned=False)
+
+        def step_pageable():
+            evaluation.clear_cache()
+            evaluation.i2t(imgs_p, caps_p, img_lens5, s_len, sim_function=alignment_sim_fn, cap_batches=5)
+            evaluation.t2i(imgs_p, caps_p, img_lens5, s_len, sim_function=alignment_sim_fn, im_batches=5)
+
+        ms_pg, _, _, _ = timed(step_pageable, 2, 1)
+        e2e["pageable_host_tensors"] = {"ms_per_step": ms_pg, "value": Ni * Nc / (ms_pg * 1e-3), "unit": "pairs/s"}
+        del imgs_p, caps_p
+
+    # ---- the other BASELINE configs in the same run (N = 1 only)
+    also = None
+    if rank == 0 and world == 1 and not args.no_also:
+        del images, captions
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_also
+            also = bench_also.also_block(pk)
+        except Exception as e:          # context, never a reason to lose the headline line
+            also = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         line = {"metric": "alignment_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu, "recall_at_1": recalls,
+                "roofline": roofline, "cpu_baseline": cpu, "recall_at_1": recalls, "also": also,
                 "tflops_algorithmic_whole_step": Ni * Nc * FLOP_PER_PAIR(regions, words, d) / (ms_step * 1e-3) / 1e12}
         print(json.dumps(line))
     if world > 1:
