@@ -39,6 +39,8 @@ class ShardBalancer:
 
     def __init__(self):
         self.speed = {}            # world -> float64 [world], mean 1
+        self.enabled = True        # False: keep the current bounds (A/B runs, tests)
+        self.last = None           # the last gathered (images, ms) lists
 
     def all_bounds(self, n, world):
         sp = self.speed.get(world)
@@ -55,7 +57,8 @@ class ShardBalancer:
     def update(self, world, images, ms):
         """images / ms: per-rank work and time of one earlier step (entries with ms <= 0 carry no measurement)."""
         images, ms = np.asarray(images, np.float64), np.asarray(ms, np.float64)
-        if len(images) != world or np.any(ms <= 0) or np.any(images <= 0):
+        self.last = (images.tolist(), ms.tolist())
+        if len(images) != world or np.any(ms <= 0) or np.any(images <= 0) or not self.enabled:
             return
         rate = images / ms
         rate = rate / rate.mean()
@@ -69,20 +72,27 @@ class ShardBalancer:
 
 
 balancer = ShardBalancer()
-# this rank's last completed scoring pass: (images scored, [(start_event, end_event), ...]); read one step later
-_last_timing = {"n": 0, "events": []}
+# Device-resident captions: pack everything, then ONE scoring launch.  Packing the second of two column phases on a side
+# stream under the first phase's scoring was measured at N = 2 (profiles/r02_n2_phase_balance_ab.md): the HBM-bound pack
+# kernel crawls next to the persistent tcgen05 kernel (1.3 ms alone, ~12 ms co-scheduled) and the step got 8-10 ms SLOWER
+# (173-177 ms against 166 ms), so the 1.3 ms stay exposed.  True re-enables the two-phase variant for A/B runs.
+DEVICE_PHASES = False
+# this rank's recent scoring passes, oldest first: (images scored, [(start_event, end_event), ...]).  The exchange of
+# step k ships the newest pass whose events have COMPLETED (normally step k-1: the launches of step k are still running
+# when its payload is assembled) -- never waits, never reads an unfinished event.
+_timings = collections.deque(maxlen=4)
 
 
 def _take_timing():
-    """(images, ms) of this rank's previous scoring pass, (0, 0) when there is none; consumes it."""
-    n, ev = _last_timing["n"], _last_timing["events"]
-    _last_timing["n"], _last_timing["events"] = 0, []
-    if not n or not ev:
+    """(images, ms) of this rank's latest completed scoring pass, (0, 0) when there is none; consumes it and
+    everything older."""
+    best = None
+    while _timings and _timings[0][1][-1][1].query():
+        best = _timings.popleft()
+    if best is None:
         return 0.0, 0.0
-    try:
-        return float(n), float(sum(a.elapsed_time(b) for a, b in ev))
-    except RuntimeError:            # events not complete (no synchronisation since): no measurement
-        return 0.0, 0.0
+    n, ev = best
+    return float(n), float(sum(a.elapsed_time(b) for a, b in ev))
 
 
 # Derived host arrays of a gallery (valid counts, clamp flags) are a function of the python length lists the
@@ -179,7 +189,8 @@ class AlignmentGallery:
 
     def _done(self, n_loc):
         if self.world > 1:
-            _last_timing["n"], _last_timing["events"] = n_loc, self._events
+            if n_loc and self._events:
+                _timings.append((n_loc, self._events))
             self._events = []
 
     def _phase_bounds(self):
@@ -363,7 +374,7 @@ class AlignmentGallery:
                     bounds.append((c0, min(self.Nc, c0 + size)))
                     c0 += size
                     size = min(chunk, 2 * size)
-            elif self.Nc >= 4096:
+            elif self.Nc >= 4096 and DEVICE_PHASES:
                 bounds = [(0, self.Nc // 16), (self.Nc // 16, self.Nc)]   # packing is HBM-bound: 6 % exposed, the rest hidden
             else:
                 bounds = [(0, self.Nc)]

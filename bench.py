@@ -214,6 +214,10 @@ def main():
     import aladin_b200
     from aladin_b200 import _cabi, evaluation, loss as L, retrieval, scoring, synth
     aladin_b200.set_precision(args.precision)
+    if os.environ.get("ALAD_NO_BALANCE"):          # diagnostics: equal image blocks
+        retrieval.balancer.enabled = False
+    if os.environ.get("ALAD_DEVICE_PHASES"):       # diagnostics: pack the captions in two column phases on a side stream
+        retrieval.DEVICE_PHASES = True
 
     images, captions, im_len, s_len = synth.dense_gallery_device(Ni, Nc, regions, words, d)
     torch.cuda.synchronize()
@@ -258,6 +262,12 @@ def main():
                                                        bounds=gal.bounds)
 
     ms_step, timeline, launches, clocks = timed(step_resident, args.steps, args.warmup)
+    shard_balance = None
+    if world > 1:
+        sp = retrieval.balancer.speed.get(world)
+        shard_balance = {"image_blocks": retrieval.balancer.all_bounds(Ni, world), "relative_speed": sp.tolist() if sp is not None else None,
+                         "last_gathered_images_ms": retrieval.balancer.last,
+                         "what": "image blocks sized by every rank's measured scoring speed (retrieval.ShardBalancer)"}
     value = Ni * Nc / (ms_step * 1e-3)
     ranks_i2t, _, ranks_t2i, _ = result["out"]
     recalls = {"i2t_r1": retrieval.recall_tuple(ranks_i2t)[0], "t2i_r1": retrieval.recall_tuple(ranks_t2i)[0]}
@@ -361,7 +371,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu, "recall_at_1": recalls, "also": also,
+                "roofline": roofline, "cpu_baseline": cpu, "recall_at_1": recalls, "also": also, "shard_balance": shard_balance,
                 "tflops_algorithmic_whole_step": Ni * Nc * FLOP_PER_PAIR(regions, words, d) / (ms_step * 1e-3) / 1e12}
         print(json.dumps(line))
     if world > 1:
