@@ -18,19 +18,64 @@ from . import retrieval, scoring
 _cache = {}
 
 
-def _find_scorer(fn):
+def fused_sim_function(scorer):
+    """The ``sim_function`` closure of alad/test.py:259-263 over a drop-in criterion, TAGGED so that i2t / t2i take
+    the fused one-pass path without probing it: ``fn(img, cap, img_len, cap_len)`` = scores of the criterion."""
+    def alignment_sim_fn(img, cap, img_len, cap_len):
+        with torch.no_grad():
+            return scorer(img, cap, img_len, cap_len, return_loss=False, return_similarity_mat=True)
+    alignment_sim_fn.alad_scorer = scorer
+    return alignment_sim_fn
+
+
+def _probe_ok(fn, scorer, images, captions, img_lens, cap_lens):
+    """Does ``fn`` return exactly the criterion's scores?  One query image x up to 8 captions through both; a closure
+    that post-processes the scores (adds the matching term, rescales, combines two criteria) differs and is then
+    invoked per query like the reference does."""
+    from .gallery import DeviceContainer
+    if isinstance(images, DeviceContainer):
+        return True                      # packed containers have no raw tokens a foreign callable could consume
+    n = min(8, captions.shape[0])
+    if images.shape[0] == 0 or n == 0:
+        return True
+    try:
+        with torch.no_grad():
+            im = images[0:1].cuda()
+            cap = captions[:n].cuda()
+            a = fn(im, cap, [img_lens[0]], list(cap_lens[:n]))
+            b = scorer(im, cap, [img_lens[0]], list(cap_lens[:n]), return_loss=False, return_similarity_mat=True)
+        a, b = torch.as_tensor(a).float().reshape(-1).cpu(), b.float().reshape(-1).cpu()
+        return a.shape == b.shape and bool(torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)))
+    except Exception:
+        return False
+
+
+def _find_scorer(fn, probe=None):
+    """The drop-in criterion behind ``sim_function`` when the fused path may replace the callable:
+    the criterion instance itself, a callable tagged by ``fused_sim_function`` (attribute ``alad_scorer``), or a bound
+    method / closure over a criterion that the probe (``probe`` = (images, captions, img_lens, cap_lens)) shows to
+    return the criterion's scores unchanged.  Anything else -> None (per-query callback path, like the reference)."""
     from .loss import AlignmentContrastiveLoss
+
+    def valid(c):
+        return isinstance(c, AlignmentContrastiveLoss) and c.aggregation in c.SUPPORTED
+
     if fn is None:
         return None
-    cands = [fn, getattr(fn, "alad_scorer", None), getattr(fn, "__self__", None)]
+    if valid(fn):
+        return fn
+    tagged = getattr(fn, "alad_scorer", None)
+    if valid(tagged):
+        return tagged
+    cands = [getattr(fn, "__self__", None)]
     for cell in getattr(fn, "__closure__", None) or ():
         try:
             cands.append(cell.cell_contents)
         except ValueError:
             pass
     for c in cands:
-        if isinstance(c, AlignmentContrastiveLoss) and c.aggregation in c.SUPPORTED:
-            return c
+        if valid(c):
+            return c if (probe is None or _probe_ok(fn, c, *probe)) else None
     return None
 
 
@@ -47,14 +92,18 @@ def _callback_scores(images, captions, img_lens, cap_lens, sim_function, cap_bat
     gallery chunk (evaluation.py:199-210); results land in a device matrix for our ranking."""
     N = images.shape[0]
     Ni = N // 5
-    per = captions.shape[0] // cap_batches
-    S = torch.empty((Ni, per * cap_batches), dtype=torch.float32, device="cuda")
-    caps_dev = [captions[b * per:(b + 1) * per].cuda() for b in range(cap_batches)]
+    Nc = captions.shape[0]
+    # the gallery chunks cover EVERY caption (the reference's `shape[0] // batches` silently drops the remainder of a
+    # non-divisible split: evaluation.py:173,262); one matrix serves i2t and t2i
+    per = max(1, -(-Nc // max(int(cap_batches), 1)))
+    spans = [(c0, min(Nc, c0 + per)) for c0 in range(0, Nc, per)]
+    S = torch.empty((Ni, Nc), dtype=torch.float32, device="cuda")
+    caps_dev = [captions[c0:c1].cuda() for c0, c1 in spans]
     for i in range(Ni):
         im = images[5 * i].reshape(1, images.shape[1], images.shape[2]).cuda()
-        for b in range(cap_batches):
-            d = sim_function(im, caps_dev[b], [img_lens[5 * i]], cap_lens[b * per:(b + 1) * per])
-            S[i, b * per:(b + 1) * per] = d.reshape(-1).float().cuda()
+        for (c0, c1), cd in zip(spans, caps_dev):
+            d = sim_function(im, cd, [img_lens[5 * i]], cap_lens[c0:c1])
+            S[i, c0:c1] = d.reshape(-1).float().cuda()
     return S
 
 
@@ -74,6 +123,12 @@ def clear_cache():
     _cache.clear()
 
 
+def _evict(key):
+    """weakref.finalize callback: the inputs of the cached block died -> release its HBM (0.5 GB at COCO-5k)."""
+    if _cache.get("key") == key:
+        _cache.clear()
+
+
 def _dist_state():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -86,7 +141,7 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
 
     Returns dict(S, img_off, ranks_i2t, top1, ranks_t2i, top50).  Under torch.distributed
     (world > 1) the fused path shards the gallery images across ranks (retrieval.py)."""
-    scorer = _find_scorer(sim_function)
+    scorer = _find_scorer(sim_function, probe=(images, captions, img_lens, cap_lens))
     mode = "global" if sim_function is None else ("callback" if scorer is None else
                                                    "fused" if scorer.aggregation == "MrSw" else "block")
     from .gallery import DeviceContainer
@@ -128,6 +183,8 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
         refs = (weakref.ref(images), weakref.ref(captions))
         _cache.clear()
         _cache.update(key=key, res=res, refs=refs)
+        for obj in (images, captions):       # the block dies with its inputs, not with the next call
+            weakref.finalize(obj, _evict, key)
     return res
 
 
@@ -140,7 +197,9 @@ def _ndcg(ndcg_scorer, res, npts, fold_index, retrieval_kind):
     rougel, spice = np.zeros(n), np.zeros(n)
     for q in range(n):
         d = S[q] if retrieval_kind == "sentence" else S[:, q]
-        inds = torch.argsort(d, descending=True, stable=True).cpu().numpy()
+        # same total order as the ranking kernels and as numpy.argsort(d)[::-1]: score descending, HIGHER index first
+        # on exact ties (stable descending sort of the reversed vector, mapped back)
+        inds = (d.numel() - 1 - torch.argsort(d.flip(0), descending=True, stable=True)).cpu().numpy()
         rougel[q], spice[q] = ndcg_scorer.compute_ndcg(npts, q, inds.astype(int), fold_index=fold_index,
                                                        retrieval=retrieval_kind).values()
     return rougel, spice

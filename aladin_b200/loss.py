@@ -20,14 +20,24 @@ def _ws(nbytes, device):
 # --------------------------------------------------------------------------------------
 # kernels as functions
 # --------------------------------------------------------------------------------------
+def _rowmajor(x):
+    """fp32, unit innermost stride and a row stride that really separates the rows (an expanded / broadcast matrix
+    has stride(0) = 0: the kernels would read B*B floats from a buffer that does not hold them)."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.dim() == 2 and x.shape[0] > 1 and (x.stride(1) != 1 or x.stride(0) < x.shape[1]):
+        x = x.contiguous()
+    elif x.dim() == 2 and x.stride(1) != 1:
+        x = x.contiguous()
+    return x
+
+
 def triplet_fwd_bwd(scores, margin, max_violation, want_grad=True):
     """(loss 0-d, G [B,B] or None, row_arg, col_arg) -- alad/loss.py:42-67 + SURVEY A.1."""
     lib = _cabi.lib()
     if scores.dim() != 2 or scores.shape[0] != scores.shape[1]:
         raise RuntimeError("compute_contrastive_loss needs a square score matrix (torch.eye at alad/loss.py:55)")
-    S = scores.detach()
-    if S.stride(1) != 1:
-        S = S.contiguous()
+    S = _rowmajor(scores.detach())
     B = S.shape[0]
     dev = S.device
     loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -44,12 +54,11 @@ def triplet_fwd_bwd(scores, margin, max_violation, want_grad=True):
 def listnet_fwd_bwd(teacher, student, temperature=6.0, eps=1e-10, want_grad=True):
     """(loss 0-d, dM or None) -- alad/loss.py:427-445 + SURVEY A.2."""
     lib = _cabi.lib()
-    T = teacher.detach().float()
-    M = student.detach().float()
+    T = teacher.detach()
+    M = student.detach()
     if T.shape != M.shape or T.dim() != 2 or T.shape[0] != T.shape[1]:
         raise RuntimeError("listnet distillation expects two square matrices of equal shape")
-    T = T if T.stride(1) == 1 else T.contiguous()
-    M = M if M.stride(1) == 1 else M.contiguous()
+    T, M = _rowmajor(T), _rowmajor(M)
     B = T.shape[0]
     dev = M.device
     loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -67,11 +76,7 @@ def _square_pair(teacher, student, what):
     M = student.detach()
     if T.shape != M.shape or T.dim() != 2 or T.shape[0] != T.shape[1]:
         raise RuntimeError(f"{what} distillation expects two square matrices of equal shape")
-    if T.dtype != torch.float32 or T.stride(1) != 1:
-        T = T.float().contiguous()
-    if M.dtype != torch.float32 or M.stride(1) != 1:
-        M = M.float().contiguous()
-    return T, M
+    return _rowmajor(T), _rowmajor(M)
 
 
 def distill_mse_fwd_bwd(teacher, student, wb, want_grad=True):
@@ -95,11 +100,10 @@ def distill_contrastive_fwd_bwd(teacher, student, margin, want_grad=True, mutate
     """(loss 0-d, dM or None) -- alad/loss.py:397-418.  With mutate_teacher the diagonal of the caller's
     teacher matrix is zeroed in place, which is what the reference's `.detach().masked_fill_` does."""
     lib = _cabi.lib()
-    M = student.detach()
-    if M.dtype != torch.float32 or M.stride(1) != 1:
-        M = M.float().contiguous()
+    M = _rowmajor(student.detach())
     T = teacher.detach()
-    in_place = mutate_teacher and T.is_cuda and T.dtype == torch.float32 and T.dim() == 2 and T.stride(1) == 1
+    in_place = (mutate_teacher and T.is_cuda and T.dtype == torch.float32 and T.dim() == 2 and T.stride(1) == 1
+                and (T.shape[0] <= 1 or T.stride(0) >= T.shape[1]))
     if not in_place:
         T = T.to(device=M.device, dtype=torch.float32).contiguous().clone()
     if T.shape != M.shape or T.dim() != 2 or T.shape[0] != T.shape[1]:

@@ -8,6 +8,7 @@ from . import _cabi
 
 def _check_S(S):
     assert S.is_cuda and S.dtype == torch.float32 and S.dim() == 2 and S.stride(1) == 1
+    assert S.shape[0] <= 1 or S.stride(0) >= S.shape[1], "rows of S overlap (expanded / broadcast matrix): call .contiguous()"
     return S.shape[0], S.shape[1], max(S.stride(0), S.shape[1])
 
 

@@ -51,6 +51,11 @@ def _require_cuda(x, name):
         raise _cabi.AladError("aladin_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
     if x.device.type != "cuda":
         x = x.cuda(non_blocking=True)
+    elif x.device.index is not None and x.device.index != torch.cuda.current_device():
+        # the C ABI launches on the CURRENT device's stream (include/alad_b200.h): pointers of another device would be
+        # dereferenced there
+        raise _cabi.AladError(f"{name} lives on cuda:{x.device.index} but the current device is cuda:{torch.cuda.current_device()}: "
+                              f"call torch.cuda.set_device({x.device.index}) or wrap the call in torch.cuda.device(...)")
     if x.dtype != torch.float32:
         x = x.float()
     if x.dim() >= 1 and x.stride(-1) != 1:

@@ -64,6 +64,7 @@ def test_cache_misses_for_other_objects_with_the_same_key(monkeypatch):
     images2.mul_(-1.0)
     ev.i2t(images2, captions2, il, cl)
     assert calls == ["scores"] * 3
-    # dead inputs never hit
+    # dead inputs never hit, and the cached block (0.5 GB of HBM at COCO-5k) is released with them
+    assert ev._cache["refs"][0]() is images2
     del images2, captions2
-    assert ev._cache["refs"][0]() is None
+    assert not ev._cache

@@ -82,6 +82,46 @@ def test_arbitrary_callable_sim_function():
     assert len(calls) == 60 * 5 and set(calls) == {60}
 
 
+def test_closure_that_post_processes_the_scores_is_not_bypassed():
+    """a closure over the drop-in criterion that changes its scores (here: adds the matching term, the
+    commented-out `+ d_matching` of alad/evaluation.py:206-210) must be CALLED, not replaced by the fused block; the
+    plain closure of alad/test.py:259-263 and the tagged helper take the fused path."""
+    from aladin_b200 import evaluation as E, loss as L
+    g = load_golden("retrieval")
+    images, captions, il, cl = _containers(g)
+    crit = L.AlignmentContrastiveLoss(aggregation="MrSw")
+    crit.precision = "fp32"
+    n_calls = []
+
+    def plain(img, cap, img_len, cap_len):
+        n_calls.append(img.shape[0])
+        return crit(img, cap, img_len, cap_len, return_loss=False, return_similarity_mat=True)
+
+    def with_matching(img, cap, img_len, cap_len):
+        n_calls.append(img.shape[0])
+        d = crit(img, cap, img_len, cap_len, return_loss=False, return_similarity_mat=True)
+        return d - 3.0 * torch.mm(img[:, 0, :], cap[:, 0, :].t())
+
+    E.clear_cache()
+    m_plain, (r_plain, _) = E.i2t(images, captions, il, cl, return_ranks=True, sim_function=plain, cap_batches=5)
+    assert len(n_calls) == 1 and E._cache["key"][-2] == "fused:MrSw"          # the probe call only
+    np.testing.assert_array_equal(r_plain, g["ranks_i2t"])
+    n_calls.clear()
+    E.clear_cache()
+    m_post, (r_post, _) = E.i2t(images, captions, il, cl, return_ranks=True, sim_function=with_matching, cap_batches=5)
+    assert len(n_calls) == 1 + 60 * 5                                         # probe, then one call per query and chunk
+    S = g["S_full"].astype(np.float64) - 3.0 * (g["images"][:, 0, :].astype(np.float64) @ g["captions"][:, 0, :].astype(np.float64).T)
+    ri, _ = O.i2t_ranks(S.astype(np.float32))
+    gt = np.array([5 * i + int(np.argmax(S[i, 5 * i:5 * i + 5])) for i in range(60)])
+    assert_ranks_equal_up_to_ties(r_post, ri, S.astype(np.float32), gt, 1e-4, "post-processed closure: i2t ranks")
+    assert not np.array_equal(r_post, r_plain)
+    n_calls.clear()
+    E.clear_cache()
+    tagged = E.fused_sim_function(crit)
+    _, (r_tag, _) = E.i2t(images, captions, il, cl, return_ranks=True, sim_function=tagged, cap_batches=5)
+    np.testing.assert_array_equal(r_tag, g["ranks_i2t"])
+
+
 def test_coco1k_shape_subset_vs_oracle():
     """Dense 34x50, d=1024 tokens (BASELINE per-pair shape) at 100 images x 500 captions."""
     from aladin_b200 import evaluation as E, loss as L, synth

@@ -127,7 +127,7 @@ def test_other_pooling_modes_one_block_equals_per_query_callbacks(agg):
     evaluation.clear_cache()
     mi, (ri, t1) = evaluation.i2t(images, captions, il, cl, return_ranks=True, sim_function=sim_fn, cap_batches=5)
     mt, (rt, t50) = evaluation.t2i(images, captions, il, cl, return_ranks=True, sim_function=sim_fn, im_batches=5)
-    assert calls == [60]                                   # one call, shared by both directions
+    assert calls == [1, 1, 60]                             # the probe (closure, criterion), then ONE block call shared by both directions
     S = evaluation._cache["res"]["S"].cpu().numpy()
     other = L.AlignmentContrastiveLoss(aggregation="MrSw" if agg != "MrSw" else "symm")
     m_other = evaluation.i2t(images, captions, il, cl, sim_function=other)

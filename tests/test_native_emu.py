@@ -79,10 +79,11 @@ def test_block_mode_of_i2t_on_a_small_gallery(virtual_b200, agg):
     orig = crit.forward
     crit.forward = lambda *a, **k: (calls.append(a[0].shape[0]), orig(*a, **k))[1]
     evaluation.clear_cache()
-    m, (ranks, top1) = evaluation.i2t(torch.from_numpy(images), torch.from_numpy(captions), il, cl, return_ranks=True,
+    ti, tc = torch.from_numpy(images), torch.from_numpy(captions)      # kept alive: the cached block dies with its inputs
+    m, (ranks, top1) = evaluation.i2t(ti, tc, il, cl, return_ranks=True,
                                       sim_function=lambda im, cap, a, b: crit(im, cap, a, b, return_loss=False,
                                                                               return_similarity_mat=True), cap_batches=2)
-    assert calls == [8]
+    assert calls == [1, 1, 8]                              # probe of the closure (closure, criterion), then one block call
     ref = (O.alignment_scores_small(images[0::5], captions, il[0::5], cl, agg) if agg != "scan-sentences"
            else O.scan_scores(images[0::5], captions, il[0::5], cl))
     S = evaluation._cache["res"]["S"].numpy()
