@@ -16,6 +16,8 @@ import torch
 from . import retrieval, scoring
 
 _cache = {}
+# verdict of the closure probe per sim_function object (i2t and t2i of one evaluation hand over the same closure)
+_probe_memo = weakref.WeakKeyDictionary()
 
 
 def fused_sim_function(scorer):
@@ -75,7 +77,20 @@ def _find_scorer(fn, probe=None):
             pass
     for c in cands:
         if valid(c):
-            return c if (probe is None or _probe_ok(fn, c, *probe)) else None
+            if probe is None:
+                return c
+            memo_key = (id(c), c.aggregation, getattr(c, "precision", None))
+            try:
+                hit = _probe_memo.get(fn)
+            except TypeError:                # not weak-referenceable: probe every time
+                hit = None
+            if hit is None or hit[0] != memo_key:
+                hit = (memo_key, _probe_ok(fn, c, *probe))
+                try:
+                    _probe_memo[fn] = hit
+                except TypeError:
+                    pass
+            return c if hit[1] else None
     return None
 
 
@@ -119,8 +134,9 @@ def _block_scores(images, captions, img_lens, cap_lens, scorer):
 
 
 def clear_cache():
-    """Forget the score block kept from the previous i2t/t2i call."""
+    """Forget the score block kept from the previous i2t/t2i call (and the closure-probe verdicts)."""
     _cache.clear()
+    _probe_memo.clear()
 
 
 def _evict(key):

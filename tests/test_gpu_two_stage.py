@@ -102,6 +102,9 @@ def test_two_stage_at_coco1k_shape_matches_dense_composition():
     from aladin_b200 import retrieval, synth, two_stage
     Ni, d, K = 1000, 256, 100
     images, captions, il, cl = synth.eval_containers(48, Ni, 53, d, max_regions=34, max_words=50, alpha=0.25)
+    # global (slot-0) vectors that carry signal, like a trained matching head: sum of the item's tokens (padding is 0)
+    images[:, 0, :] = images[:, 1:, :].sum(axis=1) / 6.0
+    captions[:, 0, :] = captions[:, 1:, :].sum(axis=1) / 6.0
     ti, tc = torch.from_numpy(images), torch.from_numpy(captions)
     out, det = two_stage.two_stage_retrieval(ti, tc, il, cl, shortlist=K, precision="bf16", return_details=True)
     gal = retrieval.AlignmentGallery(ti, tc, il, cl, n_images=Ni, img_start=0, img_step=5, precision="bf16")
