@@ -83,6 +83,7 @@ class MrswBwdArgs(C.Structure):
 
 
 PTILE_SLOTS, PTILE_WORDS = 8, 24
+MAX_PEERS, PEER_HANDLE_BYTES = 32, 64
 
 
 class PairtileArgs(C.Structure):
@@ -155,6 +156,14 @@ PROTOTYPES = {
     "alad_mrsw_scores_pairs": (C.c_int, [C.POINTER(MrswPairsArgs), _P]),
     "alad_gather_list_scores": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "alad_list_rerank": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "alad_peer_alloc": (C.c_int, [C.POINTER(C.c_void_p), _I64]),
+    "alad_peer_free": (C.c_int, [_P]),
+    "alad_peer_export": (C.c_int, [_P, _P]),
+    "alad_peer_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "alad_peer_close": (C.c_int, [_P]),
+    "alad_peer_copy": (C.c_int, [_P, _P, _I64, _P]),
+    "alad_peer_signal": (C.c_int, [_P, _I32, _I32, _P]),
+    "alad_peer_wait": (C.c_int, [_P, _I32, _I32, _I32, _I64, _P, _P]),
 }
 
 _lib = None
@@ -190,6 +199,7 @@ KERNELS_PER_CALL = {
     "alad_train_losses_fwd": 13, "alad_train_losses_bwd": 16,
     "alad_order_scores": 1, "alad_order_scores_bwd": 1, "alad_normalize_bwd": 1, "alad_pool_tokens_bwd": 1,
     "alad_pairtile_build": 5, "alad_mrsw_scores_pairs": 1, "alad_gather_list_scores": 1, "alad_list_rerank": 1,
+    "alad_peer_signal": 1, "alad_peer_wait": 1,
     "alad_scan_gram": 1, "alad_scan_gram_bwd": 1, "alad_scan_pool_fwd": 1, "alad_scan_pool_bwd": 1, "alad_scan_apply_pairs": 1,
 }
 launch_count = {"kernels": 0}

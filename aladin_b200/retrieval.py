@@ -81,6 +81,11 @@ DEVICE_PHASES = False
 # step k ships the newest pass whose events have COMPLETED (normally step k-1: the launches of step k are still running
 # when its payload is assembled) -- never waits, never reads an unfinished event.
 _timings = collections.deque(maxlen=4)
+# diagnostics (tools/e2e_timeline.py): when a list, the host-resident sharded path appends per caption phase
+# dict(c0, c1, t0, packed, gathered [prep-stream events], s0, s1 [main-stream events around the scoring launch])
+phase_timeline = None
+# diagnostics: when a list, rank_device appends one dict of CUDA events (stage name -> event recorded after that stage)
+rank_timeline = None
 
 
 def _take_timing():
@@ -93,6 +98,86 @@ def _take_timing():
         return 0.0, 0.0
     n, ev = best
     return float(n), float(sum(a.elapsed_time(b) for a, b in ev))
+
+
+# How the packed caption rows of a phase reach all ranks when the captions live on the host (every rank uploads and
+# packs 1/world of them): "peer" = copy engines through IPC peer windows (peer.py; needs NVLink / P2P access between
+# the ranks' GPUs, one node), "nccl" = all_gather_into_tensor.
+EXCHANGE = "peer"
+_exchanges = {}
+
+
+class _CaptionExchange:
+    """Per process group: the peer window (2 x words, 2 x caption ids, ready / ack flags), the side streams and the
+    global phase counter of the host-resident sharded path.  Persistent across calls: sequence numbers keep growing,
+    so the acknowledgements of one call's last phases gate the first phases of the next."""
+    FLAG_BYTES = 4096
+
+    def __init__(self, group, world, pad_max, Kp):
+        from . import peer
+        self.world, self.pad_max, self.Kp = world, pad_max, Kp
+        up = lambda x: (x + 1023) // 1024 * 1024       # noqa: E731
+        wbytes, cbytes = up(world * pad_max * Kp * 2), up(world * pad_max * 4)
+        self.off_words = [0, wbytes]
+        self.off_caps = [2 * wbytes, 2 * wbytes + cbytes]
+        self.off_flags = 2 * wbytes + 2 * cbytes
+        assert 4 * (2 * 2 * world + 1) <= self.FLAG_BYTES
+        self.win = peer.PeerWindow(self.off_flags + self.FLAG_BYTES, group)
+        self.words = [self.win.view(o, world * pad_max * Kp * 2, torch.bfloat16).view(world * pad_max, Kp) for o in self.off_words]
+        self.caps = [self.win.view(o, world * pad_max * 4, torch.int32) for o in self.off_caps]
+        self.error_ptr = self.win.local + self.off_flags + 4 * (4 * world)
+        self.error_view = self.win.view(self.off_flags + 4 * (4 * world), 4, torch.int32)
+        self.error_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        self.error_event = None
+        self.prep, self.xchg = torch.cuda.Stream(), torch.cuda.Stream()
+        self.freed, self.sent = [None, None], [None, None]
+        self.g = 0
+
+    def off_flag(self, kind, b, q):
+        """Byte offset of flag slot (kind, buffer b, source rank q) inside a window."""
+        return self.off_flags + 4 * (((0 if kind == "ready" else 2) + b) * self.world + q)
+
+    def flag_ptr(self, kind, b):
+        return self.win.local + self.off_flag(kind, b, 0)
+
+    def check_error_async(self, stream):
+        """A wait that timed out (lost peer) leaves 1 + rank in the error slot: raise at the next call."""
+        if self.error_event is not None and self.error_event.query() and int(self.error_host[0]) != 0:
+            raise _cabi.AladError(f"peer exchange: timed out waiting for rank {int(self.error_host[0]) - 1}")
+        self.error_host.copy_(self.error_view, non_blocking=True)
+        self.error_event = torch.cuda.Event()
+        self.error_event.record(stream)
+
+    def close(self):
+        self.win.close()
+
+
+def _caption_exchange(group, world, pad_max, Kp):
+    """The exchange of `group`, (re)built collectively when a call needs larger buffers.  None when peer windows are
+    not available (the caller falls back to NCCL)."""
+    global EXCHANGE
+    key = id(group)
+    xc = _exchanges.get(key)
+    if xc is not None and (xc.pad_max < pad_max or xc.Kp != Kp or xc.world != world):
+        xc.close()
+        xc = None
+        del _exchanges[key]
+    if xc is None:
+        try:
+            xc = _exchanges[key] = _CaptionExchange(group, world, pad_max, Kp)
+        except _cabi.AladError as e:
+            import warnings
+            warnings.warn(f"peer windows unavailable ({e}); the packed captions are exchanged with NCCL all-gathers")
+            EXCHANGE = "nccl"
+            return None
+    return xc
+
+
+def close_exchanges():
+    """Free the peer windows (collective; call before destroying the process group)."""
+    for xc in list(_exchanges.values()):
+        xc.close()
+    _exchanges.clear()
 
 
 # Derived host arrays of a gallery (valid counts, clamp flags) are a function of the python length lists the
@@ -249,6 +334,116 @@ class AlignmentGallery:
                 freed[bsel].record(main)
         return rows
 
+    def _score_phases_peer(self, xc, pb, plans, regions, tiles_dev, n_tiles, n_loc, S, split, dev):
+        """Phase loop with the packed rows replicated by COPY ENGINES through peer windows (peer.py): three streams per
+        rank -- `prep` uploads + packs this rank's share of phase g straight into its slot of the local window,
+        `xchg` pushes that slot into every peer's window and raises their ready flags, the main stream waits for the
+        flags and scores.  Nothing here needs an SM while the scoring kernel of phase g-1 runs, so the exchange of a
+        phase hides behind the previous phase's scoring; buffers alternate (g & 1) and a slot is overwritten only after
+        every peer has acknowledged that it scored the phase that used it."""
+        from . import peer
+        W, r, Kp = self.world, self.rank, xc.Kp
+        main = torch.cuda.current_stream()
+        prep, xchg = xc.prep, xc.xchg
+        prep.wait_stream(main)
+        others = [q for q in range(W) if q != r]
+        for (c0, c1), ((m0, m1), pad) in zip(pb, plans):
+            g = xc.g
+            xc.g += 1
+            b, seq = g & 1, g + 1
+            tl = None
+            if phase_timeline is not None:
+                tl = dict(c0=c0, c1=c1, **{k: torch.cuda.Event(enable_timing=True) for k in ("t0", "packed", "gathered", "s0", "s1")})
+                phase_timeline.append(tl)
+            words_b, caps_b = xc.words[b], xc.caps[b]
+            rows_mine = int(self.nw[m0:m1].sum())
+            with torch.cuda.stream(prep):
+                if xc.freed[b] is not None:
+                    prep.wait_event(xc.freed[b])          # local scoring of phase g-2 has read this buffer
+                if xc.sent[b] is not None:
+                    prep.wait_event(xc.sent[b])           # ... and its slot has left for the peers
+                if tl:
+                    tl["t0"].record(prep)
+                mw, mc = words_b[r * pad:(r + 1) * pad], caps_b[r * pad:(r + 1) * pad]
+                mc.fill_(-1)                              # gap rows are never scored (row_cap -1)
+                self._pack_caption_range(m0, m1, mw, mc, 0, split, dev, item_origin=c0)
+                packed = torch.cuda.Event(enable_timing=tl is not None)
+                packed.record(prep)
+                if tl:
+                    tl["packed"] = packed
+            with torch.cuda.stream(xchg):
+                xchg.wait_event(packed)
+                if g >= 2:                                # every peer has scored phase g-2 out of its buffer b
+                    peer.wait(xc.flag_ptr("ack", b), W, seq - 2, r, xc.error_ptr, xchg)
+                w_off, c_off = xc.off_words[b] + r * pad * Kp * 2, xc.off_caps[b] + r * pad * 4
+                for q in others:
+                    peer.copy(xc.win.ptrs[q] + w_off, xc.win.local + w_off, rows_mine * Kp * 2, xchg)
+                    peer.copy(xc.win.ptrs[q] + c_off, xc.win.local + c_off, pad * 4, xchg)
+                peer.signal([xc.win.ptrs[q] + xc.off_flag("ready", b, r) for q in others], seq, xchg)
+                xc.sent[b] = torch.cuda.Event()
+                xc.sent[b].record(xchg)
+            main.wait_event(packed)
+            peer.wait(xc.flag_ptr("ready", b), W, seq, r, xc.error_ptr, main)
+            if tl:
+                tl["gathered"].record(main)
+                tl["s0"].record(main)
+            if n_loc:
+                words = scoring.Packed(words_b[:W * pad], W * pad, Kp, None, None, caps_b[:W * pad], 1 if split else 0)
+                self._score(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, S[:, c0:c1])
+            if tl:
+                tl["s1"].record(main)
+            xc.freed[b] = torch.cuda.Event()
+            xc.freed[b].record(main)
+            peer.signal([xc.win.ptrs[q] + xc.off_flag("ack", b, r) for q in others], seq, main)
+        xc.check_error_async(main)
+
+    def _score_phases_nccl(self, group, pb, plans, pad_max, Kp, regions, tiles_dev, n_tiles, n_loc, S, split, dev):
+        """Phase loop with an NCCL all-gather of the packed rows.  The all-gather kernel cannot start next to the
+        persistent scoring kernel, so every phase's exchange lands in the gap after the previous phase's scoring
+        (profiles/r02_e2e_timeline.md); kept for process groups without peer access (EXCHANGE = 'nccl')."""
+        import torch.distributed as dist
+        words_buf = [torch.empty((self.world * pad_max, Kp), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        caps_buf = [torch.empty((self.world * pad_max,), dtype=torch.int32, device=dev) for _ in range(2)]
+        mine_w = [torch.empty((pad_max, Kp), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        mine_c = [torch.empty((pad_max,), dtype=torch.int32, device=dev) for _ in range(2)]
+        main = torch.cuda.current_stream()
+        prep = torch.cuda.Stream()
+        prep.wait_stream(main)
+        freed = [None, None]
+        for p, ((c0, c1), ((m0, m1), pad)) in enumerate(zip(pb, plans)):
+            b = p & 1
+            tl = None
+            if phase_timeline is not None:
+                tl = dict(c0=c0, c1=c1, **{k: torch.cuda.Event(enable_timing=True) for k in ("t0", "packed", "gathered", "s0", "s1")})
+                phase_timeline.append(tl)
+            with torch.cuda.stream(prep):
+                if freed[b] is not None:
+                    prep.wait_event(freed[b])
+                if tl:
+                    tl["t0"].record(prep)
+                mw, mc = mine_w[b][:pad], mine_c[b][:pad]
+                mc.fill_(-1)
+                self._pack_caption_range(m0, m1, mw, mc, 0, split, dev, item_origin=c0)
+                if tl:
+                    tl["packed"].record(prep)
+                wa, ca = words_buf[b][:self.world * pad], caps_buf[b][:self.world * pad]
+                dist.all_gather_into_tensor(wa, mw, group=group)      # gap rows are never scored (row_cap -1)
+                dist.all_gather_into_tensor(ca, mc, group=group)
+                ready = torch.cuda.Event(enable_timing=tl is not None)
+                ready.record(prep)
+                if tl:
+                    tl["gathered"] = ready
+            main.wait_event(ready)
+            if tl:
+                tl["s0"].record(main)
+            if n_loc:
+                words = scoring.Packed(wa, self.world * pad, Kp, None, None, ca, 1 if split else 0)
+                self._score(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, S[:, c0:c1])
+            if tl:
+                tl["s1"].record(main)
+            freed[b] = torch.cuda.Event()
+            freed[b].record(main)
+
     def packed_operands(self):
         """Device-resident packed operands of this shard: (words Packed over ALL captions incl. row_item,
         regions Packed over the image block, first packed region row of every local image [int64 numpy]).
@@ -321,8 +516,8 @@ class AlignmentGallery:
         # ---- words: all captions (single rank / device-resident) or this rank's share + all-gather
         if shard_caps:
             # captions are processed in phases; inside a phase every rank uploads + packs its 1/world
-            # share, the packed rows are all-gathered (NVLink) and the phase is scored while the next
-            # phase is being prepared on a side stream
+            # share, the packed rows are replicated on all ranks (NVLink) and the phase is scored while the next
+            # phase is being prepared on side streams
             pb = self._phase_bounds()
             plans = []
             for c0, c1 in pb:
@@ -331,33 +526,11 @@ class AlignmentGallery:
                 pad = ((rows_max + 2 * _cabi.TILE_M - 1) // (2 * _cabi.TILE_M)) * (2 * _cabi.TILE_M)
                 plans.append((spans[self.rank], max(pad, 2 * _cabi.TILE_M)))
             pad_max = max(pad for _, pad in plans)
-            words_buf = [torch.empty((self.world * pad_max, Kp), dtype=torch.bfloat16, device=dev) for _ in range(2)]
-            caps_buf = [torch.empty((self.world * pad_max,), dtype=torch.int32, device=dev) for _ in range(2)]
-            mine_w = [torch.empty((pad_max, Kp), dtype=torch.bfloat16, device=dev) for _ in range(2)]
-            mine_c = [torch.empty((pad_max,), dtype=torch.int32, device=dev) for _ in range(2)]
-            main = torch.cuda.current_stream()
-            prep = torch.cuda.Stream()
-            prep.wait_stream(main)
-            freed = [None, None]
-            for p, ((c0, c1), ((m0, m1), pad)) in enumerate(zip(pb, plans)):
-                b = p & 1
-                with torch.cuda.stream(prep):
-                    if freed[b] is not None:
-                        prep.wait_event(freed[b])
-                    mw, mc = mine_w[b][:pad], mine_c[b][:pad]
-                    mc.fill_(-1)
-                    self._pack_caption_range(m0, m1, mw, mc, 0, split, dev, item_origin=c0)
-                    wa, ca = words_buf[b][:self.world * pad], caps_buf[b][:self.world * pad]
-                    dist.all_gather_into_tensor(wa, mw, group=group)      # gap rows are never scored (row_cap -1)
-                    dist.all_gather_into_tensor(ca, mc, group=group)
-                    ready = torch.cuda.Event()
-                    ready.record(prep)
-                main.wait_event(ready)
-                if n_loc:
-                    words = scoring.Packed(wa, self.world * pad, Kp, None, None, ca, 1 if split else 0)
-                    self._score(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, S[:, c0:c1])
-                freed[b] = torch.cuda.Event()
-                freed[b].record(main)
+            xc = _caption_exchange(group, self.world, pad_max, Kp) if EXCHANGE == "peer" else None
+            if xc is not None:
+                self._score_phases_peer(xc, pb, plans, regions, tiles_dev, n_tiles, n_loc, S, split, dev)
+            else:
+                self._score_phases_nccl(group, pb, plans, pad_max, Kp, regions, tiles_dev, n_tiles, n_loc, S, split, dev)
             self._done(n_loc)
             return S
         else:
@@ -424,9 +597,20 @@ def rank_device(S, npts, img_off=0, n_images_total=None, k=50, group=None, ops=r
     dist_on = group is not None and dist.is_initialized() and dist.get_world_size(group) > 1
     Ni_total = n_images_total if n_images_total is not None else n_loc
     npts = min(npts, Ni_total)
+    marks = {} if rank_timeline is not None and S.is_cuda else None
+
+    def mark(name):
+        if marks is not None:
+            marks[name] = torch.cuda.Event(enable_timing=True)
+            marks[name].record()
+
+    if marks is not None:
+        rank_timeline.append(marks)
+    mark("start")
     # ---------------- i2t: rows (queries = images < npts), gallery = all captions
     q_loc = max(0, min(n_loc, npts - img_off))
     rank_i, top1_i = ops.rank_rows(S[:q_loc], 5, img_off)
+    mark("rank_rows")
     # ---------------- t2i: columns (queries = captions < 5*npts), gallery = all images
     ncq = min(Nc, 5 * npts)
     Sq = S[:, :ncq]
@@ -434,8 +618,10 @@ def rank_device(S, npts, img_off=0, n_images_total=None, k=50, group=None, ops=r
     ops.col_gt(Sq, gt, 5, img_off)
     cs, ci = ops.col_topk(Sq, k, img_off)
     ts, ti = ops.topk_merge(cs, ci)
+    mark("col_gt_topk")
     if not dist_on:
         count = ops.col_count(Sq, gt, 5, img_off)
+        mark("col_count")
         return rank_i, top1_i, count, ts, ti, None
     world = dist.get_world_size(group)
     if bounds is None:
@@ -452,7 +638,9 @@ def rank_device(S, npts, img_off=0, n_images_total=None, k=50, group=None, ops=r
     payload = torch.cat([gt.view(torch.int32), ts_c.view(torch.int32).reshape(-1), ti_c.reshape(-1), tail])
     n_pay = payload.numel()
     gathered = torch.empty((world * n_pay,), dtype=torch.int32, device=S.device)
+    mark("payload")
     dist.all_gather_into_tensor(gathered, payload, group=group)
+    mark("all_gather")
     gathered = gathered.view(world, n_pay)
     o = 0
     gt = gathered[:, o:o + ncq].view(torch.float32).sum(dim=0)
@@ -466,8 +654,11 @@ def rank_device(S, npts, img_off=0, n_images_total=None, k=50, group=None, ops=r
     rank_i = torch.cat([g_tail[r, :bounds[r][1] - bounds[r][0]] for r in range(world)])[:npts]
     top1_i = torch.cat([g_tail[r, per:per + bounds[r][1] - bounds[r][0]] for r in range(world)])[:npts]
     # images ahead of the ground truth: local count against the global gt, summed over the shards
+    mark("merge")
     count = ops.col_count(Sq, gt, 5, img_off)
+    mark("col_count")
     dist.all_reduce(count, group=group)
+    mark("all_reduce")
     # the gathered (images, ms) pairs update the shard balancer identically on every rank (read with the results)
     return rank_i, top1_i, count, ts, ti, g_tail[:, 2 * per:2 * per + 2].view(torch.float32)
 

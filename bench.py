@@ -320,6 +320,8 @@ def main():
                "api": "aladin_b200.evaluation.i2t + t2i (sim_function closure over AlignmentContrastiveLoss('MrSw')), "
                       "pinned host tensors [5*Ni,35,1024] / [Nc,53,1024]",
                "recall_at_1": {"i2t": result["i2t"][0], "t2i": result["t2i"][0]}}
+        if world > 1:
+            e2e["caption_exchange"] = retrieval.EXCHANGE + (" (copy engines through IPC peer windows)" if retrieval.EXCHANGE == "peer" else " all-gather")
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
@@ -375,6 +377,7 @@ def main():
                 "tflops_algorithmic_whole_step": Ni * Nc * FLOP_PER_PAIR(regions, words, d) / (ms_step * 1e-3) / 1e12}
         print(json.dumps(line))
     if world > 1:
+        retrieval.close_exchanges()
         dist.destroy_process_group()
 
 

@@ -486,6 +486,32 @@ int alad_shortlist_scatter(const float* S, int64_t ldS, float* S2, int64_t ld2, 
                            const int32_t* idx, int32_t n_lists, int32_t k, int32_t by_column, int32_t img_off,
                            void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Peer exchange over NVLink (multi-GPU gallery; no reference counterpart: alad/evaluation.py is
+ * single-process).  The packed caption rows a rank prepares are replicated on every rank by COPY ENGINES while the
+ * persistent scoring kernel owns the SMs (an SM-resident collective cannot start next to it).
+ *   alad_peer_alloc / _free     zeroed cudaMalloc buffer (the one exception to "no allocation inside": the memory
+ *                               has to be exportable); *ptr is a device pointer
+ *   alad_peer_export / _open / _close   cudaIpc handle (ALAD_PEER_HANDLE_BYTES, HOST memory) of such a buffer / mapping
+ *                               of another rank's buffer into this process (peer access is enabled on first use)
+ *   alad_peer_copy              device-to-device copy (local or peer) on the stream's copy engine
+ *   alad_peer_signal            after everything enqueued on `stream` so far: *flag_ptrs[q] = value for q < n
+ *                               (flag_ptrs: HOST array of device pointers, normally one slot in each peer's buffer)
+ *   alad_peer_wait              blocks `stream` until flags[q] - value >= 0 for every q < n, q != skip (sequence
+ *                               numbers; wrap-safe); gives up after timeout_ms and stores 1 + q into *error (device)
+ * ------------------------------------------------------------------------------- */
+#define ALAD_MAX_PEERS 32
+#define ALAD_PEER_HANDLE_BYTES 64
+int alad_peer_alloc(void** ptr, int64_t bytes);
+int alad_peer_free(void* ptr);
+int alad_peer_export(const void* ptr, void* handle64);
+int alad_peer_open(const void* handle64, void** ptr);
+int alad_peer_close(void* ptr);
+int alad_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);
+int alad_peer_signal(void* const* flag_ptrs, int32_t n, int32_t value, void* stream);
+int alad_peer_wait(const int32_t* flags, int32_t n, int32_t value, int32_t skip, int64_t timeout_ms, int32_t* error,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,7 +54,7 @@ def build(name, tsan=False):
     return lib
 
 
-FULL_LIBRARY = ["cabi", "pack", "fused", "mrsw_bwd", "losses", "train_step", "distill", "misc_sim", "scan_pool", "rank", "pairs"]
+FULL_LIBRARY = ["cabi", "pack", "fused", "mrsw_bwd", "losses", "train_step", "distill", "misc_sim", "scan_pool", "rank", "pairs", "peer"]
 
 
 def build_library(tsan=False):

@@ -22,7 +22,10 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from aladin_b200 import evaluation, loss as L, retrieval, synth
     ok = True
-    for seed, Ni, d, mr, mw, precision in ((5, 203, 128, 36, 30, "fp32"), (6, 640, 256, 34, 50, "bf16")):
+    # the host-resident sharded path replicates the packed captions through peer windows (copy engines) or NCCL
+    for seed, Ni, d, mr, mw, precision, exchange in ((5, 203, 128, 36, 30, "fp32", "peer"), (6, 640, 256, 34, 50, "bf16", "peer"),
+                                                     (6, 640, 256, 34, 50, "bf16", "nccl"), (8, 900, 64, 34, 50, "bf16", "peer")):
+        retrieval.EXCHANGE = exchange
         images, captions, img_lens, cap_lens = synth.eval_containers(seed, Ni, 71, d, max_regions=mr, max_words=mw)
         ti, tc = torch.from_numpy(images).pin_memory(), torch.from_numpy(captions).pin_memory()
         crit = L.AlignmentContrastiveLoss(aggregation="MrSw")
@@ -37,11 +40,40 @@ def main():
         ri1, t11, rt1, t501 = retrieval.rank_both_directions(S, Ni, k=50, group=None)
         same = (np.array_equal(ri, ri1) and np.array_equal(t1, t11) and np.array_equal(rt, rt1) and np.array_equal(t50, t501)
                 and mi[:5] == retrieval.recall_tuple(ri1) and mt[:5] == retrieval.recall_tuple(rt1))
-        print(f"[rank {rank}/{world}] Ni={Ni} {precision}: sharded == unsharded: {same}; i2t R@1 {mi[0]:.1f} t2i R@1 {mt[0]:.1f}",
-              flush=True)
+        print(f"[rank {rank}/{world}] Ni={Ni} {precision} exchange={retrieval.EXCHANGE}: sharded == unsharded: {same}; "
+              f"i2t R@1 {mi[0]:.1f} t2i R@1 {mt[0]:.1f}", flush=True)
+        ok = ok and retrieval.EXCHANGE == exchange           # a silent fall-back to NCCL is a failure here
         ok = ok and same
+    # the two exchanges deliver the same packed rows into the same layout: the shard's score block must be bit-identical,
+    # and equal to the unsharded block up to the fp32 rounding of a caption's <= 2 partial sums (different tile cuts)
+    for seed, Ni, d, mr, mw in ((7, 1300, 64, 20, 30), (9, 2100, 128, 34, 50)):
+        images, captions, img_lens, cap_lens = synth.eval_containers(seed, Ni, 71, d, max_regions=mr, max_words=mw)
+        ti, tc = torch.from_numpy(images).pin_memory(), torch.from_numpy(captions).pin_memory()
+        blocks = {}
+        for exchange in ("peer", "nccl", "peer"):
+            retrieval.EXCHANGE = exchange
+            gal = retrieval.AlignmentGallery(ti, tc, img_lens, cap_lens, n_images=Ni, img_start=0, img_step=5, precision="bf16",
+                                             world=world, rank=rank, bounds=[retrieval.shard_bounds(Ni, world, r) for r in range(world)])
+            S = gal.scores(group=dist.group.WORLD)
+            torch.cuda.synchronize()
+            ok = ok and retrieval.EXCHANGE == exchange
+            blocks.setdefault(exchange, []).append(S)
+        one = retrieval.AlignmentGallery(ti, tc, img_lens, cap_lens, n_images=Ni, img_start=0, img_step=5, precision="bf16",
+                                         world=1, rank=0).scores()[gal.lo:gal.hi]
+        same = all(torch.equal(blocks["peer"][0], x) for x in blocks["peer"][1:] + blocks["nccl"])
+        close = bool(torch.allclose(blocks["peer"][0], one, rtol=1e-5, atol=1e-5))
+        print(f"[rank {rank}/{world}] Ni={Ni}: peer == nccl bit for bit: {same}; == unsharded block up to rounding: {close}", flush=True)
+        ok = ok and same and close
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    for xc in retrieval._exchanges.values():
+        xc.check_error_async(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        if int(xc.error_host[0]) != 0:
+            print(f"[rank {rank}] peer wait timed out (rank {int(xc.error_host[0]) - 1})", flush=True)
+            sys.exit(1)
+    retrieval.close_exchanges()
     dist.destroy_process_group()
     if int(flag.item()) != 1:
         sys.exit(1)
