@@ -94,12 +94,12 @@ def _find_scorer(fn, probe=None):
     return None
 
 
-def _key(images, captions, img_lens, cap_lens, mode, precision):
+def _key(images, captions, lkey, mode, precision):
     from .gallery import DeviceContainer
     if isinstance(images, DeviceContainer):
         return (id(images), id(captions), images.packed.data.data_ptr(), captions.packed.data.data_ptr(), mode, precision)
     return (images.data_ptr(), captions.data_ptr(), tuple(images.shape), tuple(captions.shape), images._version,
-            captions._version, hash(tuple(img_lens)), hash(tuple(cap_lens)), mode, precision)
+            captions._version, lkey, mode, precision)
 
 
 def _callback_scores(images, captions, img_lens, cap_lens, sim_function, cap_batches):
@@ -165,7 +165,8 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
         mode = "callback"                     # sharding and packed containers exist for the 'MrSw' kernel only
     precision = getattr(scorer, "precision", None) or scoring.get_precision()
     mode_key = mode if scorer is None else f"{mode}:{scorer.aggregation}"
-    key = _key(images, captions, img_lens, cap_lens, mode_key, precision) if mode != "callback" else None
+    lkey = retrieval.lens_key(img_lens, cap_lens) if mode != "callback" else None     # one pass over the python lists per call
+    key = _key(images, captions, lkey, mode_key, precision) if mode != "callback" else None
     if (key is not None and _cache.get("key") == key and _cache["refs"][0]() is images
             and _cache["refs"][1]() is captions):
         return _cache["res"]
@@ -183,7 +184,7 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
     elif mode == "fused":
         world, rank, group = _dist_state()
         gal = retrieval.AlignmentGallery(images, captions, img_lens, cap_lens, n_images=Ni, img_start=0, img_step=5,
-                                         precision=precision, world=world, rank=rank)
+                                         precision=precision, world=world, rank=rank, lkey=lkey)
         S = gal.scores(group=group)
         img_off, bounds = gal.lo, gal.bounds
     elif mode == "block":
@@ -191,7 +192,9 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
     else:
         S = _callback_scores(images, captions, img_lens, cap_lens, sim_function, batches)
     k = min(50, Ni)
-    ri, t1, rt, tk = retrieval.rank_both_directions(S, Ni, img_off=img_off, n_images_total=Ni, k=k, group=group, bounds=bounds)
+    # ranks to the host now; the top-1 / top-50 lists stay on the device until a caller asks for them (return_ranks)
+    ri, t1, rt, tk = retrieval.rank_both_directions(S, Ni, img_off=img_off, n_images_total=Ni, k=k, group=group, bounds=bounds,
+                                                    lists_to_host=False)
     res = dict(S=S, img_off=img_off, world=world, ranks_i2t=ri, top1=t1, ranks_t2i=rt, top50=tk)
     if key is not None:
         # the key holds addresses: a hit is valid only while the very same input objects are alive (a freed
@@ -202,6 +205,13 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
         for obj in (images, captions):       # the block dies with its inputs, not with the next call
             weakref.finalize(obj, _evict, key)
     return res
+
+
+def _lists(res):
+    """(top1, top50) host arrays of a cached block, fetched from the device on first use."""
+    if res.get("lists") is None:
+        res["lists"] = retrieval.lists_host(res["top1"], res["top50"])
+    return res["lists"]
 
 
 def _ndcg(ndcg_scorer, res, npts, fold_index, retrieval_kind):
@@ -234,12 +244,11 @@ def i2t(images, captions, img_lenghts, cap_lenghts, npts=None, return_ranks=Fals
     if npts is None:
         npts = images.shape[0] // 5
     res = _retrieve(images, captions, img_lenghts, cap_lenghts, sim_function, cap_batches)
-    ranks = res["ranks_i2t"][:npts].copy()
-    top1 = res["top1"][:npts].copy()
+    ranks = res["ranks_i2t"][:npts]
     if ndcg_scorer is not None:
         _ndcg(ndcg_scorer, res, npts, fold_index, "sentence")
     metrics = retrieval.recall_tuple(ranks) + (0, 0)
-    return (metrics, (ranks, top1)) if return_ranks else metrics
+    return (metrics, (ranks.copy(), _lists(res)[0][:npts].copy())) if return_ranks else metrics
 
 
 def t2i(images, captions, img_lenghts, cap_lenghts, npts=None, return_ranks=False, ndcg_scorer=None, fold_index=0,
@@ -251,9 +260,9 @@ def t2i(images, captions, img_lenghts, cap_lenghts, npts=None, return_ranks=Fals
     if images.shape[0] // 5 < 50:
         raise ValueError("t2i keeps the 50 best images per caption (evaluation.py:257,308): need >= 50 gallery images")
     res = _retrieve(images, captions, img_lenghts, cap_lenghts, sim_function, im_batches)
-    ranks = res["ranks_t2i"][:5 * npts].copy()
-    top50 = res["top50"][:5 * npts].copy()
+    ranks = res["ranks_t2i"][:5 * npts]
     if ndcg_scorer is not None:
         _ndcg(ndcg_scorer, res, npts, fold_index, "image")
     metrics = retrieval.recall_tuple(ranks) + (0, 0)
-    return (metrics, (ranks, top50)) if return_ranks else metrics
+    # the caller owns what it gets (the block stays cached): copies only when the arrays are asked for (top50: 10 MB at COCO-5k)
+    return (metrics, (ranks.copy(), _lists(res)[1][:5 * npts].copy())) if return_ranks else metrics

@@ -185,13 +185,22 @@ def close_exchanges():
 _META = collections.OrderedDict()
 
 
-def _gallery_meta(img_shape1, cap_shape, img_lens, cap_lens, Ni, img_start, img_step):
+def lens_key(img_lens, cap_lens):
+    """Content key of the two python length lists (0.25 ms per 25 000-entry list: computed once per call and shared by
+    the score-block cache of evaluation.py and the gallery metadata memo)."""
     if isinstance(img_lens, np.ndarray):
         img_lens = img_lens.tolist()
     if isinstance(cap_lens, np.ndarray):
         cap_lens = cap_lens.tolist()
-    key = (len(img_lens), hash(tuple(img_lens)), len(cap_lens), hash(tuple(cap_lens)), img_shape1, tuple(cap_shape), Ni,
-           img_start, img_step)
+    return (len(img_lens), hash(tuple(img_lens)), len(cap_lens), hash(tuple(cap_lens)))
+
+
+def _gallery_meta(img_shape1, cap_shape, img_lens, cap_lens, Ni, img_start, img_step, lkey=None):
+    if isinstance(img_lens, np.ndarray):
+        img_lens = img_lens.tolist()
+    if isinstance(cap_lens, np.ndarray):
+        cap_lens = cap_lens.tolist()
+    key = (lkey or lens_key(img_lens, cap_lens)) + (img_shape1, tuple(cap_shape), Ni, img_start, img_step)
     hit = _META.get(key)
     if hit is not None:
         _META.move_to_end(key)
@@ -234,7 +243,7 @@ class AlignmentGallery:
     i2t reads row 5i, t2i rows 0::5 -- alad/evaluation.py:178,252)."""
 
     def __init__(self, images, captions, img_lens, cap_lens, n_images, img_start=0, img_step=1,
-                 precision=None, world=1, rank=0, caption_chunk=4096, caption_phases=None, bounds=None):
+                 precision=None, world=1, rank=0, caption_chunk=4096, caption_phases=None, bounds=None, lkey=None):
         if not torch.cuda.is_available():
             raise _cabi.AladError("aladin_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         from .gallery import DeviceContainer
@@ -259,7 +268,7 @@ class AlignmentGallery:
         self.caption_chunk = caption_chunk
         self.caption_phases = caption_phases          # None: ramped phases (see _phase_bounds)
         self.R, self.W, self.nr, self.nw, self.clamp = _gallery_meta(
-            images.shape[1], tuple(captions.shape), img_lens, cap_lens, self.Ni, img_start, img_step)
+            images.shape[1], tuple(captions.shape), img_lens, cap_lens, self.Ni, img_start, img_step, lkey)
         self._events = []
 
     def _score(self, words, regions, tiles_dev, n_tiles, n_loc, n_caps, out):
@@ -279,15 +288,19 @@ class AlignmentGallery:
             self._events = []
 
     def _phase_bounds(self):
-        """Caption-column phases of the host-resident multi-rank path: the upload + pack + all-gather of phase p+1
+        """Caption-column phases of the host-resident multi-rank path: the upload + pack + exchange of phase p+1
         hides behind the scoring of phase p, so only phase 0 is exposed -- it is small (Nc/64) and the phases grow
-        by 1.5x (the ratio of scoring time to PCIe time per caption on a B200 box) up to Nc/4."""
+        by 1.5x up to Nc/(2*world).  The cap follows the world size because the PCIe upload of a rank's share runs at a
+        fixed rate while the scoring time shrinks with 1/world: at 8 ranks the two take about as long (30 ms against 36 ms at
+        COCO-5k, profiles/r02_e2e_timeline.md), the pipeline is upload-paced, and whatever is scored after the last
+        upload has landed is exposed -- one Nc/16 phase instead of the Nc/3 one of a fixed Nc/4 cap."""
         Nc = self.Nc
         if self.caption_phases is not None:
             P = max(1, self.caption_phases if Nc >= self.caption_phases * self.world * 64 else 1)
             return [(p * Nc // P, (p + 1) * Nc // P) for p in range(P)]
         if Nc < 64 * self.world * 16:
             return [(0, Nc)]
+        cap = max(Nc // (2 * max(self.world, 2)), 64 * self.world)
         out, c0, size = [], 0, max(Nc // 64, 64 * self.world)
         while c0 < Nc:
             c1 = min(Nc, c0 + int(size))
@@ -295,7 +308,7 @@ class AlignmentGallery:
                 c1 = Nc
             out.append((c0, c1))
             c0 = c1
-            size = min(size * 1.5, max(Nc // 4, 1))
+            size = min(size * 1.5, cap)
         return out
 
     def _pack_caption_range(self, c_lo, c_hi, words_buf, cap_buf, row_base, split, dev, item_origin=0):
@@ -664,16 +677,30 @@ def rank_device(S, npts, img_off=0, n_images_total=None, k=50, group=None, ops=r
 
 
 def rank_both_directions(S, npts, img_off=0, n_images_total=None, k=50, group=None, gather_i2t=True, ops=ranking,
-                         bounds=None):
+                         bounds=None, lists_to_host=True):
     """rank_device + ONE device->host copy.  Returns numpy arrays shaped like the reference's
-    (alad/evaluation.py:166-167,255-256): ranks_i2t[npts], top1[npts], ranks_t2i[5*npts], topk[5*npts, k] (float64)."""
+    (alad/evaluation.py:166-167,255-256): ranks_i2t[npts], top1[npts], ranks_t2i[5*npts], topk[5*npts, k] (float64).
+    lists_to_host=False leaves top1 / topk on the device (int32 tensors; `lists_host` converts them on demand): the
+    reference's callers (alad/test.py:271-276, alad/train.py:504-509) only read the metrics, and topk is 10 MB at COCO-5k."""
     rank_i, top1_i, count, _, ti, timing = rank_device(S, npts, img_off, n_images_total, k, group, ops, bounds)
+    small = (rank_i, count) if not lists_to_host else (rank_i, top1_i, count, ti)
     if timing is None:
-        return _to_host_f64(rank_i, top1_i, count, ti)
-    out = _to_host_f64(rank_i, top1_i, count, ti, timing.reshape(-1))
-    tm = out[4].reshape(-1, 2)
-    balancer.update(tm.shape[0], tm[:, 0], tm[:, 1])
-    return out[:4]
+        out = _to_host_f64(*small)
+    else:
+        out = _to_host_f64(*small, timing.reshape(-1))
+        tm = out[-1].reshape(-1, 2)
+        balancer.update(tm.shape[0], tm[:, 0], tm[:, 1])
+        out = out[:-1]
+    if lists_to_host:
+        return out
+    return out[0], top1_i, out[1], ti
+
+
+def lists_host(top1_dev, topk_dev):
+    """(top1, topk) float64 numpy arrays from the device tensors rank_both_directions(lists_to_host=False) returned."""
+    if isinstance(top1_dev, np.ndarray):
+        return top1_dev, topk_dev
+    return _to_host_f64(top1_dev, topk_dev)
 
 
 def _to_host_f64(*tensors):
@@ -694,12 +721,28 @@ def _to_host_f64(*tensors):
     return tuple(out)
 
 
+def _median_of_counts(ranks):
+    """numpy.median of an array of non-negative INTEGER values (ranks are counts) from a histogram: 0.07 ms instead
+    of the 0.5 ms numpy.partition takes on 25 000 entries.  None when the values are not such integers."""
+    n = ranks.size
+    if n == 0:
+        return None
+    ri = ranks.astype(np.int64)
+    if ri.min() < 0 or ri.max() > 4 * n + 65536 or not np.array_equal(ri, ranks):
+        return None
+    cum = np.cumsum(np.bincount(ri))
+    lo = int(np.searchsorted(cum, (n - 1) // 2, side="right"))
+    hi = int(np.searchsorted(cum, n // 2, side="right"))
+    return 0.5 * (lo + hi)
+
+
 def recall_tuple(ranks):
     """(r1, r5, r10, medr, meanr) exactly as alad/evaluation.py:231-235."""
     n = ranks.size
     r1 = 100.0 * np.count_nonzero(ranks < 1) / n
     r5 = 100.0 * np.count_nonzero(ranks < 5) / n
     r10 = 100.0 * np.count_nonzero(ranks < 10) / n
-    medr = np.floor(np.median(ranks)) + 1
+    med = _median_of_counts(ranks)
+    medr = np.floor(np.median(ranks) if med is None else np.float64(med)) + 1
     meanr = ranks.mean() + 1
     return r1, r5, r10, medr, meanr

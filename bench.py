@@ -314,7 +314,7 @@ def main():
         ms_e2e, _, _, _ = timed(step_e2e, max(2, min(args.steps, 3)), 3)
         lo, hi = retrieval.balancer.bounds(Ni, world, rank)
         h2d = (hi - lo) * (regions + 1) * d * 4 + Nc * (words + 1) * d * 4
-        d2h = (Ni + Nc + Ni + Nc * 50) * 4
+        d2h = (Ni + Nc) * 8          # both directions' ranks as float64; the top-1 / top-50 lists stay on the device until asked for
         e2e = {"value": Ni * Nc / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "api": "aladin_b200.evaluation.i2t + t2i (sim_function closure over AlignmentContrastiveLoss('MrSw')), "

@@ -56,7 +56,7 @@ def test_cache_misses_for_other_objects_with_the_same_key(monkeypatch):
     key_old = ev._cache["key"]
     # a different epoch: new tensors; force the recorded key to equal the new inputs' key (recurring address / version)
     images2, captions2, _, _ = _containers(2)
-    ev._cache["key"] = ev._key(images2, captions2, il, cl, "global", ev.scoring.get_precision())
+    ev._cache["key"] = ev._key(images2, captions2, ev.retrieval.lens_key(il, cl), "global", ev.scoring.get_precision())
     r_new = ev.i2t(images2, captions2, il, cl)
     assert calls == ["scores", "scores"] and key_old != ev._cache["key"]
     assert r_new != r_old
