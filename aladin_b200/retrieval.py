@@ -72,11 +72,12 @@ class ShardBalancer:
 
 
 balancer = ShardBalancer()
-# Device-resident captions: pack everything, then ONE scoring launch.  Packing the second of two column phases on a side
-# stream under the first phase's scoring was measured at N = 2 (profiles/r02_n2_phase_balance_ab.md): the HBM-bound pack
-# kernel crawls next to the persistent tcgen05 kernel (1.3 ms alone, ~12 ms co-scheduled) and the step got 8-10 ms SLOWER
-# (173-177 ms against 166 ms), so the 1.3 ms stay exposed.  True re-enables the two-phase variant for A/B runs.
-DEVICE_PHASES = False
+# Device-resident captions: the HBM-bound pack kernel (1.3 ms for 25 000 captions) crawls next to the persistent tcgen05
+# kernel (~12 ms co-scheduled, profiles/r02_n2_phase_balance_ab.md), so a two-phase split with a large second phase
+# stalls the scoring (measured at N = 2: 173-177 ms against 166 ms).  With RAMPED phases (Nc/32, 3/32, 9/32, the rest) every
+# pack still finishes inside the previous phase's scoring even at the crawling rate, and only the first, 1/32 pack is
+# exposed.  None = on for world >= 4 (where 1.3 ms is 3 % of a rank's step), True / False force it (A/B runs).
+DEVICE_PHASES = None
 # this rank's recent scoring passes, oldest first: (images scored, [(start_event, end_event), ...]).  The exchange of
 # step k ships the newest pass whose events have COMPLETED (normally step k-1: the launches of step k are still running
 # when its payload is assembled) -- never waits, never reads an unfinished event.
@@ -311,6 +312,30 @@ class AlignmentGallery:
             size = min(size * 1.5, cap)
         return out
 
+    def _row_csum(self):
+        """First packed word row of every caption in the canonical (unsharded, unphased) packing."""
+        if getattr(self, "_csum", None) is None:
+            self._csum = np.concatenate([[0], np.cumsum(self.nw, dtype=np.int64)])
+        return self._csum
+
+    def _phase_plans(self):
+        """(phase bounds, per phase (this rank's caption span, padded rows per rank slot, first row inside the slot),
+        largest slot) of the host-resident sharded path: inside a phase every rank uploads + packs its 1/world share.
+        A share starts at row (canonical row of its first caption) mod 256 of its slot, so that the 256-row work units
+        of the scoring kernel cut every caption exactly where the unsharded single launch cuts it: the <= 2 partial sums
+        of an S entry are the same numbers and the scores are bit-identical for any world size and phase split."""
+        unit = 2 * _cabi.TILE_M
+        csum = self._row_csum()
+        pb = self._phase_bounds()
+        plans = []
+        for c0, c1 in pb:
+            spans = [tuple(c0 + x for x in shard_bounds(c1 - c0, self.world, r)) for r in range(self.world)]
+            need = max(int(csum[a] % unit + csum[b] - csum[a]) for a, b in spans)
+            pad = max(((need + unit - 1) // unit) * unit, unit)
+            a = spans[self.rank][0]
+            plans.append((spans[self.rank], pad, int(csum[a] % unit)))
+        return pb, plans, max(pad for _, pad, _ in plans)
+
     def _pack_caption_range(self, c_lo, c_hi, words_buf, cap_buf, row_base, split, dev, item_origin=0):
         """Upload (if on the host) and pack captions [c_lo, c_hi) into rows row_base.. of
         words_buf / cap_buf.  Host sources are double-buffered: the pitched H2D copy of chunk k+1
@@ -347,20 +372,24 @@ class AlignmentGallery:
                 freed[bsel].record(main)
         return rows
 
-    def _score_phases_peer(self, xc, pb, plans, regions, tiles_dev, n_tiles, n_loc, S, split, dev):
+    def _score_phases_peer(self, xc, pb, plans, prep_regions, n_loc, S, split, dev):
         """Phase loop with the packed rows replicated by COPY ENGINES through peer windows (peer.py): three streams per
         rank -- `prep` uploads + packs this rank's share of phase g straight into its slot of the local window,
         `xchg` pushes that slot into every peer's window and raises their ready flags, the main stream waits for the
         flags and scores.  Nothing here needs an SM while the scoring kernel of phase g-1 runs, so the exchange of a
         phase hides behind the previous phase's scoring; buffers alternate (g & 1) and a slot is overwritten only after
-        every peer has acknowledged that it scored the phase that used it."""
+        every peer has acknowledged that it scored the phase that used it.  The image block (`prep_regions`: upload +
+        pack on the main stream) is enqueued after the first phase's caption upload, so that phase's exchange runs
+        while the images cross PCIe."""
         from . import peer
+        regions = tiles_dev = None
+        n_tiles, first = 0, True
         W, r, Kp = self.world, self.rank, xc.Kp
         main = torch.cuda.current_stream()
         prep, xchg = xc.prep, xc.xchg
         prep.wait_stream(main)
         others = [q for q in range(W) if q != r]
-        for (c0, c1), ((m0, m1), pad) in zip(pb, plans):
+        for (c0, c1), ((m0, m1), pad, off) in zip(pb, plans):
             g = xc.g
             xc.g += 1
             b, seq = g & 1, g + 1
@@ -379,7 +408,7 @@ class AlignmentGallery:
                     tl["t0"].record(prep)
                 mw, mc = words_b[r * pad:(r + 1) * pad], caps_b[r * pad:(r + 1) * pad]
                 mc.fill_(-1)                              # gap rows are never scored (row_cap -1)
-                self._pack_caption_range(m0, m1, mw, mc, 0, split, dev, item_origin=c0)
+                self._pack_caption_range(m0, m1, mw, mc, off, split, dev, item_origin=c0)
                 packed = torch.cuda.Event(enable_timing=tl is not None)
                 packed.record(prep)
                 if tl:
@@ -388,13 +417,16 @@ class AlignmentGallery:
                 xchg.wait_event(packed)
                 if g >= 2:                                # every peer has scored phase g-2 out of its buffer b
                     peer.wait(xc.flag_ptr("ack", b), W, seq - 2, r, xc.error_ptr, xchg)
-                w_off, c_off = xc.off_words[b] + r * pad * Kp * 2, xc.off_caps[b] + r * pad * 4
+                w_off, c_off = xc.off_words[b] + (r * pad + off) * Kp * 2, xc.off_caps[b] + r * pad * 4
                 for q in others:
                     peer.copy(xc.win.ptrs[q] + w_off, xc.win.local + w_off, rows_mine * Kp * 2, xchg)
                     peer.copy(xc.win.ptrs[q] + c_off, xc.win.local + c_off, pad * 4, xchg)
                 peer.signal([xc.win.ptrs[q] + xc.off_flag("ready", b, r) for q in others], seq, xchg)
                 xc.sent[b] = torch.cuda.Event()
                 xc.sent[b].record(xchg)
+            if first:
+                regions, tiles_dev, n_tiles = prep_regions()
+                first = False
             main.wait_event(packed)
             peer.wait(xc.flag_ptr("ready", b), W, seq, r, xc.error_ptr, main)
             if tl:
@@ -423,7 +455,7 @@ class AlignmentGallery:
         prep = torch.cuda.Stream()
         prep.wait_stream(main)
         freed = [None, None]
-        for p, ((c0, c1), ((m0, m1), pad)) in enumerate(zip(pb, plans)):
+        for p, ((c0, c1), ((m0, m1), pad, off)) in enumerate(zip(pb, plans)):
             b = p & 1
             tl = None
             if phase_timeline is not None:
@@ -436,7 +468,7 @@ class AlignmentGallery:
                     tl["t0"].record(prep)
                 mw, mc = mine_w[b][:pad], mine_c[b][:pad]
                 mc.fill_(-1)
-                self._pack_caption_range(m0, m1, mw, mc, 0, split, dev, item_origin=c0)
+                self._pack_caption_range(m0, m1, mw, mc, off, split, dev, item_origin=c0)
                 if tl:
                     tl["packed"].record(prep)
                 wa, ca = words_buf[b][:self.world * pad], caps_buf[b][:self.world * pad]
@@ -517,33 +549,30 @@ class AlignmentGallery:
         d = self.captions.shape[2]
         Kp = ((d * (3 if split else 1) + _cabi.TILE_K - 1) // _cabi.TILE_K) * _cabi.TILE_K
         # ---- regions of this image block
-        regions = tiles_dev = None
-        n_tiles = 0
-        if n_loc:
+        def prep_regions():
+            if not n_loc:
+                return None, None, 0
             Lr = 1 + int(nr.max())
             im_dev = _upload_rows(self.images, self.img_start + lo * self.img_step, self.img_step, n_loc, Lr)
-            regions = scoring.pack_tokens(im_dev, nr, slot0=1, mode=2 if split else 0)
+            reg = scoring.pack_tokens(im_dev, nr, slot0=1, mode=2 if split else 0)
             _, table, _ = build_region_tiles(nr, self.clamp[lo:hi])
-            n_tiles = len(table)
-            tiles_dev = scoring._to_dev(table.view(np.int32).reshape(-1), dev) if n_tiles else None
+            return reg, (scoring._to_dev(table.view(np.int32).reshape(-1), dev) if len(table) else None), len(table)
+
+        peer_path = False
+        if shard_caps and EXCHANGE == "peer":
+            # the image block is uploaded AFTER the first caption phase has been enqueued (see _score_phases_peer)
+            pb, plans, pad_max = self._phase_plans()
+            xc = _caption_exchange(group, self.world, pad_max, Kp)
+            peer_path = xc is not None
+        if peer_path:
+            self._score_phases_peer(xc, pb, plans, prep_regions, n_loc, S, split, dev)
+            self._done(n_loc)
+            return S
+        regions, tiles_dev, n_tiles = prep_regions()
         # ---- words: all captions (single rank / device-resident) or this rank's share + all-gather
         if shard_caps:
-            # captions are processed in phases; inside a phase every rank uploads + packs its 1/world
-            # share, the packed rows are replicated on all ranks (NVLink) and the phase is scored while the next
-            # phase is being prepared on side streams
-            pb = self._phase_bounds()
-            plans = []
-            for c0, c1 in pb:
-                spans = [tuple(c0 + x for x in shard_bounds(c1 - c0, self.world, r)) for r in range(self.world)]
-                rows_max = max(int(nw[a:b].sum()) for a, b in spans)
-                pad = ((rows_max + 2 * _cabi.TILE_M - 1) // (2 * _cabi.TILE_M)) * (2 * _cabi.TILE_M)
-                plans.append((spans[self.rank], max(pad, 2 * _cabi.TILE_M)))
-            pad_max = max(pad for _, pad in plans)
-            xc = _caption_exchange(group, self.world, pad_max, Kp) if EXCHANGE == "peer" else None
-            if xc is not None:
-                self._score_phases_peer(xc, pb, plans, regions, tiles_dev, n_tiles, n_loc, S, split, dev)
-            else:
-                self._score_phases_nccl(group, pb, plans, pad_max, Kp, regions, tiles_dev, n_tiles, n_loc, S, split, dev)
+            pb, plans, pad_max = self._phase_plans()
+            self._score_phases_nccl(group, pb, plans, pad_max, Kp, regions, tiles_dev, n_tiles, n_loc, S, split, dev)
             self._done(n_loc)
             return S
         else:
@@ -560,8 +589,9 @@ class AlignmentGallery:
                     bounds.append((c0, min(self.Nc, c0 + size)))
                     c0 += size
                     size = min(chunk, 2 * size)
-            elif self.Nc >= 4096 and DEVICE_PHASES:
-                bounds = [(0, self.Nc // 16), (self.Nc // 16, self.Nc)]   # packing is HBM-bound: 6 % exposed, the rest hidden
+            elif self.Nc >= 4096 and (DEVICE_PHASES if DEVICE_PHASES is not None else self.world >= 4):
+                cuts = [0, self.Nc // 32, self.Nc // 8, 13 * self.Nc // 32, self.Nc]
+                bounds = list(zip(cuts[:-1], cuts[1:]))
             else:
                 bounds = [(0, self.Nc)]
             if len(bounds) == 1 and not on_cpu:
@@ -569,8 +599,10 @@ class AlignmentGallery:
                 self._score(words, regions, tiles_dev, n_tiles, n_loc, self.Nc, S)
                 self._done(n_loc)
                 return S
-            csum = np.concatenate([[0], np.cumsum(nw, dtype=np.int64)])
-            rows_max = max(int(csum[c1] - csum[c0]) for c0, c1 in bounds)
+            # every phase starts at row (canonical first row) mod 256 of its buffer: same cuts as the single launch (see _phase_plans)
+            unit = 2 * _cabi.TILE_M
+            csum = self._row_csum()
+            rows_max = max(int(csum[c0] % unit + csum[c1] - csum[c0]) for c0, c1 in bounds)
             n_buf = 2 if len(bounds) > 1 else 1
             words_buf = [torch.empty((max(rows_max, 1), Kp), dtype=torch.bfloat16, device=dev) for _ in range(n_buf)]
             cap_buf = [torch.empty((max(padded_rows(rows_max), 2 * _cabi.TILE_M),), dtype=torch.int32, device=dev)
@@ -585,7 +617,8 @@ class AlignmentGallery:
                     if freed[b] is not None:
                         prep.wait_event(freed[b])
                     cap_buf[b].fill_(-1)
-                    rows = self._pack_caption_range(c0, c1, words_buf[b], cap_buf[b], 0, split, dev, item_origin=c0)
+                    off = int(csum[c0] % unit)
+                    rows = off + self._pack_caption_range(c0, c1, words_buf[b], cap_buf[b], off, split, dev, item_origin=c0)
                     ready = torch.cuda.Event()
                     ready.record(prep)
                 main.wait_event(ready)

@@ -216,8 +216,8 @@ def main():
     aladin_b200.set_precision(args.precision)
     if os.environ.get("ALAD_NO_BALANCE"):          # diagnostics: equal image blocks
         retrieval.balancer.enabled = False
-    if os.environ.get("ALAD_DEVICE_PHASES"):       # diagnostics: pack the captions in two column phases on a side stream
-        retrieval.DEVICE_PHASES = True
+    if os.environ.get("ALAD_DEVICE_PHASES"):       # diagnostics: force the ramped caption phases of the device-resident path on / off
+        retrieval.DEVICE_PHASES = os.environ["ALAD_DEVICE_PHASES"] not in ("0", "false", "off")
 
     images, captions, im_len, s_len = synth.dense_gallery_device(Ni, Nc, regions, words, d)
     torch.cuda.synchronize()
