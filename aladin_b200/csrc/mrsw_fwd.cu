@@ -482,7 +482,9 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
         }
         tmem_ld_wait();
         tc_fence_before();
-        if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);   // stage may be overwritten
+        // stage may be overwritten.  Every thread arrives for itself: one arrival per warp behind a __syncwarp measured
+        // 1.3-1.9 % SLOWER on the same box (325-327 ms against 321 ms per COCO-5k launch, profiles/r02_scoring_kernel.md)
+        if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         // ---- phase 2: per-caption row sums in a fixed order; warp w owns caption runs w, w+4, ...
         const int* caps = capS + buf * BM;
@@ -576,6 +578,17 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Experiment knobs: compile-time defaults; only a -DALAD_TUNING_ENV build looks at the environment.
+static inline long long tuning_env(const char* name, long long dflt) {
+#ifdef ALAD_TUNING_ENV
+  const char* e = getenv(name);
+  return e ? atoll(e) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
+}
+
 // [rows, Kp] bf16 row-major; box = 64 elements (128 B, one swizzle row) x box_rows.
 static int make_map(CUtensorMap* m, const void* ptr, long long rows, int Kp, int box_rows) {
   EncodeTiledFn fn = encode_fn();
@@ -636,14 +649,7 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   ALAD_REQUIRE(total < (1ll << 31), "alad_mrsw_scores_fwd: too many tiles (%lld)", total);
 
   int cg = a->cta_group;
-  if (cg == 0) {
-    static const int env_cg = [] {
-      const char* e = getenv("ALAD_CTA_GROUP");
-      const int v = e ? atoi(e) : 0;
-      return (v == 1 || v == 2) ? v : 2;
-    }();
-    cg = env_cg;
-  }
+  if (cg == 0) cg = static_cast<int>(tuning_env("ALAD_CTA_GROUP", 2)) == 1 ? 1 : 2;
   ALAD_REQUIRE(cg == 1 || cg == 2, "alad_mrsw_scores_fwd: cta_group must be 0, 1 or 2");
   if (sm_count() < 2) cg = 1;
 
@@ -666,11 +672,10 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
     // COCO-5k shape, n_block = 74 runs ~8 % faster than a 30 MB block of 61 tiles and 25 % faster than
     // 16 tiles (profiles/r01_tile_order_sweep.md).  Pick the largest divisor whose block fits the budget
     // (64 MB by default: beyond ~100 MB the block thrashes the 126 MB L2).
-    // ALAD_L2_BLOCK_MB / ALAD_N_BLOCK override it; the environment is read per call so that one process
-    // can sweep the settings (tools/sweep_tile_order.py).
+    // The knobs below are fixed at their measured defaults; a build with -DALAD_TUNING_ENV reads them from the
+    // environment per call (tools/sweep_tile_order.py), the product build never calls getenv.
     const int units_in_flight = ctas / cg;
-    const char* e = getenv("ALAD_L2_BLOCK_MB");
-    const long long ev = e ? atoll(e) : 0;
+    const long long ev = tuning_env("ALAD_L2_BLOCK_MB", 0);
     const long long budget = (ev > 0 ? ev : 64) << 20;
     const long long tile_bytes = (long long)BN * a->Kp * 2;
     long long nb = 0;
@@ -678,20 +683,17 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
       if (units_in_flight % j == 0 && (units_in_flight / j) * tile_bytes <= budget) nb = units_in_flight / j;
     if (nb < 8 || ev > 0) nb = budget / tile_bytes;    // tiny grids / explicit budget: plain budget rule
     nb = nb < 8 ? 8 : nb;
-    const char* eb = getenv("ALAD_N_BLOCK");            // block size in tiles (experiments)
-    if (eb && atoll(eb) > 0) nb = atoll(eb);
+    const long long eb = tuning_env("ALAD_N_BLOCK", 0);   // block size in tiles (experiments)
+    if (eb > 0) nb = eb;
     p.n_block = (int)(nb > p.n_ntiles ? p.n_ntiles : nb);
     if ((long long)p.n_mtiles * p.n_block >= (1ll << 31)) p.n_block = 8;
-    const char* eh = getenv("ALAD_L2_HINTS");
-    p.l2_hints = eh ? atoi(eh) : 0;
-    // the word-row prefetch (ALAD_L2_PREFETCH=1) is OFF by default: with the 6-stage ring it measured +0.6 % at
-    // 74 tiles / bf16 (-8 % at 148 tiles, -19 % at 37 tiles / 3x split), but with the 4-stage ring the same-box A/B
-    // gives 322-324 ms without it against 337 ms with it (profiles/r01_tile_order_sweep.md section 10)
-    const char* ep = getenv("ALAD_L2_PREFETCH");
-    p.l2_prefetch = ep ? atoi(ep) : 0;
+    p.l2_hints = (int)tuning_env("ALAD_L2_HINTS", 0);
+    // the word-row prefetch is OFF: with the 6-stage ring it measured +0.6 % at 74 tiles / bf16 (-8 % at 148 tiles,
+    // -19 % at 37 tiles / 3x split), but with the 4-stage ring the same-box A/B gives 322-324 ms without it against
+    // 337 ms with it (profiles/r01_tile_order_sweep.md section 10)
+    p.l2_prefetch = (int)tuning_env("ALAD_L2_PREFETCH", 0);
     // resident region K blocks (compile-time Cfg<2>::RES > 0): only where a unit keeps its region tile
-    const char* er = getenv("ALAD_B_RESIDENT");
-    p.b_resident = er ? atoi(er) : (p.n_block > 0 && units_in_flight % p.n_block == 0 ? 1 : 0);
+    p.b_resident = (int)tuning_env("ALAD_B_RESIDENT", p.n_block > 0 && units_in_flight % p.n_block == 0 ? 1 : 0);
   }
 
   cudaLaunchConfig_t cfg = {};

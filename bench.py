@@ -7,7 +7,7 @@
 
 One "step" = one full pass of the hot path over the COCO-5k-shape gallery: pack (normalise +
 bf16) -> fused tcgen05 MrSw scores for all Ni x Nc pairs -> exact i2t / t2i ranks + top-50 ->
-ranks back on the host.  `value` times that with the raw fp32 features resident in HBM;
+ranks back on the host (the top-50 lists stay on the device until a caller asks for them).  `value` times that with the raw fp32 features resident in HBM;
 `e2e` times the public drop-ins (aladin_b200.evaluation.i2t + t2i) on pinned HOST tensors in the
 reference layout, H2D copies inside the timed region.  N > 1 shards the gallery images by
 contiguous blocks (strong scaling of the fixed 5k problem); rank 0 prints one JSON line."""
@@ -258,8 +258,10 @@ def main():
         gal = retrieval.AlignmentGallery(images, captions, im_len, s_len, n_images=Ni, precision=args.precision,
                                          world=world, rank=rank)
         S = gal.scores()
+        # ranks to the host; top-1 / top-50 are computed (and exchanged between the shards) but stay on the device, as in
+        # the public i2t / t2i drop-ins, whose callers read the metrics (alad/test.py:271-276)
         result["out"] = retrieval.rank_both_directions(S, Ni, img_off=gal.lo, n_images_total=Ni, k=50, group=group,
-                                                       bounds=gal.bounds)
+                                                       bounds=gal.bounds, lists_to_host=False)
 
     ms_step, timeline, launches, clocks = timed(step_resident, args.steps, args.warmup)
     shard_balance = None

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_scores_close, load_golden
+from conftest import CANCELLING_FLOOR, assert_scores_close, load_golden
 from oracle import alad_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -136,7 +136,7 @@ def test_cosine_measure_gradient_golden(key, mv):
         im, s = cu(g["im"] * 2.5, True), cu(g["s"], True)
         loss, S = L.ContrastiveLoss(margin=0.2, measure="cosine", max_violation=mv)(im, s, return_similarity_mat=True)
         loss.backward()
-        assert_scores_close(S.detach().cpu().numpy(), g["S_" + key], 1e-4, key)
+        assert_scores_close(S.detach().cpu().numpy(), g["S_" + key], 1e-4, key, floor=CANCELLING_FLOOR)
         np.testing.assert_allclose(loss.item(), g["loss_" + key], rtol=1e-4)
         np.testing.assert_allclose(im.grad.cpu().numpy(), g["dim_" + key], rtol=1e-3, atol=1e-5)
         np.testing.assert_allclose(s.grad.cpu().numpy(), g["ds_" + key], rtol=1e-3, atol=1e-5)
@@ -154,7 +154,7 @@ def test_pooling_mode_gradients_golden(agg):
     crit.precision = "fp32"
     S = crit(im, s, g["im_len"].tolist(), g["s_len"].tolist(), return_loss=False, return_similarity_mat=True)
     (S * cu(g["Gup"])).sum().backward()
-    assert_scores_close(S.detach().cpu().numpy(), g["S_" + agg], 1e-4, agg)
+    assert_scores_close(S.detach().cpu().numpy(), g["S_" + agg], 1e-4, agg, floor=CANCELLING_FLOOR if agg in ("sum", "mean") else 0.01)
     scale = np.abs(g["dim_" + agg]).max()
     np.testing.assert_allclose(im.grad.cpu().numpy(), g["dim_" + agg], rtol=2e-3, atol=2e-5 * max(scale, 1e-3))
     np.testing.assert_allclose(s.grad.cpu().numpy(), g["ds_" + agg], rtol=2e-3, atol=2e-5 * max(scale, 1e-3))

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_scores_close, load_golden
+from conftest import CANCELLING_FLOOR, assert_scores_close, load_golden
 from oracle import alad_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -162,4 +162,4 @@ def test_pooling_modes_vs_oracle_ragged(agg):
                                        aggregation=agg).cpu().numpy()
     ref = O.alignment_scores_small(im, s, im_len, s_len, agg)
     ok = np.isfinite(ref)
-    assert_scores_close(got[ok], ref[ok], FP32_RTOL, agg)
+    assert_scores_close(got[ok], ref[ok], FP32_RTOL, agg, floor=CANCELLING_FLOOR if agg in ("sum", "mean") else 0.01)

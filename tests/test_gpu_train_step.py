@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_scores_close, load_golden
+from conftest import CANCELLING_FLOOR, assert_scores_close, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -67,7 +67,7 @@ def test_fused_losses_match_reference_training_step():
     loss.backward()
     assert aladin_b200.get_precision() == "bf16"                                # the global mode is untouched
     assert_scores_close(S.cpu().numpy(), g["teacher_scores"], 1e-4, "teacher")
-    assert_scores_close(M.cpu().numpy(), g["matching_mat"], 1e-4, "matching")
+    assert_scores_close(M.cpu().numpy(), g["matching_mat"], 1e-4, "matching", floor=CANCELLING_FLOOR)
     np.testing.assert_allclose([lm.item(), la.item(), ld.item(), loss.item()],
                                [g["matching_loss"], g["alignment_loss"], g["distillation_loss"], g["loss"]], rtol=1e-4)
     np.testing.assert_allclose(img_cls.grad.cpu().numpy(), g["d_img_cls"], rtol=1e-3, atol=1e-5)

@@ -68,6 +68,14 @@ def also_block(pk, quick=False):
                      "fwd_frac_of_bf16_burst_peak": flop / t_f / 1e9 / pk["bf16_burst"] if pk.get("bf16_burst") else None,
                      "what": f"matching + MrSw alignment + hinge + ListNet, B={B}, ragged 35x53 slots, d=1024, bf16, "
                              "fused forward_loss path (one native call per direction)"}
+    # ---- config 4 with max_violation=False (alad/loss.py:60-67): dL/dS is dense, the sparse pair-list backward has to
+    # recompute all B^2 pairs on CUDA cores (missing 5: no tensor-core dense-G backward)
+    fwd, fwd_bwd, il, cl = TS.make_step(512, "bf16", fused=True, max_violation=False)
+    with torch.no_grad():
+        t_f = TS.timeit(fwd, iters=20, warm=5)
+    t_fb = TS.timeit(fwd_bwd, iters=10, warm=3)
+    out["config4_train_B512_sum_of_violations"] = {"fwd_ms": t_f, "fwd_bwd_ms": t_fb,
+                                                   "what": "same step with max_violation=False: dense dL/dS backward"}
     import aladin_b200
     aladin_b200.set_precision("bf16")
     # ---- config 2: COCO-1k shape retrieval step

@@ -26,7 +26,7 @@ def timeit(fn, iters=100, warm=10):
     return e0.elapsed_time(e1) / iters
 
 
-def make_step(B, precision, fused=False):
+def make_step(B, precision, fused=False, max_violation=True):
     """(fwd, fwd_bwd, il, cl): the three-criterion training step of alad_model.py:371-428 on synthetic features."""
     im, s, il, cl = synth.raw_batch(9, B, B, 35, 53, 1024, related=0.6)
     r = np.random.RandomState(1)
@@ -38,15 +38,15 @@ def make_step(B, precision, fused=False):
     cap_seq = torch.tensor(s.transpose(1, 0, 2).copy(), device="cuda", requires_grad=True)
     img_cls = torch.tensor(icls, device="cuda", requires_grad=True)
     cap_cls = torch.tensor(ccls, device="cuda", requires_grad=True)
-    mc = L.ContrastiveLoss(margin=0.2, measure="dot", max_violation=True)
-    ac = L.AlignmentContrastiveLoss(margin=0.2, measure="dot", max_violation=True, aggregation="MrSw")
+    mc = L.ContrastiveLoss(margin=0.2, measure="dot", max_violation=max_violation)
+    ac = L.AlignmentContrastiveLoss(margin=0.2, measure="dot", max_violation=max_violation, aggregation="MrSw")
     dl = L.DistillationLoss(mode="listnet")
     aladin_b200.set_precision(precision)
 
     def fwd():
         if fused:       # aladin_b200.alad_model: one native call per direction (the forward_loss call site)
             ml, al, d, _, _ = AM.train_losses(img_cls, cap_cls, img_set.permute(1, 0, 2), cap_seq.permute(1, 0, 2), il, cl,
-                                              margin=0.2, max_violation=True)
+                                              margin=0.2, max_violation=max_violation)
             return al + d + 0.1 * ml
         ml, mm = mc(img_cls, cap_cls, return_similarity_mat=True)
         al, ts = ac(img_set.permute(1, 0, 2), cap_seq.permute(1, 0, 2), il, cl, return_similarity_mat=True)
