@@ -29,6 +29,8 @@ SLOT_ALIGN = 1
 # re-used by ~Nc*K/Ni caption groups, so the block being swept has to stay in the 126 MB L2 next to the streamed words.
 L2_BLOCK_BYTES = 48 << 20
 _GROUPS = {}
+# diagnostics (tools/two_stage_probe.py): when a list, two_stage_retrieval appends (stage name, CUDA event) marks
+stage_timeline = None
 
 
 def _caption_groups(nw):
@@ -143,6 +145,13 @@ def two_stage_retrieval(images, captions, img_lens, cap_lens, shortlist=100, pre
         group = dist.group.WORLD if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
     world = dist.get_world_size(group) if group is not None else 1
     rank = dist.get_rank(group) if group is not None else 0
+    def mark(name):
+        if stage_timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            stage_timeline.append((name, ev))
+
+    mark("start")
     Ni = images.shape[0] // 5
     Nc = captions.shape[0]
     k = min(shortlist, Ni)
@@ -157,18 +166,24 @@ def two_stage_retrieval(images, captions, img_lens, cap_lens, shortlist=100, pre
     ims_g = scoring._require_cuda(images[0::5][lo:hi, 0, :], "images")
     caps_g = scoring._require_cuda(captions[:, 0, :], "captions")
     dev = caps_g.device
+    mark("gallery")
     M = scoring.dot_scores(ims_g, caps_g, precision="fp32")                 # [n_loc, Nc]
+    mark("stage1_gemm")
     rank1_i2t, _, rank1_t2i, _, short_t2i, _ = retrieval.rank_device(M, Ni, img_off=lo, n_images_total=Ni, k=k, group=group,
                                                                      bounds=gal.bounds)
     short_t2i = short_t2i.contiguous()                                      # [Nc, k] global image ids, best first
+    mark("stage1_rank_t2i_lists")
     Mt = scoring.dot_scores(caps_g, ims_g, precision="fp32")                # [Nc, n_loc] (columns = local images)
     cs, ci = ranking.col_topk(Mt, kc)
     _, short_i2t = ranking.topk_merge(cs, ci)
     short_i2t = short_i2t.contiguous()                                      # [n_loc, kc] caption ids per local image
+    mark("stage1_i2t_lists")
     # ---- stage 2: alignment scores of the shortlisted pairs only
     words, regions, region_row_off = gal.packed_operands()
+    mark("pack_tokens")
     nr, nw, clamp = gal.nr[lo:hi], gal.nw, gal.clamp[lo:hi]
     S, n_ptiles = pair_scores(words, regions, region_row_off, nr, clamp, nw, short_t2i, short_i2t, lo)
+    mark("pair_tiles_and_scores")
     nr_d, nw_d = scoring._to_dev_group([np.asarray(nr, np.int32), np.asarray(nw, np.int32)], dev)
     sc_t2i = gather_list_scores(S, short_t2i, True, lo, nr_d, nw_d)         # 0 where the image is another shard's
     if world > 1:
@@ -185,7 +200,9 @@ def two_stage_retrieval(images, captions, img_lens, cap_lens, shortlist=100, pre
         r2_i2t = torch.cat([allr[r * per:r * per + (b - a)] for r, (a, b) in enumerate(gal.bounds)])
     else:
         r2_i2t = r2_i2t_loc
+    mark("rerank")
     ri, rt = retrieval._to_host_f64(r2_i2t, r2_t2i)
+    mark("to_host")
     out = (retrieval.recall_tuple(ri), retrieval.recall_tuple(rt))
     if return_details:
         return out, dict(ranks_i2t=ri, ranks_t2i=rt, order_t2i=order_t2i, order_i2t=order_i2t, short_t2i=short_t2i,

@@ -64,6 +64,12 @@ def measure(Ni, Nc, K, world=1, steps=5, warmup=2, regions=34, words=50, d=1024)
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # one more call with stage marks
+    two_stage.stage_timeline = []
+    step()
+    torch.cuda.synchronize()
+    tl, two_stage.stage_timeline = two_stage.stage_timeline, None
+    stages = {b[0]: round(a[1].elapsed_time(b[1]), 3) for a, b in zip(tl[:-1], tl[1:])}
     (m_i2t, m_t2i), det = out["res"]
     n_tiles = int(det["n_ptiles"].item()) if det["n_ptiles"] is not None else 0
     pairs = Ni * min(K, Nc) + Nc * min(K, Ni)
@@ -74,7 +80,7 @@ def measure(Ni, Nc, K, world=1, steps=5, warmup=2, regions=34, words=50, d=1024)
             "ms_per_call": ms, "shortlisted_pairs": pairs, "pairs_per_s": pairs / (ms * 1e-3),
             "pair_kernel_ms": k_ms, "pair_tiles_rank0": n_tiles, "slots_per_tile": slots,
             "pair_kernel_issued_tflops": flop_issued / (k_ms * 1e-3) / 1e12 if k_ms else None,
-            "algorithmic_flop": pairs * 2.0 * regions * words * d,
+            "algorithmic_flop": pairs * 2.0 * regions * words * d, "stage_ms": stages,
             "recall_at_1": {"i2t": m_i2t[0], "t2i": m_t2i[0]}}
 
 
