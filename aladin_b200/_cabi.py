@@ -28,7 +28,7 @@ class MrswFwdArgs(C.Structure):
         ("Kp", C.c_int32), ("row_cap", C.c_void_p), ("ntiles", C.c_void_p), ("n_ntiles", C.c_int32),
         ("S", C.c_void_p), ("ldS", C.c_int64), ("Ni", C.c_int32), ("Nc", C.c_int32),
         ("epilogue", C.c_int32), ("num_ctas", C.c_int32), ("cta_group", C.c_int32),
-        ("transpose_out", C.c_int32),
+        ("transpose_out", C.c_int32), ("accumulate", C.c_int32),
     ]
 
 
@@ -164,6 +164,10 @@ PROTOTYPES = {
     "alad_peer_copy": (C.c_int, [_P, _P, _I64, _P]),
     "alad_peer_signal": (C.c_int, [_P, _I32, _I32, _P]),
     "alad_peer_wait": (C.c_int, [_P, _I32, _I32, _I32, _I64, _P, _P]),
+    "alad_host_atomic_add": (C.c_int64, [_P, _I64]),
+    "alad_host_atomic_cas": (C.c_int32, [_P, _I64, _I64]),
+    "alad_host_atomic_load": (C.c_int64, [_P]),
+    "alad_host_atomic_store": (None, [_P, _I64]),
 }
 
 _lib = None

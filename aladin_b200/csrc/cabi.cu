@@ -24,7 +24,14 @@ int sm_count() {
 
 }  // namespace alad
 
-extern "C" int alad_abi_version(void) { return 3; }
+extern "C" int alad_abi_version(void) { return 4; }
+
+extern "C" int64_t alad_host_atomic_add(int64_t* p, int64_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+extern "C" int32_t alad_host_atomic_cas(int64_t* p, int64_t expected, int64_t desired) {
+  return __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST) ? 1 : 0;
+}
+extern "C" int64_t alad_host_atomic_load(const int64_t* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+extern "C" void alad_host_atomic_store(int64_t* p, int64_t v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
 extern "C" const char* alad_last_error(void) { return alad::error_buffer(); }
 
 extern "C" int alad_h2d_2d(void* dst, int64_t dst_pitch, const void* src_host, int64_t src_pitch, int64_t width_bytes,

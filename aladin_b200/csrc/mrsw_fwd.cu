@@ -618,8 +618,9 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
                    a->n_region_rows < (1ll << 31),
                "alad_mrsw_scores_fwd: bad row counts");
   ALAD_REQUIRE(a->epilogue == 0 || a->epilogue == 1, "alad_mrsw_scores_fwd: unknown epilogue %d", a->epilogue);
+  ALAD_REQUIRE(a->accumulate == 0 || (a->accumulate == 1 && a->epilogue == 0), "alad_mrsw_scores_fwd: accumulate needs epilogue 0");
   cudaStream_t st = as_stream(stream);
-  if (a->Ni > 0 && a->Nc > 0) {
+  if (a->Ni > 0 && a->Nc > 0 && !a->accumulate) {
     if (a->ldS == out_cols) {
       ALAD_CUDA(cudaMemsetAsync(a->S, 0, sizeof(float) * (size_t)out_rows * (size_t)out_cols, st));
     } else {

@@ -76,8 +76,10 @@ balancer = ShardBalancer()
 # kernel (~12 ms co-scheduled, profiles/r02_n2_phase_balance_ab.md), so a two-phase split with a large second phase
 # stalls the scoring (measured at N = 2: 173-177 ms against 166 ms).  With RAMPED phases (Nc/32, 3/32, 9/32, the rest) every
 # pack still finishes inside the previous phase's scoring even at the crawling rate, and only the first, 1/32 pack is
-# exposed.  None = on for world >= 4 (where 1.3 ms is 3 % of a rank's step), True / False force it (A/B runs).
-DEVICE_PHASES = None
+# exposed.  Measured at N = 8 (profiles/r02_n8_device_phases_ab.md): 45.2 ms per step with the four launches against
+# 43.6 ms with one pack + one launch -- the first launch still starts 1.7-2.0 ms into the step (host enqueue, not the pack,
+# sets that), and the later packs finish only just inside the previous launch.  Off; True enables it for A/B runs.
+DEVICE_PHASES = False
 # this rank's recent scoring passes, oldest first: (images scored, [(start_event, end_event), ...]).  The exchange of
 # step k ships the newest pass whose events have COMPLETED (normally step k-1: the launches of step k are still running
 # when its payload is assembled) -- never waits, never reads an unfinished event.
@@ -99,6 +101,46 @@ def _take_timing():
         return 0.0, 0.0
     n, ev = best
     return float(n), float(sum(a.elapsed_time(b) for a, b in ev))
+
+
+# Cross-GPU work pool of the device-resident sharded pass (steal.py): the last POOL_TAIL of every rank's word units is cut
+# into POOL_CHUNKS chunks that any rank may score into the owner's block over NVLink.  False: static blocks only.
+# Chunk sizes decrease linearly (12 : 11 : ... : 1 of the tail): a rank keeps two launches queued, so the residual
+# imbalance is about two of the LAST chunks (0.2 % of a rank's work each), while the early chunks stay large.
+POOL = True
+POOL_TAIL = 0.16
+POOL_CHUNKS = 12
+_pools = {}
+
+
+def pool_cuts(n_units):
+    """Word-unit boundaries of the tail chunks: [u_main, ..., n_units], sizes decreasing linearly, every chunk >= 1 unit."""
+    tail = int(round(n_units * POOL_TAIL))
+    C = max(1, min(POOL_CHUNKS, tail))
+    if n_units < 16 or tail < 1:
+        return [0, n_units]                      # too small to split: one chunk = everything
+    w = np.arange(C, 0, -1, dtype=np.float64)
+    sizes = np.maximum(1, np.floor(w / w.sum() * tail)).astype(np.int64)
+    sizes[0] += tail - int(sizes.sum())           # rounding goes to the first (largest) chunk
+    if sizes[0] < 1:
+        return [n_units - C] + [n_units - C + k + 1 for k in range(C)]
+    cuts = [n_units - tail]
+    for sz in sizes:
+        cuts.append(cuts[-1] + int(sz))
+    return cuts
+
+
+def _work_pool(group, rows, Nc):
+    from . import steal
+    key = id(group)
+    pool = _pools.get(key)
+    if pool is not None and not pool.fits(rows, Nc):
+        pool.close()
+        del _pools[key]
+        pool = None
+    if pool is None:
+        pool = _pools[key] = steal.WorkPool(group, rows, Nc)
+    return pool
 
 
 # How the packed caption rows of a phase reach all ranks when the captions live on the host (every rank uploads and
@@ -179,6 +221,9 @@ def close_exchanges():
     for xc in list(_exchanges.values()):
         xc.close()
     _exchanges.clear()
+    for pool in list(_pools.values()):
+        pool.close()
+    _pools.clear()
 
 
 # Derived host arrays of a gallery (valid counts, clamp flags) are a function of the python length lists the
@@ -264,6 +309,11 @@ class AlignmentGallery:
         self.img_start, self.img_step = img_start, img_step
         self.world, self.rank = world, rank
         # image blocks of all ranks: equal blocks for a single rank, speed-weighted ones otherwise (ShardBalancer)
+        # the work pool evens out the ranks dynamically: equal blocks; otherwise speed-weighted ones (ShardBalancer)
+        pooled = POOL and world > 1 and bounds is None and not self.prepacked and images.is_cuda and captions.is_cuda
+        self.equal_blocks = pooled
+        if pooled:
+            bounds = [shard_bounds(self.Ni, world, r) for r in range(world)]
         self.bounds = bounds if bounds is not None else balancer.all_bounds(self.Ni, world)
         self.lo, self.hi = self.bounds[rank]
         self.caption_chunk = caption_chunk
@@ -371,6 +421,56 @@ class AlignmentGallery:
                 freed[bsel] = torch.cuda.Event()
                 freed[bsel].record(main)
         return rows
+
+    def _scores_pooled(self, group, split, dev):
+        """Device-resident sharded pass under the cross-GPU work pool (steal.py): every rank packs ALL regions (0.35 GB
+        at COCO-5k, 0.2 ms) and all captions, scores the main part of its own block with one launch and the tail in
+        chunks; idle ranks take chunks of the rank with the most left and add them into its block over NVLink."""
+        from . import steal
+        from .tiling import exclusive_cumsum
+        W, r = self.world, self.rank
+        Nc, nw = self.Nc, self.nw
+        rows_max = max(b - a for a, b in self.bounds)
+        pool = _work_pool(group, rows_max, Nc)
+        n_loc = self.hi - self.lo
+        blk = pool.block(n_loc)
+        # ---- operands: all regions, all words
+        Lr = 1 + int(self.nr.max()) if self.Ni else 1
+        im_dev = _upload_rows(self.images, self.img_start, self.img_step, self.Ni, Lr)
+        regions = scoring.pack_tokens(im_dev, self.nr, slot0=1, mode=2 if split else 0)
+        roff, _ = exclusive_cumsum(self.nr)
+        roff = np.concatenate([roff, [regions.n_rows]])
+        tables, spans = [], []
+        for lo, hi in self.bounds:
+            _, table, _ = build_region_tiles(self.nr[lo:hi], self.clamp[lo:hi])
+            spans.append((sum(len(t) for t in tables), len(table)))
+            tables.append(table)
+        flat = np.concatenate([t.reshape(-1) for t in tables]) if sum(len(t) for t in tables) else np.zeros(1, np.uint32)
+        tiles_all = scoring._to_dev(flat.view(np.int32), dev)
+        words = scoring.pack_tokens(self.captions, nw, slot0=1, mode=1 if split else 0, want_row_item=True)
+        n_rows, Kp = words.n_rows, words.Kp
+        unit = 2 * _cabi.TILE_M
+        n_units = (n_rows + unit - 1) // unit
+        cuts = pool_cuts(n_units)
+        C, u_main = len(cuts) - 1, cuts[0]
+
+        def launch(owner, u0, u1):
+            lo, hi = self.bounds[owner]
+            t0, nt = spans[owner]
+            r0, r1 = u0 * unit, min(u1 * unit, n_rows)
+            if hi <= lo or nt == 0 or r1 <= r0:
+                return
+            w = scoring.Packed(words.data[r0:r1], r1 - r0, Kp, None, None, words.row_item[r0:u1 * unit], words.mode)
+            g = scoring.Packed(regions.data[int(roff[lo]):int(roff[hi])], int(roff[hi] - roff[lo]), Kp, None, None, None, regions.mode)
+            scoring.mrsw_scores_packed(w, g, tiles_all[t0 * _cabi.NTILE_WORDS:], nt, hi - lo, Nc, accumulate=True,
+                                       out_ptr=pool.win.ptrs[owner], timeline_nc=Nc * (r1 - r0) / max(n_rows, 1))
+
+        def zero_event():
+            blk.zero_()
+            return steal._cuda_event()
+
+        steal.run(pool, C, lambda: launch(r, 0, u_main), lambda owner, c: launch(owner, cuts[c], cuts[c + 1]), n_loc, zero_event)
+        return blk.clone()
 
     def _score_phases_peer(self, xc, pb, plans, prep_regions, n_loc, S, split, dev):
         """Phase loop with the packed rows replicated by COPY ENGINES through peer windows (peer.py): three streams per
@@ -543,6 +643,9 @@ class AlignmentGallery:
             self._done(n_loc)
             return S
         shard_caps = (group is not None and self.world > 1 and not self.captions.is_cuda and dist.is_initialized())
+        if (POOL and group is not None and self.world > 1 and dist.is_initialized() and self.captions.is_cuda
+                and self.images.is_cuda and self.Nc > 0 and self.equal_blocks):
+            return self._scores_pooled(group, split, dev)
         if (n_loc == 0 and not shard_caps) or self.Nc == 0:
             return S
         nr, nw = self.nr[lo:hi], self.nw
@@ -589,7 +692,7 @@ class AlignmentGallery:
                     bounds.append((c0, min(self.Nc, c0 + size)))
                     c0 += size
                     size = min(chunk, 2 * size)
-            elif self.Nc >= 4096 and (DEVICE_PHASES if DEVICE_PHASES is not None else self.world >= 4):
+            elif self.Nc >= 4096 and DEVICE_PHASES:
                 cuts = [0, self.Nc // 32, self.Nc // 8, 13 * self.Nc // 32, self.Nc]
                 bounds = list(zip(cuts[:-1], cuts[1:]))
             else:

@@ -161,27 +161,34 @@ def pack_tokens(x, counts, *, slot0, mode=0, normalize=True, eps=1e-12, want_row
     return Packed(data, n_rows, Kp, counts, row_off, row_item, mode)
 
 
-def mrsw_scores_packed(words, regions, tiles_dev, n_tiles, Ni, Nc, out=None, num_ctas=0, cta_group=0):
-    """S[Ni,Nc] from packed operands (see alad_mrsw_scores_fwd)."""
+def mrsw_scores_packed(words, regions, tiles_dev, n_tiles, Ni, Nc, out=None, num_ctas=0, cta_group=0, accumulate=False,
+                       out_ptr=None, timeline_nc=None):
+    """S[Ni,Nc] from packed operands (see alad_mrsw_scores_fwd).  accumulate: add onto a matrix the caller zeroed;
+    out_ptr: raw device address of a dense [Ni, Nc] fp32 matrix instead of `out` (another GPU's block through a
+    peer mapping)."""
     lib = _cabi.lib()
     assert words.Kp == regions.Kp
     dev = words.data.device
-    if out is None:
-        out = torch.empty((Ni, Nc), dtype=torch.float32, device=dev)
-    assert out.shape == (Ni, Nc) and out.dtype == torch.float32 and out.stride(1) == 1
+    if out_ptr is None:
+        if out is None:
+            out = torch.empty((Ni, Nc), dtype=torch.float32, device=dev)
+        assert out.shape == (Ni, Nc) and out.dtype == torch.float32 and out.stride(1) == 1
+        s_ptr, s_ld = out.data_ptr(), (out.stride(0) if Ni > 1 else max(out.stride(0), Nc))
+    else:
+        s_ptr, s_ld = out_ptr, Nc
     a = _cabi.MrswFwdArgs(
         words=words.data.data_ptr(), n_word_rows=words.n_rows, regions=regions.data.data_ptr(),
         n_region_rows=regions.n_rows, Kp=words.Kp, row_cap=words.row_item.data_ptr(),
-        ntiles=tiles_dev.data_ptr() if n_tiles else None, n_ntiles=n_tiles, S=out.data_ptr(),
-        ldS=out.stride(0) if Ni > 1 else max(out.stride(0), Nc), Ni=Ni, Nc=Nc, epilogue=0, num_ctas=num_ctas,
-        cta_group=cta_group, transpose_out=0)
+        ntiles=tiles_dev.data_ptr() if n_tiles else None, n_ntiles=n_tiles, S=s_ptr,
+        ldS=s_ld, Ni=Ni, Nc=Nc, epilogue=0, num_ctas=num_ctas,
+        cta_group=cta_group, transpose_out=0, accumulate=1 if accumulate else 0)
     if kernel_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _cabi.check(lib.alad_mrsw_scores_fwd(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_scores_fwd")
     if kernel_timeline is not None:
         e1.record()
-        kernel_timeline.append((e0, e1, Ni, Nc, words.Kp))
+        kernel_timeline.append((e0, e1, Ni, Nc if timeline_nc is None else timeline_nc, words.Kp))   # timeline_nc: captions' worth of rows of a partial launch
     return out
 
 

@@ -214,6 +214,8 @@ def main():
     import aladin_b200
     from aladin_b200 import _cabi, evaluation, loss as L, retrieval, scoring, synth
     aladin_b200.set_precision(args.precision)
+    if os.environ.get("ALAD_NO_POOL"):             # diagnostics: static image blocks, no cross-GPU work pool
+        retrieval.POOL = False
     if os.environ.get("ALAD_NO_BALANCE"):          # diagnostics: equal image blocks
         retrieval.balancer.enabled = False
     if os.environ.get("ALAD_DEVICE_PHASES"):       # diagnostics: force the ramped caption phases of the device-resident path on / off
@@ -257,7 +259,7 @@ def main():
     def step_resident():
         gal = retrieval.AlignmentGallery(images, captions, im_len, s_len, n_images=Ni, precision=args.precision,
                                          world=world, rank=rank)
-        S = gal.scores()
+        S = gal.scores(group=group)
         # ranks to the host; top-1 / top-50 are computed (and exchanged between the shards) but stay on the device, as in
         # the public i2t / t2i drop-ins, whose callers read the metrics (alad/test.py:271-276)
         result["out"] = retrieval.rank_both_directions(S, Ni, img_off=gal.lo, n_images_total=Ni, k=50, group=group,
@@ -267,7 +269,10 @@ def main():
     shard_balance = None
     if world > 1:
         sp = retrieval.balancer.speed.get(world)
-        shard_balance = {"image_blocks": retrieval.balancer.all_bounds(Ni, world), "relative_speed": sp.tolist() if sp is not None else None,
+        pool = next(iter(retrieval._pools.values()), None)
+        shard_balance = {"work_pool": ({"tail_fraction": retrieval.POOL_TAIL, "chunks_per_rank": retrieval.POOL_CHUNKS, "chunk_sizes": "decreasing linearly",
+                                        "chunks_rank0_own_vs_taken_from_others": dict(pool.stats)} if pool else None),
+                         "image_blocks": retrieval.balancer.all_bounds(Ni, world), "relative_speed": sp.tolist() if sp is not None else None,
                          "last_gathered_images_ms": retrieval.balancer.last,
                          "what": "image blocks sized by every rank's measured scoring speed (retrieval.ShardBalancer)"}
     value = Ni * Nc / (ms_step * 1e-3)

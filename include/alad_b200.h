@@ -120,6 +120,9 @@ typedef struct alad_mrsw_fwd_args {
                                     2 = CTA pair (tcgen05 cta_group::2) per 256x240 tile       */
   int32_t transpose_out;         /* 1: write S[word item, region item] (S is [Nc, ldS]); used for the
                                     'MwSr' pooling, which is MrSw with the two token sets swapped */
+  int32_t accumulate;            /* epilogue 0 only.  0: S is zeroed here first; 1: the launch ADDS its partial sums onto S
+                                    (the caller zeroed it): several launches -- also from other GPUs, through a peer
+                                    mapping of S -- each score a range of word rows of the same block (ABI >= 4) */
 } alad_mrsw_fwd_args;
 int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream);
 
@@ -511,6 +514,16 @@ int alad_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);
 int alad_peer_signal(void* const* flag_ptrs, int32_t n, int32_t value, void* stream);
 int alad_peer_wait(const int32_t* flags, int32_t n, int32_t value, int32_t skip, int64_t timeout_ms, int32_t* error,
                    void* stream);
+
+/* Host-side atomics on a word of HOST memory shared by the ranks of one box (a /dev/shm mapping): the claim / done
+ * counters of the cross-GPU work pool (aladin_b200/steal.py).  No CUDA work.
+ *   alad_host_atomic_add   returns the value before the addition
+ *   alad_host_atomic_cas   returns 1 when *p was `expected` and has been replaced by `desired`
+ *   alad_host_atomic_load / _store   sequentially consistent */
+int64_t alad_host_atomic_add(int64_t* p, int64_t v);
+int32_t alad_host_atomic_cas(int64_t* p, int64_t expected, int64_t desired);
+int64_t alad_host_atomic_load(const int64_t* p);
+void alad_host_atomic_store(int64_t* p, int64_t v);
 
 #ifdef __cplusplus
 }

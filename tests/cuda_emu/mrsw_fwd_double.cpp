@@ -37,7 +37,8 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void*) {
   ALAD_REQUIRE(a->Kp > 0 && a->Kp % ALAD_TILE_K == 0, "alad_mrsw_scores_fwd: Kp=%d must be a positive multiple of %d", a->Kp,
                ALAD_TILE_K);
   ALAD_REQUIRE(a->epilogue == 0 || a->epilogue == 1, "alad_mrsw_scores_fwd: unknown epilogue %d", a->epilogue);
-  for (int r = 0; r < out_rows; ++r) memset(a->S + (long long)r * a->ldS, 0, sizeof(float) * (size_t)out_cols);
+  if (!a->accumulate)
+    for (int r = 0; r < out_rows; ++r) memset(a->S + (long long)r * a->ldS, 0, sizeof(float) * (size_t)out_cols);
   if (a->n_word_rows == 0 || a->n_region_rows == 0 || a->n_ntiles == 0 || a->Ni == 0 || a->Nc == 0) return ALAD_OK;
   ALAD_REQUIRE(a->words && a->regions && a->ntiles, "alad_mrsw_scores_fwd: NULL operand");
   ALAD_REQUIRE(a->epilogue == 1 || a->row_cap, "alad_mrsw_scores_fwd: NULL row_cap");

@@ -22,7 +22,7 @@ def test_header_symbols_are_exported(built_lib):
     lib = _cabi.lib()
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by libalad_b200.so"
-    assert lib.alad_abi_version() == 3
+    assert lib.alad_abi_version() == 4
 
 
 def test_kernels_are_blackwell_native(built_lib):

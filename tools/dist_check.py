@@ -64,6 +64,28 @@ def main():
         close = bool(torch.equal(blocks["peer"][0], one))        # shares start at their canonical row modulo the 256-row work unit
         print(f"[rank {rank}/{world}] Ni={Ni}: peer == nccl bit for bit: {same}; == unsharded block bit for bit: {close}", flush=True)
         ok = ok and same and close
+    # device-resident gallery under the cross-GPU work pool (steal.py): chunks of a rank's block may be scored by
+    # another GPU and added into the owner's block over NVLink -- the block must equal the unsharded one bit for bit
+    for seed, Ni, d, mr, mw in ((10, 1500, 128, 34, 50), (11, 700, 64, 20, 30)):
+        images, captions, img_lens, cap_lens = synth.eval_containers(seed, Ni, 71, d, max_regions=mr, max_words=mw)
+        ti, tc = torch.from_numpy(images[0::5].copy()).cuda(), torch.from_numpy(captions).cuda()
+        il = img_lens[0::5]
+        one = retrieval.AlignmentGallery(ti, tc, il, cap_lens, n_images=Ni, precision="bf16", world=1, rank=0).scores()
+        for use_pool in (True, False, True):
+            retrieval.POOL = use_pool
+            gal = retrieval.AlignmentGallery(ti, tc, il, cap_lens, n_images=Ni, precision="bf16", world=world, rank=rank)
+            S = gal.scores(group=dist.group.WORLD)
+            out = retrieval.rank_both_directions(S, Ni, img_off=gal.lo, n_images_total=Ni, k=50, group=dist.group.WORLD,
+                                                 bounds=gal.bounds)
+            torch.cuda.synchronize()
+            same = bool(torch.equal(S, one[gal.lo:gal.hi]))
+            ref = retrieval.rank_both_directions(one, Ni, k=50, group=None)
+            same_ranks = all(np.array_equal(a, b) for a, b in zip(out, ref))
+            pool = next(iter(retrieval._pools.values()), None)
+            print(f"[rank {rank}/{world}] Ni={Ni} device-resident, pool={use_pool}: block == unsharded bit for bit: {same}; "
+                  f"ranks equal: {same_ranks}; chunks own/taken so far: {pool.stats if pool else None}", flush=True)
+            ok = ok and same and same_ranks
+        retrieval.POOL = True
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     torch.cuda.synchronize()

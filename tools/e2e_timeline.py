@@ -27,8 +27,9 @@ def main():
     # ---- the device-resident step of bench.py (`value`): pack + scores + ranking exchange + results to the host
     def step_resident():
         gal = retrieval.AlignmentGallery(images, captions, im_len, s_len, n_images=Ni, precision="bf16", world=world, rank=rank)
-        S = gal.scores()
-        return retrieval.rank_both_directions(S, Ni, img_off=gal.lo, n_images_total=Ni, k=50, group=group, bounds=gal.bounds)
+        S = gal.scores(group=group)
+        return retrieval.rank_both_directions(S, Ni, img_off=gal.lo, n_images_total=Ni, k=50, group=group, bounds=gal.bounds,
+                                              lists_to_host=False)
 
     from aladin_b200 import scoring
     for _ in range(4):
@@ -44,7 +45,7 @@ def main():
         r1.record()
         torch.cuda.synchronize()
         marks = retrieval.rank_timeline[0]
-        k0, k1 = scoring.kernel_timeline[0][0], scoring.kernel_timeline[0][1]
+        k0, k1 = scoring.kernel_timeline[0][0], scoring.kernel_timeline[-1][1]
         res_rows.append({"step_ms": round(r0.elapsed_time(r1), 3), "kernel_start": round(r0.elapsed_time(k0), 3),
                          "kernel_end": round(r0.elapsed_time(k1), 3), **{k: round(r0.elapsed_time(ev), 3) for k, ev in marks.items()}})
     retrieval.rank_timeline, scoring.kernel_timeline = None, None
