@@ -139,7 +139,14 @@ def _work_pool(group, rows, Nc):
         del _pools[key]
         pool = None
     if pool is None:
-        pool = _pools[key] = steal.WorkPool(group, rows, Nc)
+        try:
+            pool = _pools[key] = steal.WorkPool(group, rows, Nc)
+        except _cabi.AladError as e:             # raised on every rank alike (peer.PeerWindow / steal.Counters)
+            global POOL
+            import warnings
+            warnings.warn(f"cross-GPU work pool unavailable ({e}); static image blocks")
+            POOL = False
+            return None
     return pool
 
 
@@ -432,6 +439,8 @@ class AlignmentGallery:
         Nc, nw = self.Nc, self.nw
         rows_max = max(b - a for a, b in self.bounds)
         pool = _work_pool(group, rows_max, Nc)
+        if pool is None:                        # no peer access between the ranks: the static path (equal blocks)
+            return self.scores(group=None)
         n_loc = self.hi - self.lo
         blk = pool.block(n_loc)
         # ---- operands: all regions, all words

@@ -39,16 +39,28 @@ class Counters:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         name = [None]
         if self.rank == 0:
-            name[0] = f"/dev/shm/alad_b200_pool_{os.getpid()}_{int(time.time() * 1e6) & 0xffffffff}"
-            with open(name[0], "wb") as f:
-                f.write(b"\0" * mmap.PAGESIZE)
+            try:
+                name[0] = f"/dev/shm/alad_b200_pool_{os.getpid()}_{int(time.time() * 1e6) & 0xffffffff}"
+                with open(name[0], "wb") as f:
+                    f.write(b"\0" * mmap.PAGESIZE)
+            except OSError as e:
+                name[0] = f"!{e}"
         dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if hasattr(dist, "get_global_rank") else 0, group=group)
         self.path = name[0]
-        self.fd = os.open(self.path, os.O_RDWR)
-        self.map = mmap.mmap(self.fd, mmap.PAGESIZE)
+        err = self.path[1:] if self.path.startswith("!") else None
+        self.map = self.fd = None
+        if err is None:
+            try:
+                self.fd = os.open(self.path, os.O_RDWR)
+                self.map = mmap.mmap(self.fd, mmap.PAGESIZE)
+            except OSError as e:                 # e.g. ranks in different IPC / mount namespaces
+                err = str(e)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err, group=group)     # a failure anywhere raises everywhere (also the barrier before unlink)
+        if any(errs):
+            raise _cabi.AladError("work-pool counters unavailable: " + "; ".join(f"rank {q}: {e}" for q, e in enumerate(errs) if e))
         self.words = np.frombuffer(self.map, dtype=np.int64)
         self.base = self.words.ctypes.data
-        dist.barrier(group=group)
         if self.rank == 0:
             os.unlink(self.path)                # the mappings keep the page alive
 

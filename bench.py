@@ -330,6 +330,16 @@ def main():
         if world > 1:
             e2e["caption_exchange"] = retrieval.EXCHANGE + (" (copy engines through IPC peer windows)" if retrieval.EXCHANGE == "peer" else " all-gather")
 
+    # ---- BASELINE config 5 on the same ranks (N > 1; at N = 1 it is part of the `also` block): two-stage retrieval, K = 100
+    two_stage = None
+    if world > 1 and not args.no_also and args.workload == "coco5k":
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import two_stage_probe
+            two_stage = two_stage_probe.measure(Ni, Nc, 100, world=world, steps=3, warmup=2)
+        except Exception as e:          # context, never a reason to lose the headline line (all ranks fail alike)
+            two_stage = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -380,7 +390,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu, "recall_at_1": recalls, "also": also, "shard_balance": shard_balance,
+                "roofline": roofline, "cpu_baseline": cpu, "recall_at_1": recalls, "also": also, "two_stage": two_stage if world > 1 else (also or {}).get("config5_two_stage_coco5k"),
+                "shard_balance": shard_balance,
                 "tflops_algorithmic_whole_step": Ni * Nc * FLOP_PER_PAIR(regions, words, d) / (ms_step * 1e-3) / 1e12}
         print(json.dumps(line))
     if world > 1:
