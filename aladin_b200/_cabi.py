@@ -114,6 +114,7 @@ PROTOTYPES = {
     "alad_abi_version": (C.c_int, []),
     "alad_last_error": (C.c_char_p, []),
     "alad_h2d_2d": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P]),
+    "alad_h2d_2d_staged": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _I32, _P]),
     "alad_region_tiles": (C.c_int, [_P, _P, _I32, _P, _I32, _P]),
     "alad_pack_tokens": (C.c_int, [C.POINTER(PackArgs), _P]),
     "alad_mrsw_scores_fwd": (C.c_int, [C.POINTER(MrswFwdArgs), _P]),

@@ -268,6 +268,25 @@ def _gallery_meta(img_shape1, cap_shape, img_lens, cap_lens, Ni, img_start, img_
     return val
 
 
+STAGING_THREADS_MAX = 16
+
+
+def staging_threads():
+    """Host threads that gather a pageable source into the pinned staging buffers: the CPUs this process may use,
+    shared between the ranks of the box, at most STAGING_THREADS_MAX (measured on a 16-core B200 box, profiles/r02_pageable_upload.md:
+    9.5 GB/s with 1 thread, 38 GB/s with 8, 44.5 GB/s with 16)."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    forced = os.environ.get("ALAD_H2D_THREADS")
+    if forced:
+        return max(1, int(forced))
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, min(STAGING_THREADS_MAX, n // max(local, 1)))
+
+
 def _upload_rows(x, row_start, row_step, n_rows, n_slots, out=None):
     """Rows row_start + i*row_step (i < n_rows), slots [0, n_slots) of a [N,S,d] fp32 tensor ->
     device tensor [n_rows, n_slots, d].  CPU sources go through one pitched H2D copy."""
@@ -282,8 +301,14 @@ def _upload_rows(x, row_start, row_step, n_rows, n_slots, out=None):
     assert out.shape[1] == n_slots and out.shape[2] == d and out.is_contiguous()
     if n_rows and n_slots:
         src = x.data_ptr() + row_start * x.stride(0) * 4
-        _cabi.check(_cabi.lib().alad_h2d_2d(out.data_ptr(), n_slots * d * 4, src, row_step * x.stride(0) * 4,
-                                            n_slots * d * 4, n_rows, _cabi.stream_ptr()), "alad_h2d_2d")
+        if x.is_pinned():
+            _cabi.check(_cabi.lib().alad_h2d_2d(out.data_ptr(), n_slots * d * 4, src, row_step * x.stride(0) * 4,
+                                                n_slots * d * 4, n_rows, _cabi.stream_ptr()), "alad_h2d_2d")
+        else:
+            # pageable source (what the reference's encode_data returns): multi-threaded staging through pinned buffers
+            _cabi.check(_cabi.lib().alad_h2d_2d_staged(out.data_ptr(), n_slots * d * 4, src, row_step * x.stride(0) * 4,
+                                                       n_slots * d * 4, n_rows, staging_threads(), _cabi.stream_ptr()),
+                        "alad_h2d_2d_staged")
     return dst
 
 

@@ -47,6 +47,13 @@ const char* alad_last_error(void);
  * ------------------------------------------------------------------------------- */
 int alad_h2d_2d(void* dst, int64_t dst_pitch, const void* src_host, int64_t src_pitch, int64_t width_bytes,
                 int64_t height, void* stream);
+/* alad_h2d_2d_staged -- the same upload for PAGEABLE sources (what the reference's encode_data returns,
+ * alad/evaluation.py:98-130): n_threads host threads gather the rows into a ring of pinned staging buffers while the
+ * copy engine drains the previous one (a pageable cudaMemcpy2DAsync is staged by the driver on one thread, ~10 GB/s).
+ * Returns once the source has been read; the last DMA may still be in flight on `stream`.  Process-wide staging
+ * buffers (3 x 48 MB of pinned memory, allocated on first use). */
+int alad_h2d_2d_staged(void* dst, int64_t dst_pitch, const void* src_host, int64_t src_pitch, int64_t width_bytes,
+                       int64_t height, int32_t n_threads, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * alad_pack_tokens  -- replaces F.normalize + slot slicing at alad/loss.py:80-90 and the
