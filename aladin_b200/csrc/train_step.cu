@@ -6,6 +6,7 @@
 // B <= 512 the step launches ~35 kernels of a few microseconds each and is bound by the HOST cost of a dozen
 // Python-level calls (0.8 ms enqueue for 0.3-0.6 ms of device work); done natively the enqueue takes ~0.1 ms.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -56,9 +57,47 @@ static int axpby_t(const float* A, int64_t ldA, const float* sa, const float* Bm
   return ALAD_OK;
 }
 
+// Fork / join inside one call: the matching head's chain (two packs, a small GEMM, the hinge kernels: ~50 us of launches that
+// leave most SMs idle) runs on a side stream next to the alignment head's packs, and in the backward next to the sparse
+// MrSw backward.  One side stream and two events per host thread and device; the pattern is capture-safe (event record / wait).
+struct SideLane {
+  int dev = -1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+// bit 0 = fork in the forward call, bit 1 = in the backward call.  Measured on one box (tools/train_step_quick.py, B = 512):
+// forward 0.366 -> 0.313 ms with bit 0; the backward fork made forward + backward SLOWER or bimodal (0.66 -> 0.72 ms, 1.17 ms
+// on another box: the matching head's CTA-pair GEMM competes with the 444 CTAs of the sparse MrSw backward for whole SMs),
+// and at B = 128 the step is host-bound, where the four extra stream / event calls only cost.  Hence: forward only, B >= 256.
+// A -DALAD_TUNING_ENV build reads ALAD_TRAIN_FORK instead.
+static int fork_mask(int B) {
+#ifdef ALAD_TUNING_ENV
+  static const int m = [] {
+    const char* e = getenv("ALAD_TRAIN_FORK");
+    return e ? atoi(e) : -1;
+  }();
+  if (m >= 0) return m;
+#endif
+  return B >= 256 ? 1 : 0;
+}
+static int side_lane(SideLane** out) {
+  static thread_local SideLane lanes[16];
+  int dev = 0;
+  ALAD_CUDA(cudaGetDevice(&dev));
+  SideLane& l = lanes[dev & 15];
+  if (l.dev != dev) {
+    ALAD_CUDA(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
+    ALAD_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+    ALAD_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    l.dev = dev;
+  }
+  *out = &l;
+  return ALAD_OK;
+}
+
 struct TrainLayout {
-  // forward
-  int64_t f_scores, f_scores_bytes, f_loss, f_args, f_total;
+  // forward (the matching chain has its own regions: it runs concurrently with the alignment chain)
+  int64_t f_scores, f_scores_bytes, f_loss, f_args, f_scores_m, f_scores_m_bytes, f_loss_m, f_args_m, f_total;
   // backward
   int64_t b_gt, b_gtT, b_imT, b_sT, b_cnt, b_scores, b_scores_bytes, b_mrsw, b_mrsw_bytes, b_total;
 };
@@ -72,6 +111,9 @@ static TrainLayout train_layout(int32_t B, int32_t S_im, int32_t S_s, int32_t d,
   L.f_scores = o;  L.f_scores_bytes = ws_match > ws_align ? ws_match : ws_align;  o = up256(o + L.f_scores_bytes);
   L.f_loss = o;    o = up256(o + alad_loss_workspace_bytes(B));
   L.f_args = o;    o = up256(o + 8ll * (B > 0 ? B : 1));            // row_arg | col_arg of the triplet kernels
+  L.f_scores_m = o;  L.f_scores_m_bytes = ws_match;  o = up256(o + ws_match);
+  L.f_loss_m = o;  o = up256(o + alad_loss_workspace_bytes(B));
+  L.f_args_m = o;  o = up256(o + 8ll * (B > 0 ? B : 1));
   L.f_total = o;
   o = 0;
   L.b_gt = o;   o = up256(o + bb);
@@ -131,7 +173,18 @@ extern "C" int alad_train_losses_fwd(const alad_train_losses_args* a, void* stre
   static thread_local std::vector<int32_t> ones;
   if ((int)ones.size() < B) ones.assign((size_t)B, 1);
 
-  // ---- matching head: M = im_cls @ s_cls.T (dot_sim, alad/loss.py:8-11) + hinge (loss.py:42-67)
+  SideLane* lane = nullptr;
+  if ((rc = side_lane(&lane))) return rc;
+  const bool fork_f = (fork_mask(B) & 1) != 0;
+  if (fork_f) {
+    ALAD_CUDA(cudaEventRecord(lane->fork, st));
+    ALAD_CUDA(cudaStreamWaitEvent(lane->side, lane->fork, 0));
+  }
+  void* side = fork_f ? (void*)lane->side : stream;
+  int32_t* row_arg_m = reinterpret_cast<int32_t*>(ws + L.f_args_m);
+  int32_t* col_arg_m = row_arg_m + B;
+
+  // ---- matching head (side stream): M = im_cls @ s_cls.T (dot_sim, alad/loss.py:8-11) + hinge (loss.py:42-67)
   alad_scores_fused_args f;
   memset(&f, 0, sizeof(f));
   f.max_x = a->im_cls; f.max_stride_b = a->ld_im_cls; f.max_stride_s = a->ld_im_cls;
@@ -142,11 +195,12 @@ extern "C" int alad_train_losses_fwd(const alad_train_losses_args* a, void* stre
   f.max_count = ones.data(); f.sum_count = ones.data(); f.max_clamp = nullptr;
   f.precision = a->precision_m; f.epilogue = 1; f.normalize = 0; f.eps = 0.f;
   f.S = a->M; f.ldS = B; f.transpose_out = 0;
-  f.workspace = ws + L.f_scores; f.workspace_bytes = L.f_scores_bytes;
-  if ((rc = alad_scores_fused(&f, stream))) return rc;
+  f.workspace = ws + L.f_scores_m; f.workspace_bytes = L.f_scores_m_bytes;
+  if ((rc = alad_scores_fused(&f, side))) return rc;
   if ((rc = alad_triplet_fwd_bwd(a->M, B, B, a->margin_m, a->max_violation_m, a->losses + 0, a->want_grad ? a->G_m : nullptr, B,
-                                 row_arg, col_arg, ws + L.f_loss, stream)))
+                                 row_arg_m, col_arg_m, ws + L.f_loss_m, side)))
     return rc;
+  if (fork_f) ALAD_CUDA(cudaEventRecord(lane->join, lane->side));
 
   // ---- alignment head: S = MrSw(im_set, s_seq) (loss.py:80-125) + hinge
   f.max_x = a->im_set; f.max_stride_b = a->im_stride_b; f.max_stride_s = a->im_stride_s;
@@ -156,11 +210,14 @@ extern "C" int alad_train_losses_fwd(const alad_train_losses_args* a, void* stre
   f.max_count = a->nr; f.sum_count = a->nw; f.max_clamp = a->clamp;
   f.precision = a->precision; f.epilogue = 0; f.normalize = 1; f.eps = 1e-12f;
   f.S = a->S;
+  f.workspace = ws + L.f_scores; f.workspace_bytes = L.f_scores_bytes;
   if ((rc = alad_scores_fused(&f, stream))) return rc;
   if ((rc = alad_triplet_fwd_bwd(a->S, B, B, a->margin_a, a->max_violation_a, a->losses + 1, a->want_grad ? a->G_a : nullptr, B,
                                  row_arg, col_arg, ws + L.f_loss, stream)))
     return rc;
 
+  // ---- join: M and the matching loss are complete from here on
+  if (fork_f) ALAD_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
   // ---- distillation: ListNet(teacher = S detached, student = M) (loss.py:370,427-445)
   if (a->with_distill) {
     if ((rc = alad_listnet_fwd_bwd(a->S, B, a->M, B, B, a->temperature, a->listnet_eps, a->losses + 2,
@@ -184,6 +241,8 @@ extern "C" int alad_train_losses_bwd(const alad_train_losses_args* a, void* stre
   const int32_t B = a->B, d = a->d;
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
   const bool use_m = a->has_g_m && a->G_m, use_d = a->has_g_d && a->with_distill && a->dM, use_a = a->has_g_a && a->G_a;
+  SideLane* lane = nullptr;
+  bool forked = false;
 
   // ---- matching head: dL/dM = g[0] * G_m + g[2] * dM;  d im_cls = (dL/dM) @ s_cls,  d s_cls = (dL/dM).T @ im_cls
   if (a->d_im_cls || a->d_s_cls) {
@@ -192,6 +251,15 @@ extern "C" int alad_train_losses_bwd(const alad_train_losses_args* a, void* stre
       if (a->d_s_cls && B) ALAD_CUDA(cudaMemsetAsync(a->d_s_cls, 0, (size_t)B * d * sizeof(float), st));
     } else {
       ALAD_REQUIRE(a->im_cls && a->s_cls, "alad_train_losses_bwd: NULL matching inputs");
+      // the matching head's backward (transposes + two GEMMs) runs on the side stream next to the sparse MrSw backward
+      if ((rc = side_lane(&lane))) return rc;
+      forked = (fork_mask(B) & 2) != 0;
+      if (forked) {
+        ALAD_CUDA(cudaEventRecord(lane->fork, st));
+        ALAD_CUDA(cudaStreamWaitEvent(lane->side, lane->fork, 0));
+      }
+      cudaStream_t ss = forked ? lane->side : st;
+      void* side = forked ? (void*)lane->side : stream;
       float* Gt = reinterpret_cast<float*>(ws + L.b_gt);
       float* GtT = reinterpret_cast<float*>(ws + L.b_gtT);
       float* imT = reinterpret_cast<float*>(ws + L.b_imT);
@@ -200,9 +268,9 @@ extern "C" int alad_train_losses_bwd(const alad_train_losses_args* a, void* stre
       const float* Bm = use_d ? a->dM : nullptr;
       // with only one of the two terms present it takes the "A" slot
       if (!A) {
-        if ((rc = axpby_t(Bm, B, a->g + 2, nullptr, 0, nullptr, B, B, a->d_im_cls ? Gt : nullptr, B, a->d_s_cls ? GtT : nullptr, B, st)))
+        if ((rc = axpby_t(Bm, B, a->g + 2, nullptr, 0, nullptr, B, B, a->d_im_cls ? Gt : nullptr, B, a->d_s_cls ? GtT : nullptr, B, ss)))
           return rc;
-      } else if ((rc = axpby_t(A, B, a->g + 0, Bm, B, a->g + 2, B, B, a->d_im_cls ? Gt : nullptr, B, a->d_s_cls ? GtT : nullptr, B, st))) {
+      } else if ((rc = axpby_t(A, B, a->g + 0, Bm, B, a->g + 2, B, B, a->d_im_cls ? Gt : nullptr, B, a->d_s_cls ? GtT : nullptr, B, ss))) {
         return rc;
       }
       static thread_local std::vector<int32_t> ones;
@@ -219,22 +287,23 @@ extern "C" int alad_train_losses_bwd(const alad_train_losses_args* a, void* stre
       f.ldS = d; f.transpose_out = 0;
       f.workspace = ws + L.b_scores; f.workspace_bytes = L.b_scores_bytes;
       if (a->d_im_cls) {
-        if ((rc = axpby_t(a->s_cls, a->ld_s_cls, nullptr, nullptr, 0, nullptr, B, d, nullptr, 0, sT, B, st))) return rc;
+        if ((rc = axpby_t(a->s_cls, a->ld_s_cls, nullptr, nullptr, 0, nullptr, B, d, nullptr, 0, sT, B, ss))) return rc;
         f.max_x = Gt; f.sum_x = sT; f.S = a->d_im_cls;
-        if ((rc = alad_scores_fused(&f, stream))) return rc;
+        if ((rc = alad_scores_fused(&f, side))) return rc;
       }
       if (a->d_s_cls) {
-        if ((rc = axpby_t(a->im_cls, a->ld_im_cls, nullptr, nullptr, 0, nullptr, B, d, nullptr, 0, imT, B, st))) return rc;
+        if ((rc = axpby_t(a->im_cls, a->ld_im_cls, nullptr, nullptr, 0, nullptr, B, d, nullptr, 0, imT, B, ss))) return rc;
         f.max_x = GtT; f.sum_x = imT; f.S = a->d_s_cls;
-        if ((rc = alad_scores_fused(&f, stream))) return rc;
+        if ((rc = alad_scores_fused(&f, side))) return rc;
       }
+      if (forked) ALAD_CUDA(cudaEventRecord(lane->join, lane->side));
     }
   }
 
   // ---- alignment head: dL/dS = g[1] * G_a (<= 3B non-zeros) -> sparse MrSw backward
   if (a->d_im_set || a->d_s_seq) {
     ALAD_REQUIRE(a->d_im_set && a->d_s_seq, "alad_train_losses_bwd: d_im_set and d_s_seq go together");
-    if (B == 0) return ALAD_OK;
+    if (B == 0) return ALAD_OK;                        // (B == 0 never forks)
     ALAD_REQUIRE(a->im_set && a->s_seq, "alad_train_losses_bwd: NULL alignment inputs");
     int32_t* cnt = reinterpret_cast<int32_t*>(ws + L.b_cnt);
     static thread_local std::vector<int32_t> stage;
@@ -258,5 +327,6 @@ extern "C" int alad_train_losses_bwd(const alad_train_losses_args* a, void* stre
     m.d_s_stride_b = a->d_s_stride_b;   m.d_s_stride_s = a->d_s_stride_s;
     if ((rc = alad_mrsw_scores_bwd(&m, stream))) return rc;
   }
+  if (forked) ALAD_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
   return ALAD_OK;
 }
