@@ -30,8 +30,8 @@ __global__ void peer_signal_kernel(PeerPtrs dst, int n, int32_t value) {
   }
 }
 
-// lane q < n spins until flags[q] >= value (bounded: ~timeout_ns of wall clock, then *error = 1 + q and give up, so that a
-// lost peer cannot hang the GPU)
+// lane q < n spins until flags[q] >= value (bounded: after ~timeout_ns of wall clock *error = 1 + q and the kernel traps, so
+// that a lost peer can neither hang the GPU nor let stale rows be scored)
 __global__ void peer_wait_kernel(const int32_t* flags, int n, int32_t value, int skip, long long timeout_ns, int32_t* error) {
   const int q = threadIdx.x;
   if (q >= n || q == skip) return;
@@ -46,8 +46,11 @@ __global__ void peer_wait_kernel(const int32_t* flags, int n, int32_t value, int
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if ((long long)(t1 - t0) > timeout_ns) {
+        // a peer never delivered: the rows this stream is about to score would be stale.  Record who, then abort the
+        // context -- the failure surfaces at the caller's next synchronisation instead of as silently wrong scores.
         if (error) atomicExch(error, 1 + q);
-        break;
+        __threadfence_system();
+        __trap();
       }
     }
     __nanosleep(200);

@@ -508,7 +508,8 @@ int alad_shortlist_scatter(const float* S, int64_t ldS, float* S2, int64_t ld2, 
  *   alad_peer_signal            after everything enqueued on `stream` so far: *flag_ptrs[q] = value for q < n
  *                               (flag_ptrs: HOST array of device pointers, normally one slot in each peer's buffer)
  *   alad_peer_wait              blocks `stream` until flags[q] - value >= 0 for every q < n, q != skip (sequence
- *                               numbers; wrap-safe); gives up after timeout_ms and stores 1 + q into *error (device)
+ *                               numbers; wrap-safe); after timeout_ms it stores 1 + q into *error (device) and traps: the
+ *                               failure surfaces at the caller's next synchronisation, stale rows are never scored
  * ------------------------------------------------------------------------------- */
 #define ALAD_MAX_PEERS 32
 #define ALAD_PEER_HANDLE_BYTES 64
