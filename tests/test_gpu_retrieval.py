@@ -156,3 +156,23 @@ def test_pinned_host_gallery_chunked_upload_matches_device_resident():
     assert torch.equal(a, b)
     ref = O.mrsw_scores(images[0::5], captions, il[0::5], cl, acc64=True)
     assert np.abs(a.cpu().numpy() - ref).max() <= 1e-2
+
+
+def test_pageable_host_gallery_staged_upload_matches_device_resident(monkeypatch):
+    """The tensors the reference's encode_data returns are PAGEABLE: their rows reach the device through pinned staging
+    buffers filled by several host threads (alad_h2d_2d_staged).  82 MB of captions = two 48 MB staging buffers per chunk,
+    5-row pitch on the image side, odd thread count; the scores must equal the device-resident gallery's bit for bit."""
+    from aladin_b200 import retrieval, synth
+    monkeypatch.setenv("ALAD_H2D_THREADS", "3")
+    images, captions, il, cl = synth.eval_containers(35, 800, 21, 256, max_regions=20, max_words=17)
+    ti, tc = torch.from_numpy(images), torch.from_numpy(captions)
+    assert not ti.is_pinned() and not tc.is_pinned() and captions.nbytes > (48 << 20)
+    a = retrieval.AlignmentGallery(ti, tc, il, cl, n_images=800, img_start=0, img_step=5, precision="bf16",
+                                   caption_chunk=4000).scores()
+    b = retrieval.AlignmentGallery(ti.cuda(), tc.cuda(), il, cl, n_images=800, img_start=0, img_step=5,
+                                   precision="bf16").scores()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    # and a direct check of the upload itself: every 5th image row, the first 9 slots
+    dev = retrieval._upload_rows(ti, 0, 5, 800, 9)
+    assert torch.equal(dev.cpu(), ti[0::5, :9])
