@@ -16,6 +16,9 @@ import torch
 from . import retrieval, scoring
 
 _cache = {}
+# Score matrices larger than this (or than 40 % of the free device memory) are never materialised: the fused path then ranks
+# block by block (retrieval.streaming_ranks); COCO-5k needs 0.5 GB.
+STREAM_SCORE_BYTES = 32 << 30
 # verdict of the closure probe per sim_function object (i2t and t2i of one evaluation hand over the same closure)
 _probe_memo = weakref.WeakKeyDictionary()
 
@@ -181,6 +184,14 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
             S = scoring.dot_scores(images[:, 0, :][0::5], captions[:, 0, :], precision=precision)
         else:
             S = scoring.dot_scores(images[0::5][:, 0, :], captions[:, 0, :], precision=precision)
+    elif mode == "fused" and _dist_state()[0] == 1 and not isinstance(images, DeviceContainer) and _too_large(Ni, captions.shape[0]):
+        # the [Ni, Nc] block does not fit: ranks and lists block by block, S is never materialised
+        ri, t1, rt, tk = retrieval.streaming_ranks(images, captions, img_lens, cap_lens, Ni, img_start=0, img_step=5,
+                                                   precision=precision, block_images=_stream_block(captions.shape[0]),
+                                                   k=min(50, Ni))
+        res = dict(S=None, img_off=0, world=1, ranks_i2t=ri, top1=None, ranks_t2i=rt, top50=None, lists=(t1, tk))
+        _store(key, res, images, captions)
+        return res
     elif mode == "fused":
         world, rank, group = _dist_state()
         gal = retrieval.AlignmentGallery(images, captions, img_lens, cap_lens, n_images=Ni, img_start=0, img_step=5,
@@ -196,15 +207,36 @@ def _retrieve(images, captions, img_lens, cap_lens, sim_function, batches):
     ri, t1, rt, tk = retrieval.rank_both_directions(S, Ni, img_off=img_off, n_images_total=Ni, k=k, group=group, bounds=bounds,
                                                     lists_to_host=False)
     res = dict(S=S, img_off=img_off, world=world, ranks_i2t=ri, top1=t1, ranks_t2i=rt, top50=tk)
-    if key is not None:
-        # the key holds addresses: a hit is valid only while the very same input objects are alive (a freed
-        # tensor's address, shape and version counter can all recur, e.g. the next epoch's validation embeddings)
-        refs = (weakref.ref(images), weakref.ref(captions))
-        _cache.clear()
-        _cache.update(key=key, res=res, refs=refs)
-        for obj in (images, captions):       # the block dies with its inputs, not with the next call
-            weakref.finalize(obj, _evict, key)
+    _store(key, res, images, captions)
     return res
+
+
+def _store(key, res, images, captions):
+    if key is None:
+        return
+    # the key holds addresses: a hit is valid only while the very same input objects are alive (a freed
+    # tensor's address, shape and version counter can all recur, e.g. the next epoch's validation embeddings)
+    refs = (weakref.ref(images), weakref.ref(captions))
+    _cache.clear()
+    _cache.update(key=key, res=res, refs=refs)
+    for obj in (images, captions):       # the block dies with its inputs, not with the next call
+        weakref.finalize(obj, _evict, key)
+
+
+def _too_large(Ni, Nc):
+    need = 4 * Ni * Nc
+    if need > STREAM_SCORE_BYTES:
+        return True
+    try:
+        free, _ = torch.cuda.mem_get_info()
+    except Exception:
+        return False
+    return need > 0.4 * free
+
+
+def _stream_block(Nc):
+    """Images per block of the streaming path: a ~1 GiB score buffer, at least 64 images."""
+    return max(64, int((1 << 30) // max(4 * Nc, 1)))
 
 
 def _lists(res):
@@ -216,7 +248,7 @@ def _lists(res):
 
 def _ndcg(ndcg_scorer, res, npts, fold_index, retrieval_kind):
     """NDCG hooks (evaluation.py:225-228,310-313): need the full order per query."""
-    if res["world"] > 1:
+    if res["world"] > 1 or res["S"] is None:
         raise NotImplementedError("NDCG scoring needs the whole score block on one device")
     S = res["S"]
     n = npts if retrieval_kind == "sentence" else 5 * npts

@@ -884,6 +884,77 @@ def lists_host(top1_dev, topk_dev):
     return _to_host_f64(top1_dev, topk_dev)
 
 
+def streaming_ranks(images, captions, img_lens, cap_lens, n_images, img_start=0, img_step=1, precision=None, block_images=1024,
+                    k=50):
+    """Both directions' ranks and top-k WITHOUT materialising S[Ni, Nc]: the gallery images are scored block by block into
+    one reusable [block_images, Nc] buffer, exactly the way the multi-GPU path scores one block per rank -- i2t ranks are
+    final per block, the t2i "images ahead" counts add up over the blocks and the per-caption top-k lists are merged as they
+    come.  The ground-truth scores the counts compare against come from a first pass over the block diagonal (image
+    block x its own captions, 1 / n_blocks of the work) launched on the same 256-row word units as the full pass, so they
+    are bit-identical to the entries of S they stand for.  For galleries whose score matrix does not fit (0.5 GB at COCO-5k,
+    50 GB at ten times the gallery); results equal rank_both_directions on the dense matrix.
+    Returns (ranks_i2t[Ni], top1[Ni], ranks_t2i[Nc], topk[Nc, k]) as float64 numpy arrays."""
+    from .tiling import exclusive_cumsum
+    Ni = int(n_images)
+    gal = AlignmentGallery(images, captions, img_lens, cap_lens, n_images=Ni, img_start=img_start, img_step=img_step,
+                           precision=precision, world=1, rank=0, bounds=[(0, Ni)])
+    Nc = gal.Nc
+    k = min(k, Ni)
+    B = max(int(block_images), k, 1)
+    words, regions, _ = gal.packed_operands()
+    dev = words.data.device
+    roff, n_reg = exclusive_cumsum(gal.nr)
+    roff = np.concatenate([roff, [n_reg]])
+    csum = gal._row_csum()
+    unit = 2 * _cabi.TILE_M
+    n_rows, Kp = words.n_rows, words.Kp
+    blocks = [(lo, min(Ni, lo + B)) for lo in range(0, Ni, B)]
+    S_buf = torch.empty((min(B, Ni), Nc), dtype=torch.float32, device=dev)
+
+    def score(lo, hi, r0, r1, u1):
+        """S_buf[:hi-lo] = scores of images [lo, hi) against the captions whose rows lie in word rows [r0, r1)."""
+        _, table, _ = build_region_tiles(gal.nr[lo:hi], gal.clamp[lo:hi])
+        out = S_buf[:hi - lo]
+        if len(table) == 0 or r1 <= r0:
+            out.zero_()
+            return out
+        tiles_dev = scoring._to_dev(table.view(np.int32).reshape(-1), dev)
+        w = scoring.Packed(words.data[r0:r1], r1 - r0, Kp, None, None, words.row_item[r0:u1 * unit], words.mode)
+        g = scoring.Packed(regions.data[int(roff[lo]):int(roff[hi])], int(roff[hi] - roff[lo]), Kp, None, None, None, regions.mode)
+        scoring.mrsw_scores_packed(w, g, tiles_dev, len(table), hi - lo, Nc, out=out,
+                                   timeline_nc=Nc * (r1 - r0) / max(n_rows, 1))
+        return out
+
+    n_units = (n_rows + unit - 1) // unit
+    gt = torch.zeros(Nc, dtype=torch.float32, device=dev)
+    if regions is not None and n_rows:
+        for lo, hi in blocks:                       # pass 1: the block diagonal -> ground-truth scores
+            c0, c1 = min(Nc, 5 * lo), min(Nc, 5 * hi)
+            if c1 <= c0:
+                continue
+            u0, u1 = int(csum[c0]) // unit, min(n_units, (int(csum[c1]) + unit - 1) // unit)
+            ranking.col_gt(score(lo, hi, u0 * unit, min(u1 * unit, n_rows), u1), gt, 5, lo)
+    rank_i = torch.empty(Ni, dtype=torch.int32, device=dev)
+    top1_i = torch.empty(Ni, dtype=torch.int32, device=dev)
+    count = torch.zeros(Nc, dtype=torch.int32, device=dev)
+    run_s = run_i = None
+    for lo, hi in blocks:                           # pass 2: every block against all captions
+        if regions is not None and n_rows:
+            Sb = score(lo, hi, 0, n_rows, n_units)
+        else:
+            Sb = S_buf[:hi - lo].zero_()
+        r, t1 = ranking.rank_rows(Sb, 5, lo)
+        rank_i[lo:hi], top1_i[lo:hi] = r, t1
+        count += ranking.col_count(Sb, gt, 5, lo)
+        cs, ci = ranking.col_topk(Sb, k, lo)
+        cs, ci = ranking.topk_merge(cs, ci)
+        if run_s is None:
+            run_s, run_i = cs, ci
+        else:
+            run_s, run_i = ranking.topk_merge(torch.stack([run_s, cs]).contiguous(), torch.stack([run_i, ci]).contiguous())
+    return _to_host_f64(rank_i, top1_i, count, run_i)
+
+
 def _to_host_f64(*tensors):
     """Device int tensors -> float64 numpy arrays (the reference returns numpy.zeros-typed arrays:
     alad/evaluation.py:166-167,255-256) with ONE device->host copy into pinned memory and one sync."""

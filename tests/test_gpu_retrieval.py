@@ -176,3 +176,48 @@ def test_pageable_host_gallery_staged_upload_matches_device_resident(monkeypatch
     # and a direct check of the upload itself: every 5th image row, the first 9 slots
     dev = retrieval._upload_rows(ti, 0, 5, 800, 9)
     assert torch.equal(dev.cpu(), ti[0::5, :9])
+
+
+@pytest.mark.parametrize("block,precision", [(64, "bf16"), (150, "fp32"), (1000, "bf16")])
+def test_streaming_ranks_equal_the_dense_matrix(block, precision):
+    """Block-by-block retrieval without the [Ni, Nc] matrix (retrieval.streaming_ranks): ranks, top-1 and top-50 must equal the
+    ranking of the dense score matrix exactly -- ragged lengths, an image without regions, captions without words, blocks that
+    do not divide the gallery."""
+    from aladin_b200 import retrieval, synth
+    Ni = 333
+    images, captions, il, cl = synth.eval_containers(36, Ni, 40, 192, max_regions=36, max_words=38, alpha=0.3)
+    il[5 * 7:5 * 7 + 5] = [1] * 5
+    cl[11] = cl[900] = 3
+    ti, tc = torch.from_numpy(images), torch.from_numpy(captions)
+    S = retrieval.AlignmentGallery(ti, tc, il, cl, n_images=Ni, img_start=0, img_step=5, precision=precision).scores()
+    want = retrieval.rank_both_directions(S, Ni, k=50)
+    got = retrieval.streaming_ranks(ti, tc, il, cl, Ni, img_start=0, img_step=5, precision=precision, block_images=block, k=50)
+    for a, b, name in zip(got, want, ("ranks_i2t", "top1", "ranks_t2i", "top50")):
+        np.testing.assert_array_equal(a, b, err_msg=name)
+
+
+def test_oversized_gallery_takes_the_streaming_path(monkeypatch):
+    """A score matrix above evaluation.STREAM_SCORE_BYTES is never materialised: i2t / t2i rank block by block and return
+    what the dense path returns (golden retrieval set, fp32 mode: ranks, top-1, top-50, metrics)."""
+    from aladin_b200 import evaluation as E, loss as L
+    g = load_golden("retrieval")
+    images = torch.from_numpy(np.repeat(g["images"], 5, axis=0))
+    captions = torch.from_numpy(g["captions"])
+    il, cl = g["img_lens"].tolist(), g["cap_lens"].tolist()
+    crit = L.AlignmentContrastiveLoss(aggregation="MrSw")
+    crit.precision = "fp32"
+    E.clear_cache()
+    dense = (E.i2t(images, captions, il, cl, return_ranks=True, sim_function=crit),
+             E.t2i(images, captions, il, cl, return_ranks=True, sim_function=crit))
+    assert E._cache["res"]["S"] is not None
+    monkeypatch.setattr(E, "STREAM_SCORE_BYTES", 0)
+    monkeypatch.setattr(E, "_stream_block", lambda Nc: 64)
+    E.clear_cache()
+    stream = (E.i2t(images, captions, il, cl, return_ranks=True, sim_function=crit),
+              E.t2i(images, captions, il, cl, return_ranks=True, sim_function=crit))
+    assert E._cache["res"]["S"] is None
+    for (m0, (r0, l0)), (m1, (r1, l1)) in zip(dense, stream):
+        assert m0 == m1
+        np.testing.assert_array_equal(r0, r1)
+        np.testing.assert_array_equal(l0, l1)
+    np.testing.assert_array_equal(stream[0][1][0], g["ranks_i2t"])
