@@ -105,6 +105,7 @@ class MrswPairsArgs(C.Structure):
         ("Kp", C.c_int32), ("row_cap", C.c_void_p), ("ptiles", C.c_void_p), ("n_ptiles", C.c_void_p),
         ("max_ptiles", C.c_int32), ("slot_rows", C.c_int32), ("S", C.c_void_p), ("ldS", C.c_int64),
         ("Ni", C.c_int32), ("Nc", C.c_int32), ("transpose_out", C.c_int32), ("num_ctas", C.c_int32),
+        ("word_box_rows", C.c_int32),
     ]
 
 

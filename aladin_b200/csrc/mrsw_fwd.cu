@@ -100,6 +100,7 @@ struct MrswParams {
   const int32_t* n_ptiles;   // device scalar
   int max_ptiles;
   int slot_rows;
+  int a_bytes;               // bytes of word rows a pair-list tile loads per K block (word_box_rows x 128)
 };
 
 // full = the tile lies in a complete block of n_block region tiles (the last block may be shorter)
@@ -216,7 +217,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = smem + C::OFF_A + stage * A_BYTES;
             uint8_t* sb = smem + C::OFF_B + stage * C::B_BYTES;
-            mbar_expect_tx(&full_bar[stage], A_BYTES + static_cast<uint32_t>(nseg) * slot_bytes);
+            mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.a_bytes) + static_cast<uint32_t>(nseg) * slot_bytes);
             tma_load_2d(sa, &map_words, &full_bar[stage], kb * BK, m_row0);
 #pragma unroll
             for (int s_i = 0; s_i < ALAD_PTILE_SLOTS; ++s_i)
@@ -753,8 +754,12 @@ extern "C" int alad_mrsw_scores_pairs(const alad_mrsw_pairs_args* a, void* strea
   p.n_ptiles = a->n_ptiles;
   p.max_ptiles = a->max_ptiles;
   p.slot_rows = a->slot_rows;
+  const int box_rows = a->word_box_rows > 0 ? a->word_box_rows : BM;
+  ALAD_REQUIRE(box_rows % 8 == 0 && box_rows >= 8 && box_rows <= BM, "alad_mrsw_scores_pairs: word_box_rows=%d must be a multiple of 8 in [8, %d]",
+               box_rows, BM);
+  p.a_bytes = box_rows * BK * 2;
   CUtensorMap map_w, map_r;
-  int rc = make_map(&map_w, a->words, a->n_word_rows, a->Kp, BM);
+  int rc = make_map(&map_w, a->words, a->n_word_rows, a->Kp, box_rows);
   if (rc) return rc;
   rc = make_map(&map_r, a->regions, a->n_region_rows, a->Kp, a->slot_rows);
   if (rc) return rc;

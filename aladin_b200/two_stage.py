@@ -28,6 +28,8 @@ SLOT_ALIGN = 1
 # Packed region bytes per image block of the pair-list pass (see alad_pairtile_args.block_images): a gathered slot is
 # re-used by ~Nc*K/Ni caption groups, so the block being swept has to stay in the 126 MB L2 next to the streamed words.
 L2_BLOCK_BYTES = 48 << 20
+# Load only the word rows a caption group has (104 of 128 for two 50-word captions) instead of the full 128-row box.
+WORD_BOX = True
 _GROUPS = {}
 # diagnostics (tools/two_stage_probe.py): when a list, two_stage_retrieval appends (stage name, CUDA event) marks
 stage_timeline = None
@@ -47,7 +49,11 @@ def _caption_groups(nw):
         _cabi.check(min(n_g, 0), "alad_caption_groups")
         if len(_GROUPS) >= 4:
             _GROUPS.clear()
-        hit = _GROUPS[key] = (n_g, row0[:max(n_g, 1)].copy(), cap_lo[:n_g + 1].copy(), cap_group)
+        # longest group in packed word rows, rounded up to the 8-row swizzle atom: what a tile has to load
+        rows = np.concatenate([[0], np.cumsum(nw, dtype=np.int64)])
+        longest = int((rows[cap_lo[1:n_g + 1]] - rows[cap_lo[:n_g]]).max()) if n_g else 0
+        box = min(_cabi.TILE_M, max(8, (longest + 7) // 8 * 8))
+        hit = _GROUPS[key] = (n_g, row0[:max(n_g, 1)].copy(), cap_lo[:n_g + 1].copy(), cap_group, box)
     return hit
 
 
@@ -69,7 +75,7 @@ def pair_scores(words, regions, region_row_off, nr, clamp, nw, lists_t2i, lists_
         out = torch.empty((n_loc, Nc), dtype=torch.float32, device=dev)
     if n_loc == 0 or Nc == 0 or regions is None:
         return out, None
-    n_g, row0, cap_lo, cap_group = _caption_groups(nw)
+    n_g, row0, cap_lo, cap_group, word_box = _caption_groups(nw)
     slot_rows = slot_rows_for(nr)
     slots = _cabi.TILE_N // slot_rows
     k1 = lists_t2i.shape[1] if lists_t2i is not None else 0
@@ -101,7 +107,7 @@ def pair_scores(words, regions, region_row_off, nr, clamp, nw, lists_t2i, lists_
         words=words.data.data_ptr(), n_word_rows=words.n_rows, regions=regions.data.data_ptr(), n_region_rows=regions.n_rows,
         Kp=words.Kp, row_cap=words.row_item.data_ptr(), ptiles=ptiles.data_ptr(), n_ptiles=n_ptiles.data_ptr(),
         max_ptiles=capacity, slot_rows=slot_rows, S=out.data_ptr(), ldS=max(out.stride(0), Nc), Ni=n_loc, Nc=Nc,
-        transpose_out=0, num_ctas=0)
+        transpose_out=0, num_ctas=0, word_box_rows=word_box if WORD_BOX else 0)
     if scoring.kernel_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -470,6 +470,9 @@ typedef struct alad_mrsw_pairs_args {
   int32_t Ni, Nc;
   int32_t transpose_out;
   int32_t num_ctas;              /* 0 = one persistent CTA per SM                                            */
+  int32_t word_box_rows;         /* word rows loaded per tile: 0 = 128, else a multiple of 8 >= the longest caption
+                                    group (e.g. 104 for two 50-word captions): the rows a tile never scores stay out of
+                                    the L2 -> shared-memory traffic that bounds this kernel                     */
 } alad_mrsw_pairs_args;
 int alad_mrsw_scores_pairs(const alad_mrsw_pairs_args* a, void* stream);
 

@@ -44,7 +44,8 @@ def test_two_stage_pair_list_path_on_the_emulator(virtual_b200, K, l2_bytes, mon
 def test_caption_groups_host_helper():
     from aladin_b200 import two_stage
     nw = np.array([50, 50, 50, 0, 100, 28, 1, 128, 0, 5], np.int32)
-    n_g, row0, cap_lo, cap_group = two_stage._caption_groups(nw)
+    n_g, row0, cap_lo, cap_group, word_box = two_stage._caption_groups(nw)
+    assert word_box % 8 == 0 and 8 <= word_box <= 128
     assert n_g == 6
     assert cap_lo.tolist() == [0, 2, 4, 6, 7, 9, 10]
     assert row0.tolist() == [0, 100, 150, 278, 279, 407]
