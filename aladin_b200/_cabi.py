@@ -28,7 +28,7 @@ class MrswFwdArgs(C.Structure):
         ("Kp", C.c_int32), ("row_cap", C.c_void_p), ("ntiles", C.c_void_p), ("n_ntiles", C.c_int32),
         ("S", C.c_void_p), ("ldS", C.c_int64), ("Ni", C.c_int32), ("Nc", C.c_int32),
         ("epilogue", C.c_int32), ("num_ctas", C.c_int32), ("cta_group", C.c_int32),
-        ("transpose_out", C.c_int32), ("accumulate", C.c_int32),
+        ("transpose_out", C.c_int32), ("accumulate", C.c_int32), ("operand_format", C.c_int32),
     ]
 
 

@@ -65,8 +65,9 @@ class _TrainLossesFn(torch.autograd.Function):
         dev = im_cls.device
         needs = [bool(t.requires_grad) for t in (img_emb, cap_emb, im_set, s_seq)]
         want_grad = any(needs)
-        split = 1 if (precision or scoring.get_precision()) == "fp32" else 0
-        split_m = 1 if (precision_m or scoring.get_precision()) == "fp32" else 0
+        # ('tf32' exists for the retrieval galleries only: the fused small-batch call takes the split-precision path for it)
+        split = 1 if (precision or scoring.get_precision()) in ("fp32", "tf32") else 0
+        split_m = 1 if (precision_m or scoring.get_precision()) in ("fp32", "tf32") else 0
         # one buffer: losses[3] | pad | M | S | G_m | G_a | dM
         bb = B * B
         n_mat = 5 if want_grad else 2

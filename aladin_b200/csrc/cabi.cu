@@ -24,7 +24,7 @@ int sm_count() {
 
 }  // namespace alad
 
-extern "C" int alad_abi_version(void) { return 4; }
+extern "C" int alad_abi_version(void) { return 5; }
 
 extern "C" int64_t alad_host_atomic_add(int64_t* p, int64_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 extern "C" int32_t alad_host_atomic_cas(int64_t* p, int64_t expected, int64_t desired) {

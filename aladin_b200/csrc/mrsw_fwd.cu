@@ -19,6 +19,22 @@
 #include "common.h"
 #include "sm100_ptx.cuh"
 
+// This file is compiled twice: as is (bf16 operands, tcgen05 kind::f16) and from mrsw_fwd_tf32.cu with ALAD_MMA_TF32 defined
+// (fp32 operands read as TF32, kind::tf32; dense kernel only).  Two translation units rather than one more template
+// parameter, so that the bf16 kernel is generated from exactly the source it was tuned with (its code generation is
+// sensitive: profiles/r01_tile_order_sweep.md, "build reproducibility").  A pipeline stage is 128-byte swizzle rows in both
+// (64 bf16 or 32 floats), and one MMA consumes 32 bytes of a row (K = 16 or 8), so nothing else differs.
+#ifdef ALAD_MMA_TF32
+#define mrsw_fwd_kernel mrsw_fwd_tf32_kernel
+#define ALAD_MAKE_IDESC make_idesc_tf32_f32
+#define ALAD_UMMA_CG1 umma_tf32
+#define ALAD_UMMA_CG2 umma_tf32_cg2
+#else
+#define ALAD_MAKE_IDESC make_idesc_bf16_f32
+#define ALAD_UMMA_CG1 umma_bf16
+#define ALAD_UMMA_CG2 umma_bf16_cg2
+#endif
+
 namespace alad {
 
 constexpr int BM = ALAD_TILE_M;
@@ -296,7 +312,7 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
   } else if (warp == 5) {
     // ============================== MMA issuer (leader CTA only) ==============================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM * CG, BN);
+      constexpr uint32_t idesc = ALAD_MAKE_IDESC(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -333,8 +349,8 @@ mrsw_fwd_kernel(const __grid_constant__ CUtensorMap map_words, const __grid_cons
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // +32 B per K step inside the 128 B swizzle row: start-address field is in 16 B units
-            if (CG == 2) umma_bf16_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else         umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) ALAD_UMMA_CG2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else         ALAD_UMMA_CG1(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (CG == 2) umma_commit_cg2_both(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -605,8 +621,28 @@ static int make_map(CUtensorMap* m, const void* ptr, long long rows, int Kp, int
   return 0;
 }
 
+// the dense kernel of THIS translation unit's operand format (cfg: grid, block, stream and cluster attribute already set)
+#ifdef ALAD_MMA_TF32
+int launch_mrsw_dense_tf32(int cg, cudaLaunchConfig_t* cfg, const CUtensorMap* map_w, const CUtensorMap* map_r, const MrswParams* p) {
+#else
+int launch_mrsw_dense_tf32(int cg, cudaLaunchConfig_t* cfg, const CUtensorMap* map_w, const CUtensorMap* map_r, const MrswParams* p);
+int launch_mrsw_dense_bf16(int cg, cudaLaunchConfig_t* cfg, const CUtensorMap* map_w, const CUtensorMap* map_r, const MrswParams* p) {
+#endif
+  if (cg == 2) {
+    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+    cfg->dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+    ALAD_CUDA(cudaLaunchKernelEx(cfg, mrsw_fwd_kernel<2, false>, *map_w, *map_r, *p));
+  } else {
+    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+    cfg->dynamicSmemBytes = Cfg<1>::SMEM_BYTES;
+    ALAD_CUDA(cudaLaunchKernelEx(cfg, mrsw_fwd_kernel<1, false>, *map_w, *map_r, *p));
+  }
+  return ALAD_OK;
+}
+
 }  // namespace alad
 
+#ifndef ALAD_MMA_TF32
 extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   using namespace alad;
   ALAD_REQUIRE(a != nullptr, "alad_mrsw_scores_fwd: NULL args");
@@ -620,6 +656,7 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
                "alad_mrsw_scores_fwd: bad row counts");
   ALAD_REQUIRE(a->epilogue == 0 || a->epilogue == 1, "alad_mrsw_scores_fwd: unknown epilogue %d", a->epilogue);
   ALAD_REQUIRE(a->accumulate == 0 || (a->accumulate == 1 && a->epilogue == 0), "alad_mrsw_scores_fwd: accumulate needs epilogue 0");
+  ALAD_REQUIRE(a->operand_format == 0 || a->operand_format == 1, "alad_mrsw_scores_fwd: unknown operand_format %d", a->operand_format);
   cudaStream_t st = as_stream(stream);
   if (a->Ni > 0 && a->Nc > 0 && !a->accumulate) {
     if (a->ldS == out_cols) {
@@ -709,14 +746,10 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cg == 2) {
-    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
-    cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
-    ALAD_CUDA(cudaLaunchKernelEx(&cfg, mrsw_fwd_kernel<2, false>, map_w, map_r, p));
-  } else {
-    ALAD_CUDA(cudaFuncSetAttribute(mrsw_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
-    cfg.dynamicSmemBytes = Cfg<1>::SMEM_BYTES;
-    ALAD_CUDA(cudaLaunchKernelEx(&cfg, mrsw_fwd_kernel<1, false>, map_w, map_r, p));
+  if (a->operand_format == 1) {
+    if ((rc = launch_mrsw_dense_tf32(cg, &cfg, &map_w, &map_r, &p))) return rc;
+  } else if ((rc = launch_mrsw_dense_bf16(cg, &cfg, &map_w, &map_r, &p))) {
+    return rc;
   }
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;
@@ -782,3 +815,4 @@ extern "C" int alad_mrsw_scores_pairs(const alad_mrsw_pairs_args* a, void* strea
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;
 }
+#endif  // !ALAD_MMA_TF32

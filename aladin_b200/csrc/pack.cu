@@ -29,6 +29,19 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// fp32 -> TF32 (10-bit mantissa), round to nearest, ties away from zero
+__device__ __forceinline__ float round_tf32(float v) {
+#ifndef ALAD_CPU_EMU
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+#else
+  uint32_t u = __float_as_uint(v);
+  u = (u + 0x1000u) & 0xffffe000u;
+  return __uint_as_float(u);
+#endif
+}
+
 template <bool kVec>
 __global__ void __launch_bounds__(PACK_WARPS * 32) pack_tokens_kernel(const alad_pack_args a) {
   const int warp = threadIdx.x >> 5;
@@ -51,6 +64,29 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_tokens_kernel(const alad
   for (int t = flat ? 0 : warp; t < cnt; t += flat ? 1 : PACK_WARPS) {
     const float* x = a.src + (long long)b * a.stride_b + (long long)(a.slot0 + t) * a.stride_s;
     __nv_bfloat16* y = dst + (row0 + t) * (long long)Kp;
+    if (a.mode == 3) {
+      // TF32 operands: the normalised fp32 values rounded to TF32 (the tensor core reads the upper 19 bits); a row is
+      // Kp / 2 floats = Kp two-byte units, so the tile geometry in BYTES is that of the bf16 rows
+      float* yf = reinterpret_cast<float*>(y);
+      float ssq = 0.f;
+      if (a.normalize) {
+        for (int i = lane; i < d; i += 32) {
+          const float v = __ldg(x + i);
+          ssq += v * v;
+        }
+        ssq = warp_sum(ssq);
+      }
+      const float den = a.normalize ? fmaxf(sqrtf(ssq), a.eps) : 1.f;
+      // rounded to TF32 HERE (round to nearest): the tensor core would truncate the low 13 mantissa bits, a systematic
+      // -5e-4 per operand that adds up over the d products instead of averaging out
+      for (int i = lane; i < d; i += 32) {
+        const float v = __ldg(x + i) / den;
+        yf[i] = round_tf32(v);
+      }
+      for (int i = d + lane; i < Kp / 2; i += 32) yf[i] = 0.f;
+      if (a.row_item != nullptr && lane == 0) a.row_item[row0 + t] = a.item_base + b;
+      continue;
+    }
     float ss = 0.f;
     if (a.normalize) {
       if (kVec) {
@@ -168,8 +204,8 @@ extern "C" int alad_pack_tokens(const alad_pack_args* a, void* stream) {
   using namespace alad;
   ALAD_REQUIRE(a != nullptr, "alad_pack_tokens: NULL args");
   ALAD_REQUIRE(a->B >= 0 && a->S >= 0 && a->d > 0, "alad_pack_tokens: bad shape");
-  ALAD_REQUIRE(a->mode >= 0 && a->mode <= 2, "alad_pack_tokens: unknown mode %d", a->mode);
-  ALAD_REQUIRE(a->Kp % ALAD_TILE_K == 0 && a->Kp >= (a->mode == 0 ? a->d : 3 * a->d),
+  ALAD_REQUIRE(a->mode >= 0 && a->mode <= 3, "alad_pack_tokens: unknown mode %d", a->mode);
+  ALAD_REQUIRE(a->Kp % ALAD_TILE_K == 0 && a->Kp >= (a->mode == 0 ? a->d : a->mode == 3 ? 2 * a->d : 3 * a->d),
                "alad_pack_tokens: Kp=%d too small or not a multiple of %d", a->Kp, ALAD_TILE_K);
   if (a->B == 0) return ALAD_OK;
   ALAD_REQUIRE(a->src && a->dst && a->count && a->row_off, "alad_pack_tokens: NULL pointer");

@@ -94,7 +94,7 @@ class GalleryWriter:
         """One ``model.forward_emb`` batch (alad/evaluation.py:114-130): img_emb [S_i,B,d], cap_emb
         [S_c,B,d] (sequence-major, as the backbone returns them), img_cls / cap_cls [B,d] global
         vectors, python length lists.  Tokens beyond slot 70 are dropped like the 71-slot container does."""
-        split = self.precision == "fp32"
+        split = scoring.PRECISION_CODE[self.precision]      # 0 bf16, 1 split-precision fp32, 2 tf32
         B = img_emb.shape[1]
         d = img_emb.shape[2]
         if self.d is None:
@@ -109,7 +109,7 @@ class GalleryWriter:
         nw = valid_counts(cap_length, 3, CONTAINER_SLOTS - 3)
         nw = np.minimum(nw, max(cap.shape[1] - 1, 0)).astype(np.int32)     # slots the backbone did not produce are zero rows:
         # they would be scored as zero vectors by the reference; lengths never exceed the produced extent in practice
-        self.cap_chunks.append((scoring.pack_tokens(cap, nw, slot0=1, mode=1 if split else 0), nw))
+        self.cap_chunks.append((scoring.pack_tokens(cap, nw, slot0=1, mode=scoring.WORD_MODE[split]), nw))
         # ---- images: only the distinct ones (items 0, 5, 10, ...), scored regions are slots 1 .. len-1 (R = 70)
         sel = np.nonzero(ids % 5 == 0)[0]
         if sel.size:
@@ -118,7 +118,7 @@ class GalleryWriter:
             img = img[first::step]
             nr = valid_counts([img_length[i] for i in sel], 1, CONTAINER_SLOTS - 1)
             nr = np.minimum(nr, max(img.shape[1] - 1, 0)).astype(np.int32)
-            self.img_chunks.append((scoring.pack_tokens(img, nr, slot0=1, mode=2 if split else 0), nr))
+            self.img_chunks.append((scoring.pack_tokens(img, nr, slot0=1, mode=scoring.REGION_MODE[split]), nr))
         self.img_glob[self.pos:self.pos + B] = img_cls.detach().to(self.device, torch.float32)
         self.cap_glob[self.pos:self.pos + B] = cap_cls.detach().to(self.device, torch.float32)
         self.img_lengths.extend(int(x) for x in img_length)
@@ -128,7 +128,7 @@ class GalleryWriter:
     def _concat(self, chunks, want_row_item):
         counts = np.concatenate([c for _, c in chunks]).astype(np.int32) if chunks else np.zeros(0, np.int32)
         row_off, n_rows = exclusive_cumsum(counts)
-        Kp = chunks[0][0].Kp if chunks else round_up(self.d * (3 if self.precision == "fp32" else 1), _cabi.TILE_K)
+        Kp = chunks[0][0].Kp if chunks else round_up(self.d * scoring.K_FACTOR[scoring.PRECISION_CODE[self.precision]], _cabi.TILE_K)
         data = torch.empty((max(n_rows, 1), Kp), dtype=torch.bfloat16, device=self.device)
         r = 0
         for p, _ in chunks:

@@ -457,7 +457,7 @@ class AlignmentGallery:
                 main.wait_event(ready[k])
             else:
                 cap_dev = self.captions[c0:c1]
-            scoring.pack_tokens(cap_dev, nw[c0:c1], slot0=1, mode=1 if split else 0, out=words_buf, out_row_item=cap_buf,
+            scoring.pack_tokens(cap_dev, nw[c0:c1], slot0=1, mode=scoring.WORD_MODE[split], out=words_buf, out_row_item=cap_buf,
                                 row_base=row_base + rows, item_base=c0 - item_origin)
             rows += int(nw[c0:c1].sum())
             if on_cpu:
@@ -482,7 +482,7 @@ class AlignmentGallery:
         # ---- operands: all regions, all words
         Lr = 1 + int(self.nr.max()) if self.Ni else 1
         im_dev = _upload_rows(self.images, self.img_start, self.img_step, self.Ni, Lr)
-        regions = scoring.pack_tokens(im_dev, self.nr, slot0=1, mode=2 if split else 0)
+        regions = scoring.pack_tokens(im_dev, self.nr, slot0=1, mode=scoring.REGION_MODE[split])
         roff, _ = exclusive_cumsum(self.nr)
         roff = np.concatenate([roff, [regions.n_rows]])
         tables, spans = [], []
@@ -492,7 +492,7 @@ class AlignmentGallery:
             tables.append(table)
         flat = np.concatenate([t.reshape(-1) for t in tables]) if sum(len(t) for t in tables) else np.zeros(1, np.uint32)
         tiles_all = scoring._to_dev(flat.view(np.int32), dev)
-        words = scoring.pack_tokens(self.captions, nw, slot0=1, mode=1 if split else 0, want_row_item=True)
+        words = scoring.pack_tokens(self.captions, nw, slot0=1, mode=scoring.WORD_MODE[split], want_row_item=True)
         n_rows, Kp = words.n_rows, words.Kp
         unit = 2 * _cabi.TILE_M
         n_units = (n_rows + unit - 1) // unit
@@ -578,7 +578,7 @@ class AlignmentGallery:
                 tl["gathered"].record(main)
                 tl["s0"].record(main)
             if n_loc:
-                words = scoring.Packed(words_b[:W * pad], W * pad, Kp, None, None, caps_b[:W * pad], 1 if split else 0)
+                words = scoring.Packed(words_b[:W * pad], W * pad, Kp, None, None, caps_b[:W * pad], scoring.WORD_MODE[split])
                 self._score(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, S[:, c0:c1])
             if tl:
                 tl["s1"].record(main)
@@ -627,7 +627,7 @@ class AlignmentGallery:
             if tl:
                 tl["s0"].record(main)
             if n_loc:
-                words = scoring.Packed(wa, self.world * pad, Kp, None, None, ca, 1 if split else 0)
+                words = scoring.Packed(wa, self.world * pad, Kp, None, None, ca, scoring.WORD_MODE[split])
                 self._score(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, S[:, c0:c1])
             if tl:
                 tl["s1"].record(main)
@@ -639,7 +639,7 @@ class AlignmentGallery:
         regions Packed over the image block, first packed region row of every local image [int64 numpy]).
         Used by the pair-list (two-stage) path, which scores many small tiles from the same operands."""
         from .tiling import exclusive_cumsum, padded_rows
-        split = self.precision == "fp32"
+        split = scoring.PRECISION_CODE[self.precision]      # 0 bf16, 1 split-precision fp32, 2 tf32
         lo, hi = self.lo, self.hi
         n_loc = hi - lo
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -650,18 +650,18 @@ class AlignmentGallery:
             assert np.array_equal(nr_loc, nr)
             return self.captions.packed, regions, row_off
         d = self.captions.shape[2]
-        Kp = ((d * (3 if split else 1) + _cabi.TILE_K - 1) // _cabi.TILE_K) * _cabi.TILE_K
+        Kp = ((d * scoring.K_FACTOR[split] + _cabi.TILE_K - 1) // _cabi.TILE_K) * _cabi.TILE_K
         regions = None
         if n_loc:
             Lr = 1 + int(nr.max())
             im_dev = _upload_rows(self.images, self.img_start + lo * self.img_step, self.img_step, n_loc, Lr)
-            regions = scoring.pack_tokens(im_dev, nr, slot0=1, mode=2 if split else 0)
+            regions = scoring.pack_tokens(im_dev, nr, slot0=1, mode=scoring.REGION_MODE[split])
         n_rows = int(self.nw.sum())
         words_buf = torch.empty((max(n_rows, 1), Kp), dtype=torch.bfloat16, device=dev)
         cap_buf = torch.full((max(padded_rows(n_rows), 2 * _cabi.TILE_M),), -1, dtype=torch.int32, device=dev)
         if self.Nc:
             self._pack_caption_range(0, self.Nc, words_buf, cap_buf, 0, split, dev)
-        words = scoring.Packed(words_buf, n_rows, Kp, self.nw, None, cap_buf, 1 if split else 0)
+        words = scoring.Packed(words_buf, n_rows, Kp, self.nw, None, cap_buf, scoring.WORD_MODE[split])
         return words, regions, row_off
 
     def scores(self, group=None):
@@ -671,7 +671,7 @@ class AlignmentGallery:
         only its 1/world share of the captions and the packed bf16 rows are all-gathered over
         NVLink (2.6 GB in total at COCO-5k) instead of every rank pulling all 5 GB over PCIe."""
         import torch.distributed as dist
-        split = self.precision == "fp32"
+        split = scoring.PRECISION_CODE[self.precision]      # 0 bf16, 1 split-precision fp32, 2 tf32
         lo, hi = self.lo, self.hi
         n_loc = hi - lo
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -695,14 +695,14 @@ class AlignmentGallery:
             return S
         nr, nw = self.nr[lo:hi], self.nw
         d = self.captions.shape[2]
-        Kp = ((d * (3 if split else 1) + _cabi.TILE_K - 1) // _cabi.TILE_K) * _cabi.TILE_K
+        Kp = ((d * scoring.K_FACTOR[split] + _cabi.TILE_K - 1) // _cabi.TILE_K) * _cabi.TILE_K
         # ---- regions of this image block
         def prep_regions():
             if not n_loc:
                 return None, None, 0
             Lr = 1 + int(nr.max())
             im_dev = _upload_rows(self.images, self.img_start + lo * self.img_step, self.img_step, n_loc, Lr)
-            reg = scoring.pack_tokens(im_dev, nr, slot0=1, mode=2 if split else 0)
+            reg = scoring.pack_tokens(im_dev, nr, slot0=1, mode=scoring.REGION_MODE[split])
             _, table, _ = build_region_tiles(nr, self.clamp[lo:hi])
             return reg, (scoring._to_dev(table.view(np.int32).reshape(-1), dev) if len(table) else None), len(table)
 
@@ -743,7 +743,7 @@ class AlignmentGallery:
             else:
                 bounds = [(0, self.Nc)]
             if len(bounds) == 1 and not on_cpu:
-                words = scoring.pack_tokens(self.captions, nw, slot0=1, mode=1 if split else 0, want_row_item=True)
+                words = scoring.pack_tokens(self.captions, nw, slot0=1, mode=scoring.WORD_MODE[split], want_row_item=True)
                 self._score(words, regions, tiles_dev, n_tiles, n_loc, self.Nc, S)
                 self._done(n_loc)
                 return S
@@ -770,7 +770,7 @@ class AlignmentGallery:
                     ready = torch.cuda.Event()
                     ready.record(prep)
                 main.wait_event(ready)
-                words = scoring.Packed(words_buf[b], rows, Kp, None, None, cap_buf[b], 1 if split else 0)
+                words = scoring.Packed(words_buf[b], rows, Kp, None, None, cap_buf[b], scoring.WORD_MODE[split])
                 self._score(words, regions, tiles_dev, n_tiles, n_loc, c1 - c0, S[:, c0:c1])
                 freed[b] = torch.cuda.Event()
                 freed[b].record(main)

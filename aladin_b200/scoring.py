@@ -14,7 +14,12 @@ import torch
 from . import _cabi
 from .tiling import exclusive_cumsum, padded_rows, round_up, valid_counts
 
-PRECISIONS = ("bf16", "fp32")
+PRECISIONS = ("bf16", "fp32", "tf32")
+# per precision code (0 bf16, 1 split-precision fp32, 2 tf32): pack mode of the word / region rows, row width in units of d
+PRECISION_CODE = {"bf16": 0, "fp32": 1, "tf32": 2}
+WORD_MODE = (0, 1, 3)
+REGION_MODE = (0, 2, 3)
+K_FACTOR = (1, 3, 2)
 # bench.py sets this to a list to collect (start_event, end_event, pairs, Kp) of every scoring launch
 kernel_timeline = None
 _precision = "bf16"
@@ -22,6 +27,10 @@ _precision = "bf16"
 
 def set_precision(mode):
     """'bf16': bf16 operands, fp32 accumulate (<= 1e-2 abs on scores).
+    'tf32': fp32 operands rounded to TF32 on the tensor cores' TF32 path (retrieval galleries: i2t / t2i /
+            AlignmentGallery): worst score entry 3e-4 .. 6e-4 relative -- NOT the 1e-4 parity mode, that is 'fp32' -- at half
+            the time of 'fp32' (COCO-5k: 0.74 s against 1.5 s; 'bf16' 0.33 s).  The small training-batch calls take the
+            'fp32' path for it.
     'fp32': split-precision hi/lo bf16 operands (3 tensor-core products per dot product,
     fp32-grade results, <= 1e-4 rel)."""
     global _precision
@@ -138,7 +147,7 @@ def pack_tokens(x, counts, *, slot0, mode=0, normalize=True, eps=1e-12, want_row
         if B and (counts.min() < 0 or counts.max() > max(S - slot0, 0)):
             raise ValueError("token counts exceed the container")
         row_off, n_rows = exclusive_cumsum(counts)
-    Kp = round_up(d * (1 if mode == 0 else 3), _cabi.TILE_K)
+    Kp = round_up(d * (1 if mode == 0 else 2 if mode == 3 else 3), _cabi.TILE_K)      # in 2-byte units (mode 3: fp32 rows)
     if out is not None:
         # pack into rows [row_base, row_base + n_rows) of a caller-owned buffer (sharded packing)
         assert out.dtype == torch.bfloat16 and out.shape[1] == Kp and out.is_contiguous() and row_base + n_rows <= out.shape[0]
@@ -167,7 +176,7 @@ def mrsw_scores_packed(words, regions, tiles_dev, n_tiles, Ni, Nc, out=None, num
     out_ptr: raw device address of a dense [Ni, Nc] fp32 matrix instead of `out` (another GPU's block through a
     peer mapping)."""
     lib = _cabi.lib()
-    assert words.Kp == regions.Kp
+    assert words.Kp == regions.Kp and (words.mode == 3) == (regions.mode == 3), "operands packed for different precisions"
     dev = words.data.device
     if out_ptr is None:
         if out is None:
@@ -181,7 +190,8 @@ def mrsw_scores_packed(words, regions, tiles_dev, n_tiles, Ni, Nc, out=None, num
         n_region_rows=regions.n_rows, Kp=words.Kp, row_cap=words.row_item.data_ptr(),
         ntiles=tiles_dev.data_ptr() if n_tiles else None, n_ntiles=n_tiles, S=s_ptr,
         ldS=s_ld, Ni=Ni, Nc=Nc, epilogue=0, num_ctas=num_ctas,
-        cta_group=cta_group, transpose_out=0, accumulate=1 if accumulate else 0)
+        cta_group=cta_group, transpose_out=0, accumulate=1 if accumulate else 0,
+        operand_format=1 if words.mode == 3 else 0)
     if kernel_timeline is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -215,7 +225,7 @@ def _scores_fused(max_x, max_counts, max_clamp, sum_x, sum_counts, slot0, precis
     max_counts = np.ascontiguousarray(max_counts, dtype=np.int32)
     sum_counts = np.ascontiguousarray(sum_counts, dtype=np.int32)
     clamp = np.ascontiguousarray(max_clamp, dtype=np.uint8) if max_clamp is not None else None
-    split = 1 if precision == "fp32" else 0
+    split = 1 if precision in ("fp32", "tf32") else 0      # the fused small-batch call has no TF32 variant: 'tf32' -> split precision
     nbytes = lib.alad_scores_fused_workspace_bytes(n_max, S_max, slot0, n_sum, S_sum, slot0, d, split)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=max_x.device)
     a = _cabi.ScoresFusedArgs(

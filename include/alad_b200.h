@@ -64,6 +64,8 @@ int alad_h2d_2d_staged(void* dst, int64_t dst_pitch, const void* src_host, int64
  *   mode 0: plain bf16 (Kp >= d)
  *   mode 1: split-precision "word side"   [hi | hi | lo] (Kp >= 3d)
  *   mode 2: split-precision "region side" [hi | lo | hi] (Kp >= 3d)
+ *   mode 3: TF32 operands: the normalised fp32 values, Kp / 2 floats per row (Kp >= 2d counts 2-byte units, so
+ *           the row pitch is 2 * Kp bytes in every mode)
  * so that <mode1 row, mode2 row> = hi*hi + hi*lo + lo*hi (fp32-grade dot product on the
  * bf16 tensor pipe).  row_item (optional) receives b for every packed row.
  * ------------------------------------------------------------------------------- */
@@ -130,6 +132,10 @@ typedef struct alad_mrsw_fwd_args {
   int32_t accumulate;            /* epilogue 0 only.  0: S is zeroed here first; 1: the launch ADDS its partial sums onto S
                                     (the caller zeroed it): several launches -- also from other GPUs, through a peer
                                     mapping of S -- each score a range of word rows of the same block (ABI >= 4) */
+  int32_t operand_format;        /* 0 = bf16 rows (pack modes 0-2), 1 = fp32 rows read as TF32 (pack mode 3): tcgen05.mma
+                                    kind::tf32, half the tensor rate of bf16 on twice the bytes: an intermediate precision (worst
+                                    score entry 3e-4 .. 6e-4 relative; the 1e-4 parity mode is the 3-term split-precision
+                                    bf16 one) at half that mode's time (ABI >= 5; append-only: older callers pass 0)    */
 } alad_mrsw_fwd_args;
 int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void* stream);
 

@@ -27,6 +27,22 @@ inline float dot_rows(const uint16_t* a, const uint16_t* b, int Kp) {
   return static_cast<float>(acc);
 }
 
+// operand_format 1: the rows are fp32 (Kp / 2 floats) and the tensor core reads them as TF32 (10-bit mantissa, truncated)
+inline float tf32_of(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u &= 0xffffe000u;
+  memcpy(&v, &u, 4);
+  return v;
+}
+inline float dot_rows_tf32(const uint16_t* a, const uint16_t* b, int Kp) {
+  const float* fa = reinterpret_cast<const float*>(a);
+  const float* fb = reinterpret_cast<const float*>(b);
+  double acc = 0.0;
+  for (int k = 0; k < Kp / 2; ++k) acc += static_cast<double>(tf32_of(fa[k])) * tf32_of(fb[k]);
+  return static_cast<float>(acc);
+}
+
 }  // namespace
 
 extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void*) {
@@ -45,6 +61,9 @@ extern "C" int alad_mrsw_scores_fwd(const alad_mrsw_fwd_args* a, void*) {
   const uint16_t* words = static_cast<const uint16_t*>(a->words);
   const uint16_t* regions = static_cast<const uint16_t*>(a->regions);
   const long long ld_seg = a->transpose_out ? 1 : a->ldS, ld_row = a->transpose_out ? a->ldS : 1;
+  auto dot_rows = [&](const uint16_t* x, const uint16_t* y, int Kp) {
+    return a->operand_format == 1 ? dot_rows_tf32(x, y, Kp) : ::dot_rows(x, y, Kp);
+  };
   for (int t = 0; t < a->n_ntiles; ++t) {
     const alad_ntile& nt = a->ntiles[t];
     if (a->epilogue == 1) {

@@ -22,7 +22,7 @@ def test_header_symbols_are_exported(built_lib):
     lib = _cabi.lib()
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by libalad_b200.so"
-    assert lib.alad_abi_version() == 4
+    assert lib.alad_abi_version() == 5
 
 
 def test_kernels_are_blackwell_native(built_lib):
@@ -49,11 +49,11 @@ def test_scoring_kernel_resources(built_lib):
     seen = 0
     lines = out.splitlines()
     for i, line in enumerate(lines):
-        if "mrsw_fwd_kernel" in line and i + 1 < len(lines):
+        if ("mrsw_fwd_kernel" in line or "mrsw_fwd_tf32_kernel" in line) and i + 1 < len(lines):
             m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", lines[i + 1])
             assert m, lines[i + 1]
             reg, stack, _, local = map(int, m.groups())
             assert stack == 0 and local == 0, f"spills in {line.strip()}"
             assert reg <= 168, f"{reg} registers in {line.strip()}"     # 135-136 today; a jump = different code generation
             seen += 1
-    assert seen == 3                                     # single-CTA, CTA-pair and the pair-list (two-stage) variants
+    assert seen == 5                                     # single-CTA, CTA-pair (bf16 and TF32 operands each) and the pair-list (two-stage) variant

@@ -16,7 +16,7 @@ def _containers(g):
     return images, captions, g["img_lens"].tolist(), g["cap_lens"].tolist()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "tf32"])
 def test_i2t_t2i_alignment_golden(precision):
     from aladin_b200 import evaluation as E, loss as L
     g = load_golden("retrieval")

@@ -92,6 +92,14 @@ def also_block(pk, quick=False):
             "issued_tflops": 3 * algo, "frac_issued_of_bf16_sustained_peak": 3 * algo / pk["bf16_sustained"],
             "frac_algorithmic_of_bf16_sustained_peak": algo / pk["bf16_sustained"],
             "what": "fp32-grade scores (<= 1e-4 rel) from split-precision bf16 operands: 3x the tensor FLOP of bf16 mode"}
+        # the same step on the TF32 tensor path (fp32 operands rounded to TF32, kind::tf32): an intermediate precision (worst
+        # entry 3e-4 .. 6e-4 relative; the 1e-4 parity mode is the split-precision one above)
+        ms, k_ms = retrieval_step(5000, 25000, "tf32", steps=2, warmup=2)
+        algo = 1.25e8 * flop_pair / (k_ms * 1e-3) / 1e12
+        out["config3_coco5k_tf32_mode"] = {
+            "ms_per_step": ms, "pairs_per_s": 1.25e8 / (ms * 1e-3), "kernel_ms": k_ms, "algorithmic_tflops": algo,
+            "frac_of_half_the_bf16_sustained_peak": algo / (0.5 * pk["bf16_sustained"]),
+            "what": "fp32 operands read as TF32 by the tensor core (half the bf16 rate, twice the operand bytes)"}
     # ---- config 5: two-stage retrieval
     out["config5_two_stage_coco5k"] = P2.measure(5000, 25000, 100, world=1, steps=3, warmup=2)
     return out

@@ -52,7 +52,7 @@ def main():
               f" | {c.get('FMNMX3', 0)} | {c.get('REDG', 0) + c.get('RED', 0) + c.get('ATOMG', 0)} | {c.get('SHFL', 0)} |")
     print("\n## Variants of the tensor-core / TMA instructions in the scoring kernels\n")
     for (mangled, c), name in zip(kernels.items(), demangle):
-        if "mrsw_fwd_kernel" not in name:
+        if "mrsw_fwd" not in name:
             continue
         short = re.sub(r"\(.*$", "", name).replace("void ", "")
         print(f"* `{short}`: " + ", ".join(f"{k[5:]} x{v}" for k, v in sorted(c.items()) if k.startswith("full:")))
