@@ -99,9 +99,10 @@ struct Staging {
   int next = 0;
   HostPool* pool = nullptr;
 };
-Staging& staging() {
-  static Staging s;
-  return s;
+// one set of staging buffers and events per device (events belong to the device they were created on)
+Staging& staging(int dev) {
+  static Staging s[16];
+  return s[dev & 15];
 }
 #endif
 
@@ -122,7 +123,9 @@ extern "C" int alad_h2d_2d_staged(void* dst, int64_t dst_pitch, const void* src_
 #else
   if ((size_t)width_bytes > kBufBytes)             // rows larger than a staging buffer: let the driver stage them
     return alad_h2d_2d(dst, dst_pitch, src_host, src_pitch, width_bytes, height, stream);
-  Staging& S = staging();
+  int dev = 0;
+  ALAD_CUDA(cudaGetDevice(&dev));
+  Staging& S = staging(dev);
   std::lock_guard<std::mutex> lock(S.m);
   if (!S.pool || S.pool->size() != n_threads) {
     delete S.pool;
