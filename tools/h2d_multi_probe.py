@@ -9,6 +9,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def measure(src, dst, iters=6):
@@ -36,7 +37,7 @@ def main():
     a = measure(src, dst)
     info = {}
     try:
-        from aladin_b200 import hostbind
+        import hostbind
         info = hostbind.bind_to_gpu(local)
     except Exception as e:                      # diagnostics only
         info = {"error": repr(e)}
