@@ -267,6 +267,200 @@ col_groupmax_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, 
   gmax[(long long)g * Nc + c] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
+// ------------------------------------------------------------------ both directions in ONE sweep of S
+// rank_sweep_kernel replaces rank_rows + col_count + col_groupmax (three reads of S) by one: a CTA owns one row
+// group of the threshold-select plan x FS_COLS columns; every thread keeps 8 columns in registers (two float4 per
+// row: a warp reads 512 contiguous bytes per load) and carries their running maximum and "ahead of the ground
+// truth" count down the rows, while the row statistics (entries ahead of the row's best ground-truth caption, row
+// arg-max) are reduced across the warp with redux.sync and collected per CTA in shared memory.  Cross-CTA merges
+// are integer atomics (adds, and a 64-bit max of (order key, column) = the total order's arg-best), so the results
+// do not depend on the order CTAs finish in.  Exact ties take a rare slow branch (index comparison).
+constexpr int FS_THREADS = 256;
+constexpr int FS_VEC = 2;                          // float4 per thread and row
+constexpr int FS_E = 4 * FS_VEC;                   // columns per thread
+constexpr int FS_COLS = FS_THREADS * FS_E;         // columns per CTA
+constexpr int FS_ROWS = 64;                        // rows per block of shared row statistics
+
+// largest float below a finite g (g + 0.f: no -0): "v >= g" as the strict comparison "v > below(g)"
+__device__ __forceinline__ float float_below(float g) {
+  const uint32_t u = __float_as_uint(g);
+  if (u == 0u) return __uint_as_float(0x80000001u);
+  return __uint_as_float((u & 0x80000000u) ? u + 1u : u - 1u);
+}
+__device__ __forceinline__ bool is_finite(float x) { return fabsf(x) < INFINITY; }
+// c += (v > t) as one compare and one predicated add (the compiler's own lowering of the C expression is a
+// three-instruction add / select / move chain per element, which makes the sweep issue-bound)
+__device__ __forceinline__ void count_gt(int& c, float v, float t) {
+#ifdef ALAD_CPU_EMU
+  c += v > t ? 1 : 0;
+#else
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c) : "f"(v), "f"(t));
+#endif
+}
+
+// The total order's tie rule (equal scores: the higher index is ahead) is folded into the threshold wherever a whole
+// CTA / thread sits on one side of the ground truth: entries after it compare against below(g) (>= g), entries before
+// it against g itself.  Only the threads whose columns (rows) straddle the ground truth, and non-finite ground-truth
+// scores (-inf of masked matrices), take the exact comparison.
+template <bool COUNT>
+__global__ void __launch_bounds__(FS_THREADS)
+rank_sweep_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int group, int img_off, int q_rows,
+                  int q_cols, int rows_per_group, const float* __restrict__ gt, int* __restrict__ rank,
+                  unsigned long long* __restrict__ best, int* __restrict__ count, float* __restrict__ gmax) {
+  __shared__ float s_gs[FS_ROWS];                  // the row's best ground-truth score (strict threshold) ...
+  __shared__ float s_ge[FS_ROWS];                  // ... and the value just below it (ties count)
+  __shared__ int s_gi[FS_ROWS];                    // its caption index; -1 none
+  __shared__ int s_mode[FS_ROWS];                  // 0 not a query row, 1 thresholds, 2 exact comparison
+  __shared__ int s_cnt[FS_ROWS];
+  __shared__ unsigned long long s_best[FS_ROWS];
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.y;
+  const int r0 = g * rows_per_group, r1 = min(Ni, r0 + rows_per_group);
+  const int cbase = blockIdx.x * FS_COLS + 4 * threadIdx.x;
+  auto col = [&](int e) { return cbase + (e >> 2) * (4 * FS_THREADS) + (e & 3); };
+  const int c_first = col(0), c_last = col(FS_E - 1);
+  float cmax[FS_E], cthr[FS_E];
+  int ccnt[FS_E];
+  bool c_exact = false;
+#pragma unroll
+  for (int e = 0; e < FS_E; ++e) {
+    const int c = col(e);
+    cmax[e] = -INFINITY;
+    ccnt[e] = 0;
+    cthr[e] = INFINITY;                              // non-query columns: nothing is ahead
+    if (COUNT && c < q_cols) {
+      const float gv = __ldg(gt + c) + 0.f;
+      const int gl = c / group - img_off;            // block-local row of the caption's image
+      if (!is_finite(gv) || (gl >= r0 && gl < r1 - 1)) c_exact = true;
+      else cthr[e] = gl < r0 ? float_below(gv) : gv;
+    }
+  }
+  bool whole[FS_VEC];                               // the float4 lies inside the row
+#pragma unroll
+  for (int u = 0; u < FS_VEC; ++u) whole[u] = cbase + u * (4 * FS_THREADS) + 3 < Nc;
+  auto load_row = [&](int r, float* v) {
+    const float* rowp = S + (long long)r * ldS;
+#pragma unroll
+    for (int u = 0; u < FS_VEC; ++u) {
+      const int c4 = cbase + u * (4 * FS_THREADS);
+      if (whole[u]) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(rowp + c4));
+        v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
+      } else {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v[4 * u + w] = (c4 + w < Nc) ? __ldg(rowp + c4 + w) : -INFINITY;
+      }
+    }
+  };
+  auto consume = [&](int rb, int rr, const float* v) {
+    const int r = rb + rr;
+    // ---- columns: running maximum, images ahead of the caption's ground truth
+#pragma unroll
+    for (int e = 0; e < FS_E; ++e) cmax[e] = fmaxf(cmax[e], v[e]);
+    if (COUNT) {
+      if (!c_exact) {
+#pragma unroll
+        for (int e = 0; e < FS_E; ++e) count_gt(ccnt[e], v[e], cthr[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < FS_E; ++e) {
+          const int c = col(e);
+          if (c < q_cols) ccnt[e] += ahead(v[e], img_off + r, __ldg(gt + c), c / group) ? 1 : 0;
+        }
+      }
+    }
+    // ---- row: captions ahead of the image's best ground truth, arg-max caption
+    const int mode = s_mode[rr];
+    if (mode == 0) return;                           // uniform over the CTA
+    const int gi = s_gi[rr];
+    int cnt = 0;
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < FS_E; ++e) tmax = fmaxf(tmax, v[e]);
+    if (mode == 1 && (gi < c_first || gi >= c_last)) {
+      const float thr = gi < c_first ? s_ge[rr] : s_gs[rr];
+#pragma unroll
+      for (int e = 0; e < FS_E; ++e) count_gt(cnt, v[e], thr);
+    } else {
+      const float gs = s_gs[rr];
+#pragma unroll
+      for (int e = 0; e < FS_E; ++e) cnt += (col(e) < Nc && ahead(v[e], col(e), gs, gi)) ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    const unsigned key = order_key(tmax);
+    const unsigned mk = __reduce_max_sync(0xffffffffu, key);
+    if (key == mk) {                                 // normally one lane of the warp
+      const float top = key_to_float(mk);
+      int idx = -1;
+#pragma unroll
+      for (int e = 0; e < FS_E; ++e)
+        if (v[e] == top && col(e) < Nc) idx = col(e);           // columns ascend with e: the largest index stays
+      if (idx >= 0) atomicMax(&s_best[rr], ((unsigned long long)mk << 32) | (unsigned)idx);
+    }
+    if (lane == 0 && cnt) atomicAdd(&s_cnt[rr], cnt);
+  };
+  for (int rb = r0; rb < r1; rb += FS_ROWS) {
+    const int nrows = min(FS_ROWS, r1 - rb);
+    if ((int)threadIdx.x < nrows) {
+      const int r = rb + threadIdx.x;
+      float gs = INFINITY;
+      int gi = -1, mode = 0;
+      if (r < q_rows) {
+        const long long g0 = (long long)group * (img_off + r);
+        for (int j = 0; j < group; ++j) {
+          const long long c = g0 + j;
+          if (c < Nc) {
+            const float v = __ldg(S + (long long)r * ldS + c);
+            if (gi < 0 || ahead(v, (int)c, gs, gi)) {
+              gs = v;
+              gi = (int)c;
+            }
+          }
+        }
+        if (gi < 0) gs = INFINITY;                   // no ground truth in range: nothing is ahead, rank = Nc
+        gs += 0.f;
+        mode = (gi < 0 || is_finite(gs)) ? 1 : 2;
+      }
+      s_gs[threadIdx.x] = gs;
+      s_ge[threadIdx.x] = is_finite(gs) ? float_below(gs) : gs;
+      s_gi[threadIdx.x] = gi;
+      s_mode[threadIdx.x] = mode;
+      s_cnt[threadIdx.x] = 0;
+      s_best[threadIdx.x] = 0ull;
+    }
+    __syncthreads();
+    float va[FS_E], vb[FS_E];                        // two rows in flight
+    load_row(rb, va);
+    for (int rr = 0; rr < nrows; rr += 2) {
+      if (rr + 1 < nrows) load_row(rb + rr + 1, vb);
+      consume(rb, rr, va);
+      if (rr + 2 < nrows) load_row(rb + rr + 2, va);
+      if (rr + 1 < nrows) consume(rb, rr + 1, vb);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nrows && s_mode[threadIdx.x] != 0) {
+      const int r = rb + threadIdx.x;
+      const int add = s_gi[threadIdx.x] >= 0 ? s_cnt[threadIdx.x] : (blockIdx.x == 0 ? Nc : 0);
+      if (add) atomicAdd(rank + r, add);
+      if (s_best[threadIdx.x]) atomicMax(best + r, s_best[threadIdx.x]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int e = 0; e < FS_E; ++e) {
+    const int c = col(e);
+    if (c < q_cols) {
+      gmax[(long long)g * q_cols + c] = cmax[e];
+      if (COUNT && ccnt[e]) atomicAdd(count + c, ccnt[e]);
+    }
+  }
+}
+
+__global__ void rank_sweep_finish_kernel(const unsigned long long* __restrict__ best, int q_rows, int* __restrict__ top1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q_rows) top1[i] = best[i] ? (int)(unsigned)(best[i] & 0xffffffffull) : -1;
+}
+
 // 8 warps per CTA, 32 captions per CTA (4 per warp); the [G][32] tile of group maxima goes through shared
 // memory so that the global reads stay coalesced
 template <int PER_LANE>                                        // keys per lane: ceil(G / 32) rounded up to 4, 8 or 11
@@ -625,6 +819,105 @@ extern "C" int alad_col_topk_select(const float* S, int64_t ldS, int32_t Ni, int
     heap_set = heap_smem;
   }
   col_topk_kernel<<<dim3(col_blocks, 1), 32, heap_smem, st>>>(S, ldS, Ni, Nc, k, img_off, 1, out_score, out_idx, ovf_list,
+                                                              ovf_n);
+  ALAD_CUDA(cudaGetLastError());
+  return ALAD_OK;
+}
+
+namespace alad {
+struct FusedPlan {
+  SelectPlan sel;
+  size_t off_best, off_gt, bytes;
+};
+static FusedPlan fused_plan(int Ni, int q_rows, int q_cols, int k) {
+  FusedPlan f;
+  f.sel = select_plan(Ni, q_cols, k);
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t o = up(f.sel.bytes);
+  f.off_best = o; o += up(sizeof(unsigned long long) * (size_t)(q_rows > 0 ? q_rows : 1));
+  f.off_gt = o;   o += up(sizeof(float) * (size_t)(q_cols > 0 ? q_cols : 1));
+  f.bytes = o + 256;
+  return f;
+}
+}  // namespace alad
+
+extern "C" int64_t alad_rank_fused_workspace_bytes(int32_t Ni, int32_t q_rows, int32_t q_cols, int32_t k) {
+  if (Ni < 0 || q_rows < 0 || q_cols < 0 || k <= 0) return 0;
+  return (int64_t)alad::fused_plan(Ni, q_rows, q_cols, k).bytes;
+}
+
+extern "C" int alad_rank_fused(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t group, int32_t img_off,
+                               int32_t q_rows, int32_t q_cols, int32_t k, const float* gt, int32_t* rank, int32_t* top1,
+                               int32_t* count, float* out_score, int32_t* out_idx, void* workspace, void* stream) {
+  using namespace alad;
+  ALAD_REQUIRE(Ni >= 0 && Nc >= 0 && ldS >= Nc && group > 0, "alad_rank_fused: bad shape");
+  ALAD_REQUIRE(q_rows >= 0 && q_rows <= Ni && q_cols >= 0 && q_cols <= Nc, "alad_rank_fused: q_rows=%d q_cols=%d out of range",
+               q_rows, q_cols);
+  ALAD_REQUIRE(k > 0 && k <= 256, "alad_rank_fused: k=%d out of range", k);
+  ALAD_REQUIRE((rank && top1) || q_rows == 0, "alad_rank_fused: NULL pointer");
+  ALAD_REQUIRE((out_score && out_idx) || q_cols == 0, "alad_rank_fused: NULL pointer");
+  ALAD_REQUIRE(S || Ni == 0 || Nc == 0, "alad_rank_fused: NULL pointer");
+  ALAD_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "alad_rank_fused: bad workspace");
+  cudaStream_t st = as_stream(stream);
+  const FusedPlan fp = fused_plan(Ni, q_rows, q_cols, k);
+  const SelectPlan& pl = fp.sel;
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  // count != NULL without gt: this block holds every query caption's image, the ground-truth scores are its own entries
+  const float* gt_use = gt;
+  if (count && !gt && q_cols > 0) {
+    float* own = reinterpret_cast<float*>(w + fp.off_gt);
+    ALAD_CUDA(cudaMemsetAsync(own, 0, sizeof(float) * (size_t)q_cols, st));
+    if (Ni > 0) col_gt_kernel<<<(q_cols + 255) / 256, 256, 0, st>>>(S, ldS, Ni, q_cols, group, img_off, own);
+    gt_use = own;
+  }
+  const bool fused = pl.select && pl.threshold && Nc > 0 && q_cols > 0 && (ldS & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+  if (!fused) {          // small or unaligned blocks: the one-purpose kernels
+    int rc = q_rows > 0 ? alad_rank_rows(S, ldS, q_rows, Nc, group, img_off, rank, top1, stream) : ALAD_OK;
+    if (rc == ALAD_OK && count && q_cols > 0) rc = alad_col_count(S, ldS, Ni, q_cols, group, img_off, gt_use, count, stream);
+    if (rc == ALAD_OK && q_cols > 0) rc = alad_col_topk_select(S, ldS, Ni, q_cols, k, img_off, out_score, out_idx, workspace, stream);
+    return rc;
+  }
+  float* tau = reinterpret_cast<float*>(w + pl.off_tau);
+  int* cnt = reinterpret_cast<int*>(w + pl.off_cnt);
+  int* ovf_n = cnt + q_cols;
+  int* ovf_list = reinterpret_cast<int*>(w + pl.off_ovf);
+  float* cs = reinterpret_cast<float*>(w + pl.off_cs);
+  int* ci = reinterpret_cast<int*>(w + pl.off_ci);
+  float* gmax = reinterpret_cast<float*>(w + pl.off_gmax);
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(w + fp.off_best);
+  ALAD_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)q_cols + 1), st));
+  if (q_rows > 0) {
+    ALAD_CUDA(cudaMemsetAsync(rank, 0, sizeof(int32_t) * (size_t)q_rows, st));
+    ALAD_CUDA(cudaMemsetAsync(best, 0, sizeof(unsigned long long) * (size_t)q_rows, st));
+  }
+  if (count) ALAD_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)q_cols, st));
+  // rows beyond the query columns still count for the i2t direction: the sweep covers all Nc columns
+  dim3 gs((unsigned)((Nc + FS_COLS - 1) / FS_COLS), (unsigned)pl.G);
+  if (count)
+    rank_sweep_kernel<true><<<gs, FS_THREADS, 0, st>>>(S, ldS, Ni, Nc, group, img_off, q_rows, q_cols, pl.rows_per_group, gt_use,
+                                                       rank, best, count, gmax);
+  else
+    rank_sweep_kernel<false><<<gs, FS_THREADS, 0, st>>>(S, ldS, Ni, Nc, group, img_off, q_rows, q_cols, pl.rows_per_group, nullptr,
+                                                        rank, best, nullptr, gmax);
+  if (q_rows > 0) rank_sweep_finish_kernel<<<(q_rows + 255) / 256, 256, 0, st>>>(best, q_rows, top1);
+  const unsigned col_blocks = (unsigned)((q_cols + 31) / 32);
+  const size_t tile_bytes = (size_t)pl.G * 33 * sizeof(float);
+  if (pl.G <= 128)      col_threshold_kernel<4><<<col_blocks, 256, tile_bytes, st>>>(gmax, q_cols, pl.G, k, tau);
+  else if (pl.G <= 256) col_threshold_kernel<8><<<col_blocks, 256, tile_bytes, st>>>(gmax, q_cols, pl.G, k, tau);
+  else                  col_threshold_kernel<SEL_MAX_G / 32><<<col_blocks, 256, tile_bytes, st>>>(gmax, q_cols, pl.G, k, tau);
+  dim3 g3(col_blocks, (unsigned)((Ni + SEL_CHUNK - 1) / SEL_CHUNK)), b3(32, SEL_ROWS);
+  col_collect_kernel<<<g3, b3, 0, st>>>(S, ldS, Ni, q_cols, img_off, tau, pl.cap, cnt, cs, ci);
+  const size_t sel_smem = (size_t)SELECT_WARPS * pl.cap * sizeof(float2);
+  col_select_kernel<<<(unsigned)((q_cols + SELECT_WARPS - 1) / SELECT_WARPS), 32 * SELECT_WARPS, sel_smem, st>>>(
+      cnt, cs, ci, q_cols, k, pl.cap, out_score, out_idx, ovf_list, ovf_n);
+  const size_t heap_smem = (size_t)k * 32 * 8;
+  static thread_local size_t heap_set = 0;
+  if (heap_smem > 48 * 1024 && heap_smem > heap_set) {
+    ALAD_CUDA(cudaFuncSetAttribute(col_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heap_smem));
+    heap_set = heap_smem;
+  }
+  col_topk_kernel<<<dim3(col_blocks, 1), 32, heap_smem, st>>>(S, ldS, Ni, q_cols, k, img_off, 1, out_score, out_idx, ovf_list,
                                                               ovf_n);
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;

@@ -63,6 +63,34 @@ def col_topk(S, k, img_off=0, splits=None):
     return cs, ci
 
 
+def rank_fused(S, k, img_off=0, q_rows=None, q_cols=None, gt=None, count=True, group=5):
+    """Both directions of one score block in two sweeps of S (alad_rank_fused): i2t (rank, top1) of rows [0, q_rows)
+    over all captions, t2i top-k (score[q_cols, k], global image idx[q_cols, k]) of captions [0, q_cols) over the block's
+    rows and -- with count=True -- their "images ahead of the ground truth" counts against `gt` (default: the block's
+    own entries, i.e. a block that holds every image).  Returns (rank, top1, count or None, topk_score, topk_idx);
+    identical to rank_rows + col_gt + col_count + col_topk on the same block."""
+    Ni, Nc, ld = _check_S(S)
+    q_rows = Ni if q_rows is None else q_rows
+    q_cols = Nc if q_cols is None else q_cols
+    dev = S.device
+    rank = torch.empty(q_rows, dtype=torch.int32, device=dev)
+    top1 = torch.empty(q_rows, dtype=torch.int32, device=dev)
+    cnt = torch.empty(q_cols, dtype=torch.int32, device=dev) if count else None
+    ts = torch.empty((q_cols, k), dtype=torch.float32, device=dev)
+    ti = torch.empty((q_cols, k), dtype=torch.int32, device=dev)
+    if gt is not None:
+        assert count and gt.is_cuda and gt.dtype == torch.float32 and gt.numel() == q_cols and gt.is_contiguous()
+    nbytes = _cabi.lib().alad_rank_fused_workspace_bytes(Ni, q_rows, q_cols, k)
+    ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+    _cabi.check(_cabi.lib().alad_rank_fused(S.data_ptr(), ld, Ni, Nc, group, img_off, q_rows, q_cols, k,
+                                             gt.data_ptr() if gt is not None else None, rank.data_ptr(), top1.data_ptr(),
+                                             cnt.data_ptr() if count else None, ts.data_ptr(), ti.data_ptr(), ws.data_ptr(),
+                                             _cabi.stream_ptr()), "alad_rank_fused")
+    if count and gt is None:
+        _cabi.launch_count["kernels"] += 1          # the block's own ground-truth gather
+    return rank, top1, cnt, ts, ti
+
+
 def topk_merge(cand_score, cand_idx):
     """Merge P sorted candidate lists per caption: [P,Nc,k] -> ([Nc,k], [Nc,k])."""
     P, Nc, k = cand_score.shape

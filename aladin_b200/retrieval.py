@@ -803,20 +803,34 @@ def rank_device(S, npts, img_off=0, n_images_total=None, k=50, group=None, ops=r
     mark("start")
     # ---------------- i2t: rows (queries = images < npts), gallery = all captions
     q_loc = max(0, min(n_loc, npts - img_off))
-    rank_i, top1_i = ops.rank_rows(S[:q_loc], 5, img_off)
-    mark("rank_rows")
     # ---------------- t2i: columns (queries = captions < 5*npts), gallery = all images
     ncq = min(Nc, 5 * npts)
     Sq = S[:, :ncq]
-    gt = torch.zeros(ncq, dtype=torch.float32, device=S.device)
-    ops.col_gt(Sq, gt, 5, img_off)
-    cs, ci = ops.col_topk(Sq, k, img_off)
-    ts, ti = ops.topk_merge(cs, ci)
-    mark("col_gt_topk")
-    if not dist_on:
-        count = ops.col_count(Sq, gt, 5, img_off)
-        mark("col_count")
-        return rank_i, top1_i, count, ts, ti, None
+    fused = getattr(ops, "rank_fused", None)
+    if fused is not None and S.is_cuda:
+        # one sweep of S for the i2t ranks, the group maxima of the top-k select and (single shard) the t2i counts, one for
+        # the top-k candidates -- instead of the four sweeps of rank_rows / col_count / col_topk
+        if not dist_on:
+            rank_i, top1_i, count, ts, ti = fused(S, k, img_off, q_loc, ncq)
+            mark("rank_fused")
+            return rank_i, top1_i, count, ts, ti, None
+        gt = torch.zeros(ncq, dtype=torch.float32, device=S.device)
+        ops.col_gt(Sq, gt, 5, img_off)
+        rank_i, top1_i, _, ts, ti = fused(S, k, img_off, q_loc, ncq, count=False)
+        mark("rank_rows")
+        mark("col_gt_topk")
+    else:
+        rank_i, top1_i = ops.rank_rows(S[:q_loc], 5, img_off)
+        mark("rank_rows")
+        gt = torch.zeros(ncq, dtype=torch.float32, device=S.device)
+        ops.col_gt(Sq, gt, 5, img_off)
+        cs, ci = ops.col_topk(Sq, k, img_off)
+        ts, ti = ops.topk_merge(cs, ci)
+        mark("col_gt_topk")
+        if not dist_on:
+            count = ops.col_count(Sq, gt, 5, img_off)
+            mark("col_count")
+            return rank_i, top1_i, count, ts, ti, None
     world = dist.get_world_size(group)
     if bounds is None:
         bounds = [shard_bounds(Ni_total, world, r) for r in range(world)]
@@ -943,11 +957,9 @@ def streaming_ranks(images, captions, img_lens, cap_lens, n_images, img_start=0,
             Sb = score(lo, hi, 0, n_rows, n_units)
         else:
             Sb = S_buf[:hi - lo].zero_()
-        r, t1 = ranking.rank_rows(Sb, 5, lo)
+        r, t1, cnt, cs, ci = ranking.rank_fused(Sb, k, lo, gt=gt)
         rank_i[lo:hi], top1_i[lo:hi] = r, t1
-        count += ranking.col_count(Sb, gt, 5, lo)
-        cs, ci = ranking.col_topk(Sb, k, lo)
-        cs, ci = ranking.topk_merge(cs, ci)
+        count += cnt
         if run_s is None:
             run_s, run_i = cs, ci
         else:

@@ -394,6 +394,19 @@ int alad_col_topk(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t k
 int64_t alad_col_topk_select_workspace_bytes(int32_t Ni, int32_t Nc, int32_t k);
 int alad_col_topk_select(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t k, int32_t img_off,
                          float* out_score, int32_t* out_idx, void* workspace, void* stream);
+/* Both directions of one score block in TWO sweeps of S instead of four (replaces alad_rank_rows + alad_col_count +
+ * alad_col_topk_select on the same block; alad/evaluation.py:213-223 and :303-308 in one pass): the first sweep carries
+ * the i2t counts / arg-max of rows [0, q_rows), the per-caption group maxima of the threshold select and -- when
+ * `count` is given -- the t2i "images ahead of the ground truth" counts of captions [0, q_cols); the second sweep
+ * collects the top-k candidates.  rank/top1 are [q_rows] (i2t gallery = all Nc captions), count [q_cols] or NULL,
+ * out_score/out_idx [q_cols, k] (t2i gallery = all Ni rows of the block).  gt [q_cols]: the captions' ground-truth
+ * scores (after the exchange between shards); gt == NULL with count != NULL takes them from the block itself (single
+ * block).  Small or unaligned blocks run the one-purpose kernels.  Results are identical to the separate entry points.
+ * Workspace: alad_rank_fused_workspace_bytes, 16-byte aligned. */
+int64_t alad_rank_fused_workspace_bytes(int32_t Ni, int32_t q_rows, int32_t q_cols, int32_t k);
+int alad_rank_fused(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t group, int32_t img_off, int32_t q_rows,
+                    int32_t q_cols, int32_t k, const float* gt, int32_t* rank, int32_t* top1, int32_t* count,
+                    float* out_score, int32_t* out_idx, void* workspace, void* stream);
 /* merge P sorted candidate lists per caption (after the all-gather across shards). */
 int alad_topk_merge(const float* cand_score, const int32_t* cand_idx, int32_t P, int32_t Nc, int32_t k,
                     float* out_score, int32_t* out_idx, void* stream);

@@ -155,6 +155,19 @@ inline T __reduce_add_sync(unsigned, T v) {
   return (T)acc;
 }
 template <class T>
+inline T __reduce_max_sync(unsigned, T v) {
+  using namespace cuda_emu;
+  cta->xchg[tid] = (uint64_t)(int64_t)v;
+  warp_barrier();
+  T acc = (T)(int64_t)cta->xchg[tid & ~31];
+  for (int l = 1; l < 32; ++l) {
+    const T o = (T)(int64_t)cta->xchg[(tid & ~31) | l];
+    acc = o > acc ? o : acc;
+  }
+  warp_barrier();
+  return acc;
+}
+template <class T>
 inline T __ldg(const T* p) { return *p; }
 template <class T>
 inline T __ldcg(const T* p) { return *p; }
@@ -171,6 +184,11 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicMax(int* p, int v) {
   int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
   return old;
 }

@@ -217,6 +217,70 @@ def test_ranking_emulated(rank, Ni, ties, k):
         np.testing.assert_array_equal(top1, t1)
 
 
+def _fused(rank, S, Nc, q_rows, q_cols, k, img_off, gt, want_count):
+    Ni = S.shape[0]
+    ld = S.strides[0] // 4
+    rk, top1 = np.full(q_rows, -7, np.int32), np.full(q_rows, -7, np.int32)
+    cnt = np.full(q_cols, -7, np.int32) if want_count else None
+    ts, ti = np.zeros((q_cols, k), np.float32), np.zeros((q_cols, k), np.int32)
+    ws = workspace(rank.alad_rank_fused_workspace_bytes(Ni, q_rows, q_cols, k))
+    ok(rank, rank.alad_rank_fused(p(S), ld, Ni, Nc, 5, img_off, q_rows, q_cols, k, p(gt), p(rk), p(top1), p(cnt), p(ts), p(ti),
+                                  p(ws), None))
+    return rk, top1, cnt, ts, ti
+
+
+@pytest.mark.parametrize("Ni,Nc,q_rows,q_cols,k,img_off,mode", [(264, 60, 264, 60, 10, 0, "own")] + big(
+    (300, 204, 300, 204, 10, 0, "ties"), (270, 2100, 200, 1000, 12, 3, "given"), (260, 52, 260, 52, 10, 0, "nocount"),
+    (260, 48, 260, 48, 10, 0, "masked"), (30, 150, 30, 150, 10, 0, "own"), (264, 61, 264, 61, 10, 0, "own")))
+def test_rank_fused_emulated(rank, Ni, Nc, q_rows, q_cols, k, img_off, mode):
+    """alad_rank_fused (one sweep for rows + counts + group maxima, one for the candidates) == the one-purpose entry
+    points on the same block: query sub-ranges, an image offset, exact ties, -inf (masked) scores, a column count that is
+    not a multiple of four (unaligned: falls back), blocks too small for the threshold select (fall back)."""
+    r = np.random.RandomState(Ni + Nc)
+    S = r.standard_normal((Ni, Nc)).astype(np.float32)
+    if mode == "ties":
+        S = np.round(S * 2) / 2
+    if mode == "masked":
+        S[r.rand(Ni, Nc) < 0.6] = -np.inf
+        S[5] = -np.inf
+    gt = None
+    if mode in ("given", "nocount"):
+        gt = r.standard_normal(q_cols).astype(np.float32)
+        gt[::3] = S[(np.arange(q_cols) // 5) % Ni, np.arange(q_cols)][::3]
+    rk, top1, cnt, ts, ti = _fused(rank, S, Nc, q_rows, q_cols, k, img_off, gt if mode == "given" else None, mode != "nocount")
+    # the one-purpose kernels on the same block
+    rk0, top10 = np.zeros(q_rows, np.int32), np.zeros(q_rows, np.int32)
+    ok(rank, rank.alad_rank_rows(p(S), Nc, q_rows, Nc, 5, img_off, p(rk0), p(top10), None))
+    np.testing.assert_array_equal(rk, rk0)
+    np.testing.assert_array_equal(top1, top10)
+    if mode != "nocount":
+        if mode != "given":
+            gt = np.zeros(q_cols, np.float32)
+            ok(rank, rank.alad_col_gt(p(S), Nc, Ni, q_cols, 5, img_off, p(gt), None))
+        cnt0 = np.zeros(q_cols, np.int32)
+        ok(rank, rank.alad_col_count(p(S), Nc, Ni, q_cols, 5, img_off, p(gt), p(cnt0), None))
+        np.testing.assert_array_equal(cnt, cnt0)
+    s0, i0 = np.zeros((q_cols, k), np.float32), np.zeros((q_cols, k), np.int32)
+    ws = workspace(rank.alad_col_topk_select_workspace_bytes(Ni, q_cols, k))
+    ok(rank, rank.alad_col_topk_select(p(S), Nc, Ni, q_cols, k, img_off, p(s0), p(i0), p(ws), None))
+    np.testing.assert_array_equal(ti, i0)
+    np.testing.assert_array_equal(ts, s0)
+    # and numpy's stable argsort reversed, the reference's order (alad/evaluation.py:213-223, 303-308)
+    for i in range(0, q_rows, 37):
+        inds = _stable_desc(S[i])
+        assert top1[i] == inds[0]
+        g0 = 5 * (img_off + i)
+        if g0 < Nc:
+            pos = np.empty(Nc, np.int64)
+            pos[inds] = np.arange(Nc)
+            assert rk[i] == pos[g0:g0 + 5].min()
+        else:
+            assert rk[i] == Nc
+    for c in range(0, q_cols, 11):
+        inds = _stable_desc(S[:, c])
+        np.testing.assert_array_equal(ti[c], inds[:k] + img_off)
+
+
 def test_ranking_emulated_reference_golden(rank):
     from conftest import load_golden
     g = load_golden("retrieval")
