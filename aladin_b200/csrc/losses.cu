@@ -326,6 +326,11 @@ __global__ void __launch_bounds__(LT) triplet_finish_kernel(const TripletParams 
 }
 
 // ------------------------------------------------------------------------------------ listnet
+// Three sweeps of T and M (statistics, cost, gradient); each sweep serves BOTH softmax directions from one read:
+// a CTA owns SW columns x one row chunk, thread (tx, ty) the columns tx + 32u of the rows ty, ty + CS, ...  The
+// column direction accumulates down the rows in registers; the row direction is reduced across the warp that holds
+// the row's SW columns and leaves one partial per (strip, row).  The last CTA to finish a strip / a row chunk merges
+// that strip's column partials / that chunk's row partials in a fixed order (deterministic).
 // per-row / per-column softmax statistics of tau*M (student) and T (teacher)
 struct SoftStats {
   float m_s, iz_s, m_t, iz_t;   // max and 1 / sum(exp(x - max)): one reciprocal per row / column, not per element
@@ -363,7 +368,9 @@ struct ListnetParams {
   float* rcost;        // [B]
   float* ccost;        // [B]
   float* cpart;        // [n_chunks][B][4] per-chunk column partials: softmax stats, then (cost, A)
+  float* rpart;        // [n_strips][B][4] per-strip row partials: softmax stats, then (cost, A)
   unsigned int* strip_cnt;   // [n_strips]
+  unsigned int* chunk_cnt;   // [n_chunks]
   unsigned int* counter;
 };
 
@@ -377,154 +384,136 @@ __device__ __forceinline__ void listnet_elem(float xm, float xt, const SoftStats
   pout = pr;
 }
 
+// sweep 1: softmax statistics of every row and every column
 __global__ void __launch_bounds__(LT) listnet_stats_kernel(const ListnetParams p) {
-  __shared__ float sf[LT / 32];
-  __shared__ float sm[4][LT / 32];
   __shared__ float cs[CS][SW][4];
   const int B = p.B;
-  if ((int)blockIdx.x < B) {
-    // ---------------- row i: softmax over j (sentence retrieval, dim=1)
-    const int i = blockIdx.x;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n_strips = n_strips_of(B), nch = n_chunks_of(B);
+  const int strip = blockIdx.x % n_strips, chunk = blockIdx.x / n_strips;
+  const int j0 = strip * SW + tx;
+  const int chunk_rows = chunk_rows_of(B);
+  const int r_begin = chunk * chunk_rows, r_end = min(B, r_begin + chunk_rows);
+  float ms[CV], zs[CV], mt[CV], zt[CV];
+#pragma unroll
+  for (int u = 0; u < CV; ++u) {
+    ms[u] = -INFINITY; zs[u] = 0.f; mt[u] = -INFINITY; zt[u] = 0.f;
+  }
+  for (int i = r_begin + ty; i < r_end; i += CS) {
     const float* rm = p.M + (long long)i * p.ldM;
     const float* rt = p.T + (long long)i * p.ldT;
-    float ms = -INFINITY, zs = 0.f, mt = -INFINITY, zt = 0.f;
-#pragma unroll 4
-    for (int j = threadIdx.x; j < B; j += LT) {
-      online_update(ms, zs, p.tau * __ldg(rm + j));
-      online_update(mt, zt, __ldg(rt + j));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      online_merge(ms, zs, __shfl_xor_sync(0xffffffffu, ms, o), __shfl_xor_sync(0xffffffffu, zs, o));
-      online_merge(mt, zt, __shfl_xor_sync(0xffffffffu, mt, o), __shfl_xor_sync(0xffffffffu, zt, o));
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-      sm[0][warp] = ms; sm[1][warp] = zs; sm[2][warp] = mt; sm[3][warp] = zt;
-    }
-    __syncthreads();
-    SoftStats st;
-    {
-      float a = sm[0][0], b = sm[1][0], c = sm[2][0], d = sm[3][0];
-      for (int w = 1; w < LT / 32; ++w) {
-        online_merge(a, b, sm[0][w], sm[1][w]);
-        online_merge(c, d, sm[2][w], sm[3][w]);
-      }
-      st.m_s = a; st.iz_s = 1.f / b; st.m_t = c; st.iz_t = 1.f / d;
-    }
-    __syncthreads();
-    float cost = 0.f, A = 0.f;
-#pragma unroll 4
-    for (int j = threadIdx.x; j < B; j += LT) {
-      float c, a, pr;
-      listnet_elem(__ldg(rm + j), __ldg(rt + j), st, p.tau, p.eps, c, a, pr);
-      cost += c;
-      A += a;
-    }
-    const float ctot = block_sum<float>(cost, sf);
-    const float atot = block_sum<float>(A, sf);
-    if (threadIdx.x == 0) {
-      float* o = p.rstat + 5 * (long long)i;
-      o[0] = st.m_s; o[1] = st.iz_s; o[2] = st.m_t; o[3] = st.iz_t; o[4] = atot;
-      p.rcost[i] = ctot;
-    }
-  } else {
-    // ---------------- SW columns x one row chunk: partial softmax statistics over i (image retrieval, dim=0)
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int n_strips = n_strips_of(B);
-    const int cta = blockIdx.x - B;
-    const int strip = cta % n_strips, chunk = cta / n_strips;
-    const int j0 = strip * SW + tx;
-    const int chunk_rows = chunk_rows_of(B);
-    const int r_end = min(B, (chunk + 1) * chunk_rows);
-    float ms[CV], zs[CV], mt[CV], zt[CV];
+    float vm[CV], vt[CV];
 #pragma unroll
     for (int u = 0; u < CV; ++u) {
-      ms[u] = -INFINITY; zs[u] = 0.f; mt[u] = -INFINITY; zt[u] = 0.f;
+      const bool ok = j0 + 32 * u < B;
+      vm[u] = ok ? p.tau * __ldg(rm + j0 + 32 * u) : -INFINITY;
+      vt[u] = ok ? __ldg(rt + j0 + 32 * u) : -INFINITY;
     }
-    for (int i = chunk * chunk_rows + ty; i < r_end; i += CS) {
-      const float* rm = p.M + (long long)i * p.ldM;
-      const float* rt = p.T + (long long)i * p.ldT;
-      float vm[CV], vt[CV];
+    // ---- row direction: this warp holds the row's SW columns -> (max, sum of exp) of the piece
+    float xs = vm[0], xt = vt[0];
 #pragma unroll
-      for (int u = 0; u < CV; ++u) {
-        const bool ok = j0 + 32 * u < B;
-        vm[u] = ok ? __ldg(rm + j0 + 32 * u) : 0.f;
-        vt[u] = ok ? __ldg(rt + j0 + 32 * u) : 0.f;
-      }
+    for (int u = 1; u < CV; ++u) {
+      xs = fmaxf(xs, vm[u]);
+      xt = fmaxf(xt, vt[u]);
+    }
+    xs = warp_max_f(xs);
+    xt = warp_max_f(xt);                               // finite: the strip has at least one valid column
+    float es = 0.f, et = 0.f;
 #pragma unroll
-      for (int u = 0; u < CV; ++u) {
-        online_update(ms[u], zs[u], p.tau * vm[u]);
+    for (int u = 0; u < CV; ++u) {
+      es += __expf(vm[u] - xs);                        // exp(-inf) = 0 for the columns beyond B
+      et += __expf(vt[u] - xt);
+    }
+    es = warp_sum_f(es);
+    et = warp_sum_f(et);
+    if (tx == 0) {
+      float* o = p.rpart + 4 * ((long long)strip * B + i);
+      o[0] = xs; o[1] = es; o[2] = xt; o[3] = et;
+    }
+    // ---- column direction: running statistics down the rows
+#pragma unroll
+    for (int u = 0; u < CV; ++u) {
+      if (j0 + 32 * u < B) {
+        online_update(ms[u], zs[u], vm[u]);
         online_update(mt[u], zt[u], vt[u]);
       }
     }
+  }
 #pragma unroll
-    for (int u = 0; u < CV; ++u) {
-      float* c = cs[ty][tx + 32 * u];
-      c[0] = ms[u]; c[1] = zs[u]; c[2] = mt[u]; c[3] = zt[u];
-    }
-    __syncthreads();
-    if (ty < CV) {
-      const int c = tx + 32 * ty, j = strip * SW + c;
-      if (j < B) {
-        float a0 = cs[0][c][0], a1 = cs[0][c][1], a2 = cs[0][c][2], a3 = cs[0][c][3];
-        for (int y = 1; y < CS; ++y) {
-          online_merge(a0, a1, cs[y][c][0], cs[y][c][1]);
-          online_merge(a2, a3, cs[y][c][2], cs[y][c][3]);
-        }
-        float* o = p.cpart + 4 * ((long long)chunk * B + j);
-        o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
+  for (int u = 0; u < CV; ++u) {
+    float* c = cs[ty][tx + 32 * u];
+    c[0] = ms[u]; c[1] = zs[u]; c[2] = mt[u]; c[3] = zt[u];
+  }
+  __syncthreads();
+  if (ty < CV) {
+    const int c = tx + 32 * ty, j = strip * SW + c;
+    if (j < B) {
+      float a0 = cs[0][c][0], a1 = cs[0][c][1], a2 = cs[0][c][2], a3 = cs[0][c][3];
+      for (int y = 1; y < CS; ++y) {
+        online_merge(a0, a1, cs[y][c][0], cs[y][c][1]);
+        online_merge(a2, a3, cs[y][c][2], cs[y][c][3]);
       }
+      float* o = p.cpart + 4 * ((long long)chunk * B + j);
+      o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
     }
-    // the last chunk CTA of this strip merges the partial statistics in chunk order
-    const int nch = n_chunks_of(B);
-    if (last_of_group(p.strip_cnt + strip, nch) && ty < CV) {
-      const int j = strip * SW + tx + 32 * ty;
-      if (j < B) {
-        float a = -INFINITY, b = 0.f, c = -INFINITY, d = 0.f;
-        for (int ch = 0; ch < nch; ++ch) {
-          const float* o = p.cpart + 4 * ((long long)ch * B + j);
-          online_merge(a, b, __ldcg(o), __ldcg(o + 1));
-          online_merge(c, d, __ldcg(o + 2), __ldcg(o + 3));
-        }
-        float* o = p.cstat + 5 * (long long)j;
-        o[0] = a; o[1] = 1.f / b; o[2] = c; o[3] = 1.f / d;
+  }
+  // the last chunk CTA of this strip merges the column partials in chunk order
+  if (last_of_group(p.strip_cnt + strip, nch) && ty < CV) {
+    const int j = strip * SW + tx + 32 * ty;
+    if (j < B) {
+      float a = -INFINITY, b = 0.f, c = -INFINITY, d = 0.f;
+      for (int ch = 0; ch < nch; ++ch) {
+        const float* o = p.cpart + 4 * ((long long)ch * B + j);
+        online_merge(a, b, __ldcg(o), __ldcg(o + 1));
+        online_merge(c, d, __ldcg(o + 2), __ldcg(o + 3));
       }
+      float* o = p.cstat + 5 * (long long)j;
+      o[0] = a; o[1] = 1.f / b; o[2] = c; o[3] = 1.f / d;
+    }
+  }
+  // the last strip CTA of this row chunk merges the row partials in strip order
+  if (last_of_group(p.chunk_cnt + chunk, n_strips)) {
+    for (int i = r_begin + threadIdx.x; i < r_end; i += LT) {
+      float a = -INFINITY, b = 0.f, c = -INFINITY, d = 0.f;
+      for (int s = 0; s < n_strips; ++s) {
+        const float* o = p.rpart + 4 * ((long long)s * B + i);
+        online_merge(a, b, __ldcg(o), __ldcg(o + 1));
+        online_merge(c, d, __ldcg(o + 2), __ldcg(o + 3));
+      }
+      float* o = p.rstat + 5 * (long long)i;
+      o[0] = a; o[1] = 1.f / b; o[2] = c; o[3] = 1.f / d;
     }
   }
 }
 
-// second column pass: final statistics of every column (merge of the chunk partials, fixed order), then the
-// chunk's share of cost and A = sum t*p/(p+eps); the last CTA adds the shares up and writes the loss
-__global__ void __launch_bounds__(LT) listnet_colcost_kernel(const ListnetParams p) {
+// sweep 2: with the final statistics, every row's and column's cost and A = sum t*p/(p+eps); the last CTA adds the
+// costs up in a fixed order and writes the loss
+__global__ void __launch_bounds__(LT) listnet_cost_kernel(const ListnetParams p) {
   __shared__ float sf[LT / 32];
   __shared__ float cs[CS][SW][2];
-  __shared__ SoftStats fin[SW];
   const int B = p.B;
-  const int nch = n_chunks_of(B);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n_strips = n_strips_of(B);
+  const int n_strips = n_strips_of(B), nch = n_chunks_of(B);
   const int strip = blockIdx.x % n_strips, chunk = blockIdx.x / n_strips;
   const int j0 = strip * SW + tx;
   const int chunk_rows = chunk_rows_of(B);
-  const int r_end = min(B, (chunk + 1) * chunk_rows);
-  if (ty < CV) {
-    const int c = tx + 32 * ty, j = strip * SW + c;
-    const float* o = p.cstat + 5 * (long long)(j < B ? j : 0);
-    fin[c].m_s = o[0]; fin[c].iz_s = o[1]; fin[c].m_t = o[2]; fin[c].iz_t = o[3];
-  }
-  __syncthreads();
+  const int r_begin = chunk * chunk_rows, r_end = min(B, r_begin + chunk_rows);
   SoftStats st[CV];
   float cost[CV], A[CV];
 #pragma unroll
   for (int u = 0; u < CV; ++u) {
-    st[u] = fin[tx + 32 * u];
+    const float* o = p.cstat + 5 * (long long)min(j0 + 32 * u, B - 1);
+    st[u] = SoftStats{__ldg(o), __ldg(o + 1), __ldg(o + 2), __ldg(o + 3)};
     cost[u] = 0.f;
     A[u] = 0.f;
   }
-  for (int i = chunk * chunk_rows + ty; i < r_end; i += CS) {
+  float* rshare = p.rpart;     // the statistic partials are dead by now: reuse the buffers as [..][B][2]
+  float* cshare = p.cpart;
+  for (int i = r_begin + ty; i < r_end; i += CS) {
     const float* rm = p.M + (long long)i * p.ldM;
     const float* rt = p.T + (long long)i * p.ldT;
+    const float* rs = p.rstat + 5 * (long long)i;
+    const SoftStats sr{__ldg(rs), __ldg(rs + 1), __ldg(rs + 2), __ldg(rs + 3)};
     float vm[CV], vt[CV];
 #pragma unroll
     for (int u = 0; u < CV; ++u) {
@@ -532,14 +521,24 @@ __global__ void __launch_bounds__(LT) listnet_colcost_kernel(const ListnetParams
       vm[u] = ok ? __ldg(rm + j0 + 32 * u) : 0.f;
       vt[u] = ok ? __ldg(rt + j0 + 32 * u) : 0.f;
     }
+    float rc = 0.f, ra = 0.f;
 #pragma unroll
     for (int u = 0; u < CV; ++u) {
       if (j0 + 32 * u < B) {
         float c, a, pr;
+        listnet_elem(vm[u], vt[u], sr, p.tau, p.eps, c, a, pr);
+        rc += c;
+        ra += a;
         listnet_elem(vm[u], vt[u], st[u], p.tau, p.eps, c, a, pr);
         cost[u] += c;
         A[u] += a;
       }
+    }
+    rc = warp_sum_f(rc);
+    ra = warp_sum_f(ra);
+    if (tx == 0) {
+      rshare[2 * ((long long)strip * B + i)] = rc;
+      rshare[2 * ((long long)strip * B + i) + 1] = ra;
     }
   }
 #pragma unroll
@@ -548,7 +547,6 @@ __global__ void __launch_bounds__(LT) listnet_colcost_kernel(const ListnetParams
     cs[ty][tx + 32 * u][1] = A[u];
   }
   __syncthreads();
-  float* share = p.cpart;      // the statistic partials are dead by now: reuse the buffer as [n_chunks][B][2]
   if (ty < CV) {
     const int c = tx + 32 * ty, j = strip * SW + c;
     if (j < B) {
@@ -557,8 +555,8 @@ __global__ void __launch_bounds__(LT) listnet_colcost_kernel(const ListnetParams
         ct += cs[y][c][0];
         at += cs[y][c][1];
       }
-      share[2 * ((long long)chunk * B + j)] = ct;
-      share[2 * ((long long)chunk * B + j) + 1] = at;
+      cshare[2 * ((long long)chunk * B + j)] = ct;
+      cshare[2 * ((long long)chunk * B + j) + 1] = at;
     }
   }
   if (last_of_group(p.strip_cnt + strip, nch) && ty < CV) {
@@ -566,11 +564,22 @@ __global__ void __launch_bounds__(LT) listnet_colcost_kernel(const ListnetParams
     if (j < B) {
       float ct = 0.f, at = 0.f;
       for (int ch = 0; ch < nch; ++ch) {
-        ct += __ldcg(share + 2 * ((long long)ch * B + j));
-        at += __ldcg(share + 2 * ((long long)ch * B + j) + 1);
+        ct += __ldcg(cshare + 2 * ((long long)ch * B + j));
+        at += __ldcg(cshare + 2 * ((long long)ch * B + j) + 1);
       }
       p.cstat[5 * (long long)j + 4] = at;
       p.ccost[j] = ct;
+    }
+  }
+  if (last_of_group(p.chunk_cnt + chunk, n_strips)) {
+    for (int i = r_begin + threadIdx.x; i < r_end; i += LT) {
+      float ct = 0.f, at = 0.f;
+      for (int s = 0; s < n_strips; ++s) {
+        ct += __ldcg(rshare + 2 * ((long long)s * B + i));
+        at += __ldcg(rshare + 2 * ((long long)s * B + i) + 1);
+      }
+      p.rstat[5 * (long long)i + 4] = at;
+      p.rcost[i] = ct;
     }
   }
   if (!last_cta_done(p.counter)) return;
@@ -582,48 +591,88 @@ __global__ void __launch_bounds__(LT) listnet_colcost_kernel(const ListnetParams
   }
 }
 
-// dL/dM[i,j] = (tau/B) * [ (p_r*A_r(i) - a_r) + (p_c*A_c(j) - a_c) ]   
-constexpr int GV = 4;            // columns per thread (j, j + LT, ...: coalesced without alignment requirements)
+// sweep 3: dL/dM[i,j] = (tau/B) * [ (p_r*A_r(i) - a_r) + (p_c*A_c(j) - a_c) ]   
+__device__ __forceinline__ float listnet_grad_elem(float xm, float xt, const SoftStats& sr, float A_r, const SoftStats& sc,
+                                                   float A_c, float tau, float eps, float scale) {
+  float cost, a_r, p_r, a_c, p_c;
+  listnet_elem(xm, xt, sr, tau, eps, cost, a_r, p_r);
+  listnet_elem(xm, xt, sc, tau, eps, cost, a_c, p_c);
+  return scale * ((p_r * A_r - a_r) + (p_c * A_c - a_c));
+}
+constexpr int GV = 4;            // columns per thread
 constexpr int GR = 8;            // rows per CTA: the column statistics are loaded once per thread and reused GR times
+// VEC: a thread owns 4 consecutive columns (128-bit loads and stores, two rows in flight); needs 16-byte aligned rows.
+// Otherwise the columns j, j + LT, ... (coalesced without alignment requirements).
+template <bool VEC>
 __global__ void __launch_bounds__(LT) listnet_grad_kernel(const ListnetParams p) {
   __shared__ float rs[GR][5];
   const int B = p.B;
   const int i0 = blockIdx.y * GR;
   const int n_rows = min(GR, B - i0);
-  if (threadIdx.x < 5 * n_rows) rs[threadIdx.x / 5][threadIdx.x % 5] = p.rstat[5 * (long long)i0 + threadIdx.x];
+  if ((int)threadIdx.x < 5 * n_rows) rs[threadIdx.x / 5][threadIdx.x % 5] = p.rstat[5 * (long long)i0 + threadIdx.x];
   const float scale = p.tau / B;
-  const int j0 = blockIdx.x * (LT * GV) + threadIdx.x;
+  const int j0 = VEC ? (blockIdx.x * LT + threadIdx.x) * GV : blockIdx.x * (LT * GV) + threadIdx.x;
+  const int jstep = VEC ? 1 : LT;
   SoftStats sc[GV];
   float A_c[GV];
 #pragma unroll
   for (int u = 0; u < GV; ++u) {
-    const int j = min(j0 + u * LT, B - 1);
+    const int j = min(j0 + u * jstep, B - 1);
     const float* c = p.cstat + 5 * (long long)j;
     sc[u] = SoftStats{__ldg(c), __ldg(c + 1), __ldg(c + 2), __ldg(c + 3)};
     A_c[u] = __ldg(c + 4);
   }
   __syncthreads();
-  for (int r = 0; r < n_rows; ++r) {
-    const long long i = i0 + r;
-    const SoftStats sr{rs[r][0], rs[r][1], rs[r][2], rs[r][3]};
-    const float A_r = rs[r][4];
-    const float* rm = p.M + i * p.ldM;
-    const float* rt = p.T + i * p.ldT;
-    float* out = p.dM + i * p.ldG;
-    float xm[GV], xt[GV];
-#pragma unroll
-    for (int u = 0; u < GV; ++u) {
-      const int j = j0 + u * LT;
-      xm[u] = j < B ? __ldg(rm + j) : 0.f;
-      xt[u] = j < B ? __ldg(rt + j) : 0.f;
+  if (VEC) {
+    if (j0 >= B) return;                             // B is a multiple of 4 here: the float4 is whole or absent
+    for (int r = 0; r < n_rows; r += 2) {
+      const bool two = r + 1 < n_rows;
+      const long long ia = i0 + r, ib = two ? ia + 1 : ia;
+      const float4 ma = __ldg(reinterpret_cast<const float4*>(p.M + ia * p.ldM + j0));
+      const float4 ta = __ldg(reinterpret_cast<const float4*>(p.T + ia * p.ldT + j0));
+      const float4 mb = __ldg(reinterpret_cast<const float4*>(p.M + ib * p.ldM + j0));
+      const float4 tb = __ldg(reinterpret_cast<const float4*>(p.T + ib * p.ldT + j0));
+      {
+        const SoftStats sr{rs[r][0], rs[r][1], rs[r][2], rs[r][3]};
+        const float A_r = rs[r][4];
+        float4 g;
+        g.x = listnet_grad_elem(ma.x, ta.x, sr, A_r, sc[0], A_c[0], p.tau, p.eps, scale);
+        g.y = listnet_grad_elem(ma.y, ta.y, sr, A_r, sc[1], A_c[1], p.tau, p.eps, scale);
+        g.z = listnet_grad_elem(ma.z, ta.z, sr, A_r, sc[2], A_c[2], p.tau, p.eps, scale);
+        g.w = listnet_grad_elem(ma.w, ta.w, sr, A_r, sc[3], A_c[3], p.tau, p.eps, scale);
+        *reinterpret_cast<float4*>(p.dM + ia * p.ldG + j0) = g;
+      }
+      if (two) {
+        const SoftStats sr{rs[r + 1][0], rs[r + 1][1], rs[r + 1][2], rs[r + 1][3]};
+        const float A_r = rs[r + 1][4];
+        float4 g;
+        g.x = listnet_grad_elem(mb.x, tb.x, sr, A_r, sc[0], A_c[0], p.tau, p.eps, scale);
+        g.y = listnet_grad_elem(mb.y, tb.y, sr, A_r, sc[1], A_c[1], p.tau, p.eps, scale);
+        g.z = listnet_grad_elem(mb.z, tb.z, sr, A_r, sc[2], A_c[2], p.tau, p.eps, scale);
+        g.w = listnet_grad_elem(mb.w, tb.w, sr, A_r, sc[3], A_c[3], p.tau, p.eps, scale);
+        *reinterpret_cast<float4*>(p.dM + ib * p.ldG + j0) = g;
+      }
     }
+  } else {
+    for (int r = 0; r < n_rows; ++r) {
+      const long long i = i0 + r;
+      const SoftStats sr{rs[r][0], rs[r][1], rs[r][2], rs[r][3]};
+      const float A_r = rs[r][4];
+      const float* rm = p.M + i * p.ldM;
+      const float* rt = p.T + i * p.ldT;
+      float* out = p.dM + i * p.ldG;
+      float xm[GV], xt[GV];
 #pragma unroll
-    for (int u = 0; u < GV; ++u) {
-      const int j = j0 + u * LT;
-      float cost, a_r, p_r, a_c, p_c;
-      listnet_elem(xm[u], xt[u], sr, p.tau, p.eps, cost, a_r, p_r);
-      listnet_elem(xm[u], xt[u], sc[u], p.tau, p.eps, cost, a_c, p_c);
-      if (j < B) out[j] = scale * ((p_r * A_r - a_r) + (p_c * A_c[u] - a_c));
+      for (int u = 0; u < GV; ++u) {
+        const int j = j0 + u * LT;
+        xm[u] = j < B ? __ldg(rm + j) : 0.f;
+        xt[u] = j < B ? __ldg(rt + j) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < GV; ++u) {
+        const int j = j0 + u * LT;
+        if (j < B) out[j] = listnet_grad_elem(xm[u], xt[u], sr, A_r, sc[u], A_c[u], p.tau, p.eps, scale);
+      }
     }
   }
 }
@@ -631,10 +680,12 @@ __global__ void __launch_bounds__(LT) listnet_grad_kernel(const ListnetParams p)
 }  // namespace alad
 
 extern "C" int64_t alad_loss_workspace_bytes(int32_t B) {
-  // shared by both losses: 12 arrays of B 4-byte words + counter + padding, plus the column partials
-  // (listnet: 4 + 2 floats per row chunk and column; triplet: 2 words per row block and column)
+  // shared by both losses: 12 arrays of B 4-byte words + counter + padding, plus the partials
+  // (listnet: 4 floats per row chunk and column and per column strip and row, and the group counters;
+  // triplet: 2 words per row block and column)
   const int64_t b = B > 0 ? B : 1;
-  const int64_t listnet_part = 6 * 4 * b * alad::n_chunks_of((int)b);
+  const int64_t nch = alad::n_chunks_of((int)b), nst = alad::n_strips_of((int)b);
+  const int64_t listnet_part = 4 * 4 * b * (nch + nst) + 4 * (nch + nst) + 64;
   const int64_t rb = alad::triplet_rows_of((int)b);
   const int64_t triplet_part = 2 * 4 * b * ((b + rb - 1) / rb);
   return 12 * 4 * b + 256 + (listnet_part > triplet_part ? listnet_part : triplet_part) + 4 * ((b + 31) / 32) + 64;
@@ -694,17 +745,21 @@ extern "C" int alad_listnet_fwd_bwd(const float* teacher, int64_t ldT, const flo
   p.T = teacher; p.ldT = ldT; p.M = student; p.ldM = ldM; p.B = B; p.tau = temperature; p.eps = eps;
   p.loss = loss; p.dM = dM; p.ldG = ldG;
   p.rstat = w; p.cstat = w + 5 * (size_t)B; p.rcost = w + 10 * (size_t)B; p.ccost = w + 11 * (size_t)B;
-  p.counter = reinterpret_cast<unsigned int*>(w + 12 * (size_t)B);
-  const int nch = n_chunks_of(B);
+  const int nch = n_chunks_of(B), nst = n_strips_of(B);
   p.cpart = w + 12 * (size_t)B + 64;
-  p.strip_cnt = reinterpret_cast<unsigned int*>(p.cpart + 6 * (size_t)nch * B);
-  ALAD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
-  ALAD_CUDA(cudaMemsetAsync(p.strip_cnt, 0, sizeof(unsigned int) * (size_t)((B + 31) / 32), st));
-  listnet_stats_kernel<<<B + n_strips_of(B) * nch, LT, 0, st>>>(p);
-  listnet_colcost_kernel<<<n_strips_of(B) * nch, LT, 0, st>>>(p);
+  p.rpart = p.cpart + 4 * (size_t)nch * B;
+  p.strip_cnt = reinterpret_cast<unsigned int*>(p.rpart + 4 * (size_t)nst * B);
+  p.chunk_cnt = p.strip_cnt + nst;
+  p.counter = p.chunk_cnt + nch;                     // the three groups of arrival counters: one memset
+  ALAD_CUDA(cudaMemsetAsync(p.strip_cnt, 0, sizeof(unsigned int) * (size_t)(nst + nch + 1), st));
+  listnet_stats_kernel<<<nst * nch, LT, 0, st>>>(p);
+  listnet_cost_kernel<<<nst * nch, LT, 0, st>>>(p);
   if (dM) {
     dim3 grid((B + LT * GV - 1) / (LT * GV), (B + GR - 1) / GR);
-    listnet_grad_kernel<<<grid, LT, 0, st>>>(p);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec = (B & 3) == 0 && (ldT & 3) == 0 && (ldM & 3) == 0 && (ldG & 3) == 0 && al16(teacher) && al16(student) && al16(dM);
+    if (vec) listnet_grad_kernel<true><<<grid, LT, 0, st>>>(p);
+    else     listnet_grad_kernel<false><<<grid, LT, 0, st>>>(p);
   }
   ALAD_CUDA(cudaGetLastError());
   return ALAD_OK;

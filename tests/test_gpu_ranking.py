@@ -138,3 +138,77 @@ def test_col_topk_select_strided_view():
     Sd = torch.from_numpy(S).cuda()
     _, ci = ranking.col_topk(Sd[:, :333], 50)
     np.testing.assert_array_equal(ci[0].cpu().numpy(), _expected_topk(S[:, :333], 50))
+
+
+@pytest.mark.parametrize("Ni,Nc,q_rows,q_cols,k,img_off,kind", [
+    (1000, 5000, 1000, 5000, 50, 0, "random"),      # COCO-1k: 4 column CTAs (the last one partly filled) x 125 row groups
+    (333, 1664, 333, 1664, 50, 0, "ties"),          # heavy exact ties in both directions
+    (700, 4096, 500, 2400, 50, 7, "given"),         # query sub-ranges, an image offset, ground truth from outside
+    (640, 2052, 640, 2052, 50, 0, "masked"),        # -inf scores (shortlist-masked matrices): exact-comparison branches
+    (900, 96, 900, 96, 50, 0, "constant"),          # constant columns: candidate overflow -> heap path
+    (2500, 1024, 2500, 1024, 100, 0, "random"),     # the two-stage shortlist size, many rows per group
+    (700, 333, 700, 333, 50, 0, "random"),          # row stride not a multiple of four: the one-purpose kernels
+    (100, 500, 100, 500, 50, 0, "random"),          # too small for the threshold select: the one-purpose kernels
+    (300, 1500, 300, 1500, 50, 0, "nocount"),       # multi-GPU first sweep: no t2i counts
+])
+def test_rank_fused_equals_one_purpose_kernels(Ni, Nc, q_rows, q_cols, k, img_off, kind):
+    """alad_rank_fused (two sweeps of S) against rank_rows + col_gt + col_count + col_topk (four) on the same block:
+    every output identical, and the documented total order (numpy stable argsort reversed) on sampled queries."""
+    from aladin_b200 import ranking
+    r = np.random.RandomState(Ni + Nc)
+    S = r.standard_normal((Ni, Nc)).astype(np.float32)
+    cols = np.arange(Nc)
+    own = (cols // 5 - img_off >= 0) & (cols // 5 - img_off < Ni)
+    S[(cols // 5 - img_off)[own], cols[own]] += 1.5
+    if kind == "ties":
+        S = np.round(S * 2) / 2
+    if kind == "masked":
+        S[r.rand(Ni, Nc) < 0.7] = -np.inf
+        S[17] = -np.inf
+        S[:, 23] = -np.inf
+    if kind == "constant":
+        S[:] = 0.25
+    Sd = torch.from_numpy(S).cuda()
+    gt = None
+    if kind == "given":
+        g = r.standard_normal(q_cols).astype(np.float32)
+        g[::2] = S[(np.arange(q_cols) * 7) % Ni, np.arange(q_cols)][::2]        # exact ties with entries of the block
+        gt = torch.from_numpy(g).cuda()
+    rank, top1, cnt, ts, ti = ranking.rank_fused(Sd, k, img_off, q_rows, q_cols, gt=gt, count=kind != "nocount")
+    rank0, top10 = ranking.rank_rows(Sd[:q_rows], 5, img_off)
+    Sq = Sd[:, :q_cols]
+    if gt is None:
+        gt = torch.zeros(q_cols, dtype=torch.float32, device="cuda")
+        ranking.col_gt(Sq, gt, 5, img_off)
+    cnt0 = ranking.col_count(Sq, gt, 5, img_off)
+    cs0, ci0 = ranking.col_topk(Sq, k, img_off)
+    assert torch.equal(rank, rank0) and torch.equal(top1, top10)
+    if kind != "nocount":
+        assert torch.equal(cnt, cnt0)
+    else:
+        assert cnt is None
+    assert torch.equal(ti, ci0[0]) and torch.equal(ts, cs0[0])
+    rank, top1, ti = rank.cpu().numpy(), top1.cpu().numpy(), ti.cpu().numpy()
+    for i in range(0, q_rows, 41):
+        inds = _stable_desc_order(S[i])
+        assert top1[i] == inds[0]
+        g0 = 5 * (img_off + i)
+        if g0 < Nc:
+            pos = np.empty(Nc, np.int64); pos[inds] = np.arange(Nc)
+            assert rank[i] == pos[g0:g0 + 5].min()
+        else:
+            assert rank[i] == Nc
+    kk = min(k, Ni)
+    for c in range(0, q_cols, 53):
+        np.testing.assert_array_equal(ti[c, :kk], _stable_desc_order(S[:, c])[:kk] + img_off)
+
+
+def test_rank_fused_reproduces_reference_golden():
+    from aladin_b200 import ranking
+    g = load_golden("retrieval")
+    Sd = torch.from_numpy(g["S_full"]).cuda()
+    rank, top1, count, _, top50 = ranking.rank_fused(Sd, 50)
+    np.testing.assert_array_equal(rank.cpu().numpy(), g["ranks_i2t"])
+    np.testing.assert_array_equal(top1.cpu().numpy(), g["top1"])
+    np.testing.assert_array_equal(count.cpu().numpy(), g["ranks_t2i"])
+    np.testing.assert_array_equal(top50.cpu().numpy(), g["top50"])

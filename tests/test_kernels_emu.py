@@ -109,7 +109,7 @@ def test_triplet_emulated_golden(losses):
         np.testing.assert_array_equal(G, g[f"G_{key}"])
 
 
-@pytest.mark.parametrize("B", [1, 9] + big(40))
+@pytest.mark.parametrize("B", [1, 9] + big(40, 136, 150))      # 136 / 150: two column strips x five row chunks
 def test_listnet_emulated(losses, B):
     r = np.random.RandomState(B)
     T = (r.standard_normal((B, B)) * 2 + 3).astype(np.float32)

@@ -41,6 +41,8 @@ CASES = [
     (TR.test_rank_kernels_reproduce_reference_golden, {}),
     (TR.test_sharded_ranking_equals_single_shard, {}),
     (TR.test_col_topk_select_strided_view, {}),
+    (TR.test_rank_fused_reproduces_reference_golden, {}),
+    (TR.test_rank_fused_equals_one_purpose_kernels, dict(Ni=300, Nc=200, q_rows=260, q_cols=120, k=10, img_off=2, kind="given")),
     (TE.test_i2t_t2i_alignment_golden, dict(precision="fp32")),
     (TE.test_arbitrary_callable_sim_function, {}),
     (TC.test_recall_1k_5fold_small_folds_and_missing_folds, {}),
