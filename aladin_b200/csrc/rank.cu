@@ -276,7 +276,11 @@ col_groupmax_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, 
 // are integer atomics (adds, and a 64-bit max of (order key, column) = the total order's arg-best), so the results
 // do not depend on the order CTAs finish in.  Exact ties take a rare slow branch (index comparison).
 constexpr int FS_THREADS = 256;
-constexpr int FS_VEC = 2;                          // float4 per thread and row
+#ifndef ALAD_FS_VEC
+#define ALAD_FS_VEC 2
+#endif
+constexpr int FS_VEC = ALAD_FS_VEC;                // float4 per thread and row
+constexpr int FS_CTAS = FS_VEC <= 2 ? 4 : 2;       // resident CTAs per SM the register budget is held to
 constexpr int FS_E = 4 * FS_VEC;                   // columns per thread
 constexpr int FS_COLS = FS_THREADS * FS_E;         // columns per CTA
 constexpr int FS_ROWS = 64;                        // rows per block of shared row statistics
@@ -302,18 +306,23 @@ __device__ __forceinline__ void count_gt(int& c, float v, float t) {
 // CTA / thread sits on one side of the ground truth: entries after it compare against below(g) (>= g), entries before
 // it against g itself.  Only the threads whose columns (rows) straddle the ground truth, and non-finite ground-truth
 // scores (-inf of masked matrices), take the exact comparison.
+struct __align__(16) RowQuery {
+  float gs;          // the row's best ground-truth score (strict threshold) ...
+  float ge;          // ... and the value just below it (ties count)
+  int gi;            // its caption index; -1 none
+  int mode;          // 0 not a query row, 1 thresholds, 2 exact comparison (non-finite ground-truth score)
+};
+
 template <bool COUNT>
-__global__ void __launch_bounds__(FS_THREADS)
+__global__ void __launch_bounds__(FS_THREADS, FS_CTAS)
 rank_sweep_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, int group, int img_off, int q_rows,
                   int q_cols, int rows_per_group, const float* __restrict__ gt, int* __restrict__ rank,
                   unsigned long long* __restrict__ best, int* __restrict__ count, float* __restrict__ gmax) {
-  __shared__ float s_gs[FS_ROWS];                  // the row's best ground-truth score (strict threshold) ...
-  __shared__ float s_ge[FS_ROWS];                  // ... and the value just below it (ties count)
-  __shared__ int s_gi[FS_ROWS];                    // its caption index; -1 none
-  __shared__ int s_mode[FS_ROWS];                  // 0 not a query row, 1 thresholds, 2 exact comparison
-  __shared__ int s_cnt[FS_ROWS];
-  __shared__ unsigned long long s_best[FS_ROWS];
-  const int lane = threadIdx.x & 31;
+  // per-warp slots instead of shared-memory atomics: every warp writes its share of every query row once
+  __shared__ RowQuery s_row[FS_ROWS];
+  __shared__ int s_cnt[FS_THREADS / 32][FS_ROWS];
+  __shared__ unsigned long long s_best[FS_THREADS / 32][FS_ROWS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = blockIdx.y;
   const int r0 = g * rows_per_group, r1 = min(Ni, r0 + rows_per_group);
   const int cbase = blockIdx.x * FS_COLS + 4 * threadIdx.x;
@@ -335,25 +344,29 @@ rank_sweep_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, in
       else cthr[e] = gl < r0 ? float_below(gv) : gv;
     }
   }
-  bool whole[FS_VEC];                               // the float4 lies inside the row
+  // 0: the float4 lies beyond the row, 1: inside, 2: across its end
+  int piece[FS_VEC];
 #pragma unroll
-  for (int u = 0; u < FS_VEC; ++u) whole[u] = cbase + u * (4 * FS_THREADS) + 3 < Nc;
-  auto load_row = [&](int r, float* v) {
-    const float* rowp = S + (long long)r * ldS;
+  for (int u = 0; u < FS_VEC; ++u) {
+    const int c4 = cbase + u * (4 * FS_THREADS);
+    piece[u] = c4 + 3 < Nc ? 1 : (c4 < Nc ? 2 : 0);
+  }
+  auto load_row = [&](const float* rowp, float* v) {  // rowp = this thread's first column of the row
 #pragma unroll
     for (int u = 0; u < FS_VEC; ++u) {
-      const int c4 = cbase + u * (4 * FS_THREADS);
-      if (whole[u]) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(rowp + c4));
-        v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
-      } else {
-#pragma unroll
-        for (int w = 0; w < 4; ++w) v[4 * u + w] = (c4 + w < Nc) ? __ldg(rowp + c4 + w) : -INFINITY;
+      float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      const float* q = rowp + u * (4 * FS_THREADS);
+      if (piece[u] == 1) x = __ldg(reinterpret_cast<const float4*>(q));
+      else if (piece[u] == 2) {
+        const int c4 = cbase + u * (4 * FS_THREADS);
+        x.x = __ldg(q);
+        if (c4 + 1 < Nc) x.y = __ldg(q + 1);
+        if (c4 + 2 < Nc) x.z = __ldg(q + 2);
       }
+      v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
     }
   };
-  auto consume = [&](int rb, int rr, const float* v) {
-    const int r = rb + rr;
+  auto consume = [&](int r, int rr, const float* v) {
     // ---- columns: running maximum, images ahead of the caption's ground truth
 #pragma unroll
     for (int e = 0; e < FS_E; ++e) cmax[e] = fmaxf(cmax[e], v[e]);
@@ -370,79 +383,93 @@ rank_sweep_kernel(const float* __restrict__ S, long long ldS, int Ni, int Nc, in
       }
     }
     // ---- row: captions ahead of the image's best ground truth, arg-max caption
-    const int mode = s_mode[rr];
-    if (mode == 0) return;                           // uniform over the CTA
-    const int gi = s_gi[rr];
+    const RowQuery q = s_row[rr];
+    if (q.mode == 0) return;                         // uniform over the CTA
     int cnt = 0;
     float tmax = -INFINITY;
 #pragma unroll
     for (int e = 0; e < FS_E; ++e) tmax = fmaxf(tmax, v[e]);
-    if (mode == 1 && (gi < c_first || gi >= c_last)) {
-      const float thr = gi < c_first ? s_ge[rr] : s_gs[rr];
+    if (q.mode == 1 && (q.gi < c_first || q.gi >= c_last)) {
+      const float thr = q.gi < c_first ? q.ge : q.gs;
 #pragma unroll
       for (int e = 0; e < FS_E; ++e) count_gt(cnt, v[e], thr);
     } else {
-      const float gs = s_gs[rr];
 #pragma unroll
-      for (int e = 0; e < FS_E; ++e) cnt += (col(e) < Nc && ahead(v[e], col(e), gs, gi)) ? 1 : 0;
+      for (int e = 0; e < FS_E; ++e) cnt += (col(e) < Nc && ahead(v[e], col(e), q.gs, q.gi)) ? 1 : 0;
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     const unsigned key = order_key(tmax);
     const unsigned mk = __reduce_max_sync(0xffffffffu, key);
+    int idx = -1;
     if (key == mk) {                                 // normally one lane of the warp
-      const float top = key_to_float(mk);
-      int idx = -1;
+      int at = -1;                                   // slots ascend with the column: the largest index stays
+      if (tmax > -INFINITY) {                        // columns beyond the row hold -inf: no bounds check needed
 #pragma unroll
-      for (int e = 0; e < FS_E; ++e)
-        if (v[e] == top && col(e) < Nc) idx = col(e);           // columns ascend with e: the largest index stays
-      if (idx >= 0) atomicMax(&s_best[rr], ((unsigned long long)mk << 32) | (unsigned)idx);
+        for (int e = 0; e < FS_E; ++e) at = v[e] == tmax ? e : at;
+      } else {
+#pragma unroll
+        for (int e = 0; e < FS_E; ++e) at = (v[e] == tmax && col(e) < Nc) ? e : at;
+      }
+      if (at >= 0) idx = cbase + (at >> 2) * (4 * FS_THREADS) + (at & 3);
     }
-    if (lane == 0 && cnt) atomicAdd(&s_cnt[rr], cnt);
+    idx = __reduce_max_sync(0xffffffffu, idx);
+    if (lane == 0) {
+      s_cnt[warp][rr] = cnt;
+      s_best[warp][rr] = idx >= 0 ? (((unsigned long long)mk << 32) | (unsigned)idx) : 0ull;
+    }
   };
   for (int rb = r0; rb < r1; rb += FS_ROWS) {
     const int nrows = min(FS_ROWS, r1 - rb);
     if ((int)threadIdx.x < nrows) {
       const int r = rb + threadIdx.x;
-      float gs = INFINITY;
-      int gi = -1, mode = 0;
+      RowQuery q;
+      q.gs = INFINITY;
+      q.gi = -1;
+      q.mode = 0;
       if (r < q_rows) {
         const long long g0 = (long long)group * (img_off + r);
         for (int j = 0; j < group; ++j) {
           const long long c = g0 + j;
           if (c < Nc) {
             const float v = __ldg(S + (long long)r * ldS + c);
-            if (gi < 0 || ahead(v, (int)c, gs, gi)) {
-              gs = v;
-              gi = (int)c;
+            if (q.gi < 0 || ahead(v, (int)c, q.gs, q.gi)) {
+              q.gs = v;
+              q.gi = (int)c;
             }
           }
         }
-        if (gi < 0) gs = INFINITY;                   // no ground truth in range: nothing is ahead, rank = Nc
-        gs += 0.f;
-        mode = (gi < 0 || is_finite(gs)) ? 1 : 2;
+        if (q.gi < 0) q.gs = INFINITY;               // no ground truth in range: nothing is ahead, rank = Nc
+        q.gs += 0.f;
+        q.mode = (q.gi < 0 || is_finite(q.gs)) ? 1 : 2;
       }
-      s_gs[threadIdx.x] = gs;
-      s_ge[threadIdx.x] = is_finite(gs) ? float_below(gs) : gs;
-      s_gi[threadIdx.x] = gi;
-      s_mode[threadIdx.x] = mode;
-      s_cnt[threadIdx.x] = 0;
-      s_best[threadIdx.x] = 0ull;
+      q.ge = is_finite(q.gs) ? float_below(q.gs) : q.gs;
+      s_row[threadIdx.x] = q;
     }
     __syncthreads();
     float va[FS_E], vb[FS_E];                        // two rows in flight
-    load_row(rb, va);
+    const float* rowp = S + (long long)rb * ldS + cbase;
+    load_row(rowp, va);
     for (int rr = 0; rr < nrows; rr += 2) {
-      if (rr + 1 < nrows) load_row(rb + rr + 1, vb);
-      consume(rb, rr, va);
-      if (rr + 2 < nrows) load_row(rb + rr + 2, va);
-      if (rr + 1 < nrows) consume(rb, rr + 1, vb);
+      if (rr + 1 < nrows) load_row(rowp + ldS, vb);
+      consume(rb + rr, rr, va);
+      if (rr + 2 < nrows) load_row(rowp + 2 * ldS, va);
+      if (rr + 1 < nrows) consume(rb + rr + 1, rr + 1, vb);
+      rowp += 2 * ldS;
     }
     __syncthreads();
-    if ((int)threadIdx.x < nrows && s_mode[threadIdx.x] != 0) {
+    if ((int)threadIdx.x < nrows && s_row[threadIdx.x].mode != 0) {
       const int r = rb + threadIdx.x;
-      const int add = s_gi[threadIdx.x] >= 0 ? s_cnt[threadIdx.x] : (blockIdx.x == 0 ? Nc : 0);
+      int add = 0;
+      unsigned long long top = 0ull;
+#pragma unroll
+      for (int w = 0; w < FS_THREADS / 32; ++w) {
+        add += s_cnt[w][threadIdx.x];
+        const unsigned long long b = s_best[w][threadIdx.x];
+        top = b > top ? b : top;
+      }
+      if (s_row[threadIdx.x].gi < 0) add = blockIdx.x == 0 ? Nc : 0;
       if (add) atomicAdd(rank + r, add);
-      if (s_best[threadIdx.x]) atomicMax(best + r, s_best[threadIdx.x]);
+      if (top) atomicMax(best + r, top);
     }
     __syncthreads();
   }
