@@ -106,10 +106,5 @@ def topk_merge(cand_score, cand_idx):
 
 def t2i_rank_topk(S, k, group=5):
     """Single-shard t2i: (rank[Nc] int32, topk[Nc,k] int32)."""
-    Ni, Nc, _ = _check_S(S)
-    gt = torch.zeros(Nc, dtype=torch.float32, device=S.device)
-    col_gt(S, gt, group, 0)
-    count = col_count(S, gt, group, 0)
-    cs, ci = col_topk(S, k, 0)
-    _, idx = topk_merge(cs, ci)
+    _, _, count, _, idx = rank_fused(S, k, q_rows=0, group=group)
     return count, idx

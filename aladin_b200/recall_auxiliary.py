@@ -30,8 +30,7 @@ def recall_test(img_embs, cap_embs, tot_lengths=None, model=None):
     with torch.no_grad():
         ims = img_embs[0::5]
         S = scoring.dot_scores(ims, cap_embs)                       # one GEMM serves both directions
-        ri, _ = ranking.rank_rows(S, 5, 0)
-        rt, _ = ranking.t2i_rank_topk(S, 1)
+        ri, _, rt, _, _ = ranking.rank_fused(S, 1)                # both directions: two sweeps of S
         r1, r5, r10, _, _ = retrieval.recall_tuple(ri.cpu().numpy().astype(np.float64))
         r1i, r5i, r10i, _, _ = retrieval.recall_tuple(rt.cpu().numpy().astype(np.float64))
     return r1, r5, r10, r1i, r5i, r10i, r1 + r5 + r10 + r1i + r5i + r10i

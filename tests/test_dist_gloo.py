@@ -150,3 +150,70 @@ def test_shard_bounds_cover_everything():
             spans = [retrieval.shard_bounds(n, w, r) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _emulated_worker(rank, world, port, S_full, lib_path, k, out):
+    """One rank of the sharded ranking with the REAL ranking entry points (alad_rank_fused without counts, alad_col_gt,
+    alad_col_count, alad_topk_merge) from the host-thread emulation of csrc/rank.cu; the exchange runs over gloo."""
+    import ctypes
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from aladin_b200 import _cabi, ranking, retrieval
+        lib = ctypes.CDLL(lib_path)
+        for name, (res, args) in _cabi.PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _cabi._lib = lib
+        _cabi.stream_ptr = lambda: None
+        torch.Tensor.is_cuda = property(lambda self: True)          # "device" tensors are host tensors in this process
+        Ni = S_full.shape[0]
+        lo, hi = retrieval.shard_bounds(Ni, world, rank)
+        block = torch.from_numpy(np.ascontiguousarray(S_full.numpy()[lo:hi]))
+        res = retrieval.rank_device(block, Ni, img_off=lo, n_images_total=Ni, k=k, group=dist.group.WORLD, ops=ranking)
+        if rank == 0:
+            out.put([np.asarray(r) for r in res[:5]])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_ranking_world2_gloo_with_the_emulated_kernels():
+    """The N > 1 composition the GPU box runs (fused sweep without counts -> one all-gather -> counts against the
+    gathered ground truth -> all-reduce), on the real kernels' sources: equals the stable-argsort order of the whole matrix."""
+    import shutil
+    import sys
+    import pytest
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emu"))
+    import build_emu
+    lib_path = build_emu.build_library()
+    r = np.random.RandomState(11)
+    Ni, Nc, k = 540, 200, 10                                       # 270 rows per rank: the threshold-select / fused-sweep path
+    S = np.round(r.standard_normal((Ni, Nc)).astype(np.float32) * 4) / 4          # exact ties
+    S[np.arange(Nc) // 5, np.arange(Nc)] += 1.0
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_emulated_worker, args=(rk, 2, port, torch.from_numpy(S), lib_path, k, out)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    rank_i, top1, count, ts, ti = out.get(timeout=600)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    order = lambda v: np.argsort(v, kind="stable")[::-1]
+    for i in range(Ni):
+        inds = order(S[i])
+        assert top1[i] == inds[0]
+        if 5 * i < Nc:
+            pos = np.empty(Nc, np.int64)
+            pos[inds] = np.arange(Nc)
+            assert rank_i[i] == pos[5 * i:5 * i + 5].min()
+        else:
+            assert rank_i[i] == Nc
+    for c in range(Nc):
+        inds = order(S[:, c])
+        assert count[c] == np.where(inds == c // 5)[0][0]
+        np.testing.assert_array_equal(ti[c], inds[:k])
+        np.testing.assert_array_equal(ts[c], S[inds[:k], c])
