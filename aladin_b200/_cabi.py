@@ -46,6 +46,19 @@ class ScoresFusedArgs(C.Structure):
     ]
 
 
+class MrswRetrievalArgs(C.Structure):
+    """struct alad_mrsw_retrieval_args (include/alad_b200.h)."""
+    _fields_ = [
+        ("words", C.c_void_p), ("n_word_rows", C.c_int64), ("row_cap", C.c_void_p),
+        ("regions", C.c_void_p), ("n_region_rows", C.c_int64), ("Kp", C.c_int32), ("operand_format", C.c_int32),
+        ("nr", C.c_void_p), ("clamp", C.c_void_p), ("cap_row", C.c_void_p),
+        ("Ni", C.c_int32), ("Nc", C.c_int32), ("group", C.c_int32), ("k", C.c_int32), ("block_images", C.c_int32),
+        ("S", C.c_void_p), ("ldS", C.c_int64),
+        ("rank_i2t", C.c_void_p), ("top1", C.c_void_p), ("rank_t2i", C.c_void_p), ("topk_score", C.c_void_p),
+        ("topk_idx", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 class TrainLossesArgs(C.Structure):
     """struct alad_train_losses_args (include/alad_b200.h)."""
     _fields_ = [
@@ -151,6 +164,8 @@ PROTOTYPES = {
     "alad_col_topk_select_workspace_bytes": (C.c_int64, [_I32, _I32, _I32]),
     "alad_col_topk_select": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "alad_topk_merge": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "alad_mrsw_retrieval_workspace_bytes": (C.c_int64, [_I32, _I32, _I32, _I32, _I32]),
+    "alad_mrsw_retrieval": (C.c_int, [C.POINTER(MrswRetrievalArgs), _P]),
     "alad_rank_fused_workspace_bytes": (C.c_int64, [_I32, _I32, _I32, _I32]),
     "alad_rank_fused": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "alad_shortlist_scatter": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P]),
@@ -202,7 +217,7 @@ def lib():
 KERNELS_PER_CALL = {
     "alad_h2d_2d": 0, "alad_pack_tokens": 1, "alad_pool_tokens": 1, "alad_scale_scores": 1, "alad_mrsw_scores_fwd": 1, "alad_scores_fused": 3, "alad_mrsw_scores_bwd": 4,
     "alad_triplet_fwd_bwd": 2, "alad_listnet_fwd_bwd": 3, "alad_rank_rows": 1, "alad_col_gt": 1,
-    "alad_col_count": 1, "alad_col_topk": 1, "alad_col_topk_select": 5, "alad_rank_fused": 6, "alad_topk_merge": 1, "alad_shortlist_scatter": 2,
+    "alad_col_count": 1, "alad_col_topk": 1, "alad_col_topk_select": 5, "alad_rank_fused": 6, "alad_mrsw_retrieval": 0, "alad_topk_merge": 1, "alad_shortlist_scatter": 2,
     "alad_distill_mse_fwd_bwd": 1, "alad_distill_contrastive_fwd_bwd": 2, "alad_distill_ordinal_fwd_bwd": 2,
     "alad_train_losses_fwd": 13, "alad_train_losses_bwd": 16,
     "alad_order_scores": 1, "alad_order_scores_bwd": 1, "alad_normalize_bwd": 1, "alad_pool_tokens_bwd": 1,

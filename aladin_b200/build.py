@@ -8,7 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libalad_b200.so")
-SOURCES = ["cabi.cu", "pack.cu", "mrsw_fwd.cu", "mrsw_fwd_tf32.cu", "fused.cu", "mrsw_bwd.cu", "losses.cu", "train_step.cu", "distill.cu", "misc_sim.cu", "scan_pool.cu", "rank.cu", "pairs.cu", "peer.cu", "h2d.cu"]
+SOURCES = ["cabi.cu", "pack.cu", "mrsw_fwd.cu", "mrsw_fwd_tf32.cu", "fused.cu", "mrsw_bwd.cu", "losses.cu", "train_step.cu", "distill.cu", "misc_sim.cu", "scan_pool.cu", "rank.cu", "retrieval.cu", "pairs.cu", "peer.cu", "h2d.cu"]
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -899,72 +899,52 @@ def lists_host(top1_dev, topk_dev):
 
 
 def streaming_ranks(images, captions, img_lens, cap_lens, n_images, img_start=0, img_step=1, precision=None, block_images=1024,
-                    k=50):
-    """Both directions' ranks and top-k WITHOUT materialising S[Ni, Nc]: the gallery images are scored block by block into
-    one reusable [block_images, Nc] buffer, exactly the way the multi-GPU path scores one block per rank -- i2t ranks are
-    final per block, the t2i "images ahead" counts add up over the blocks and the per-caption top-k lists are merged as they
-    come.  The ground-truth scores the counts compare against come from a first pass over the block diagonal (image
-    block x its own captions, 1 / n_blocks of the work) launched on the same 256-row word units as the full pass, so they
-    are bit-identical to the entries of S they stand for.  For galleries whose score matrix does not fit (0.5 GB at COCO-5k,
-    50 GB at ten times the gallery); results equal rank_both_directions on the dense matrix.
+                    k=50, keep_scores=False):
+    """Both directions' ranks and top-k WITHOUT materialising S[Ni, Nc] (alad_mrsw_retrieval, one native call): the gallery
+    images are scored block by block into one reusable [block_images, Nc] buffer, exactly the way the multi-GPU path scores one
+    block per rank -- i2t ranks are final per block, the t2i "images ahead" counts add up over the blocks and the per-caption
+    top-k lists are merged as they come.  The ground-truth scores the counts compare against come from a first pass over the
+    block diagonal (image block x its own captions, 1 / n_blocks of the work) launched on the same 256-row word units as the
+    full pass, so they are bit-identical to the entries of S they stand for.  For galleries whose score matrix does not fit
+    (0.5 GB at COCO-5k, 50 GB at ten times the gallery); results equal rank_both_directions on the dense matrix.
+    keep_scores=True writes the dense matrix as well (one pass, one ranking) and returns it as a fifth value.
     Returns (ranks_i2t[Ni], top1[Ni], ranks_t2i[Nc], topk[Nc, k]) as float64 numpy arrays."""
-    from .tiling import exclusive_cumsum
+    import ctypes as C
     Ni = int(n_images)
+    if Ni <= 0:
+        raise ValueError("streaming_ranks needs at least one gallery image")
     gal = AlignmentGallery(images, captions, img_lens, cap_lens, n_images=Ni, img_start=img_start, img_step=img_step,
                            precision=precision, world=1, rank=0, bounds=[(0, Ni)])
     Nc = gal.Nc
     k = min(k, Ni)
-    B = max(int(block_images), k, 1)
     words, regions, _ = gal.packed_operands()
     dev = words.data.device
-    roff, n_reg = exclusive_cumsum(gal.nr)
-    roff = np.concatenate([roff, [n_reg]])
-    csum = gal._row_csum()
-    unit = 2 * _cabi.TILE_M
-    n_rows, Kp = words.n_rows, words.Kp
-    blocks = [(lo, min(Ni, lo + B)) for lo in range(0, Ni, B)]
-    S_buf = torch.empty((min(B, Ni), Nc), dtype=torch.float32, device=dev)
-
-    def score(lo, hi, r0, r1, u1):
-        """S_buf[:hi-lo] = scores of images [lo, hi) against the captions whose rows lie in word rows [r0, r1)."""
-        _, table, _ = build_region_tiles(gal.nr[lo:hi], gal.clamp[lo:hi])
-        out = S_buf[:hi - lo]
-        if len(table) == 0 or r1 <= r0:
-            out.zero_()
-            return out
-        tiles_dev = scoring._to_dev(table.view(np.int32).reshape(-1), dev)
-        w = scoring.Packed(words.data[r0:r1], r1 - r0, Kp, None, None, words.row_item[r0:u1 * unit], words.mode)
-        g = scoring.Packed(regions.data[int(roff[lo]):int(roff[hi])], int(roff[hi] - roff[lo]), Kp, None, None, None, regions.mode)
-        scoring.mrsw_scores_packed(w, g, tiles_dev, len(table), hi - lo, Nc, out=out,
-                                   timeline_nc=Nc * (r1 - r0) / max(n_rows, 1))
-        return out
-
-    n_units = (n_rows + unit - 1) // unit
-    gt = torch.zeros(Nc, dtype=torch.float32, device=dev)
-    if regions is not None and n_rows:
-        for lo, hi in blocks:                       # pass 1: the block diagonal -> ground-truth scores
-            c0, c1 = min(Nc, 5 * lo), min(Nc, 5 * hi)
-            if c1 <= c0:
-                continue
-            u0, u1 = int(csum[c0]) // unit, min(n_units, (int(csum[c1]) + unit - 1) // unit)
-            ranking.col_gt(score(lo, hi, u0 * unit, min(u1 * unit, n_rows), u1), gt, 5, lo)
+    nr = np.ascontiguousarray(gal.nr, dtype=np.int32)
+    clamp = np.ascontiguousarray(gal.clamp, dtype=np.uint8)
+    cap_row = np.ascontiguousarray(gal._row_csum(), dtype=np.int64)
+    lib = _cabi.lib()
     rank_i = torch.empty(Ni, dtype=torch.int32, device=dev)
     top1_i = torch.empty(Ni, dtype=torch.int32, device=dev)
-    count = torch.zeros(Nc, dtype=torch.int32, device=dev)
-    run_s = run_i = None
-    for lo, hi in blocks:                           # pass 2: every block against all captions
-        if regions is not None and n_rows:
-            Sb = score(lo, hi, 0, n_rows, n_units)
-        else:
-            Sb = S_buf[:hi - lo].zero_()
-        r, t1, cnt, cs, ci = ranking.rank_fused(Sb, k, lo, gt=gt)
-        rank_i[lo:hi], top1_i[lo:hi] = r, t1
-        count += cnt
-        if run_s is None:
-            run_s, run_i = cs, ci
-        else:
-            run_s, run_i = ranking.topk_merge(torch.stack([run_s, cs]).contiguous(), torch.stack([run_i, ci]).contiguous())
-    return _to_host_f64(rank_i, top1_i, count, run_i)
+    count = torch.empty(Nc, dtype=torch.int32, device=dev)
+    ts = torch.empty((Nc, k), dtype=torch.float32, device=dev)
+    ti = torch.empty((Nc, k), dtype=torch.int32, device=dev)
+    S = torch.empty((Ni, Nc), dtype=torch.float32, device=dev) if keep_scores else None
+    nbytes = int(lib.alad_mrsw_retrieval_workspace_bytes(Ni, Nc, k, int(block_images), 1 if keep_scores else 0))
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+    a = _cabi.MrswRetrievalArgs(
+        words=words.data.data_ptr(), n_word_rows=words.n_rows, row_cap=words.row_item.data_ptr(),
+        regions=regions.data.data_ptr() if regions is not None else None,
+        n_region_rows=regions.n_rows if regions is not None else 0, Kp=words.Kp,
+        operand_format=1 if words.mode == 3 else 0, nr=nr.ctypes.data, clamp=clamp.ctypes.data, cap_row=cap_row.ctypes.data,
+        Ni=Ni, Nc=Nc, group=5, k=k, block_images=int(block_images),
+        S=S.data_ptr() if S is not None else None, ldS=Nc,
+        rank_i2t=rank_i.data_ptr(), top1=top1_i.data_ptr(), rank_t2i=count.data_ptr(), topk_score=ts.data_ptr(),
+        topk_idx=ti.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+    _cabi.check(lib.alad_mrsw_retrieval(C.byref(a), _cabi.stream_ptr()), "alad_mrsw_retrieval")
+    n_blocks = 1 if keep_scores else -(-Ni // max(int(block_images), k, 1))
+    _cabi.launch_count["kernels"] += n_blocks * 9 + (0 if keep_scores else n_blocks * 2)
+    out = _to_host_f64(rank_i, top1_i, count, ti)
+    return out + (S,) if keep_scores else out
 
 
 def _to_host_f64(*tensors):

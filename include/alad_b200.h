@@ -407,6 +407,40 @@ int64_t alad_rank_fused_workspace_bytes(int32_t Ni, int32_t q_rows, int32_t q_co
 int alad_rank_fused(const float* S, int64_t ldS, int32_t Ni, int32_t Nc, int32_t group, int32_t img_off, int32_t q_rows,
                     int32_t q_cols, int32_t k, const float* gt, int32_t* rank, int32_t* top1, int32_t* count,
                     float* out_score, int32_t* out_idx, void* workspace, void* stream);
+/* ---------------------------------------------------------------------------------
+ * alad_mrsw_retrieval -- i2t + t2i of alad/evaluation.py:158-327 from PACKED operands in one call, the score matrix
+ * OPTIONAL: a composition of alad_region_tiles, alad_mrsw_scores_fwd, alad_col_gt, alad_rank_fused and
+ * alad_topk_merge.  S != NULL: the whole [Ni, ldS] matrix is written and ranked.  S == NULL: the images are scored in blocks
+ * of max(block_images, k) rows into one reusable buffer of the workspace -- a first pass over the block diagonal gives the
+ * captions' ground-truth scores (same 256-row word units as the full pass: bit-identical entries), a second pass ranks every
+ * block against all captions, sums the t2i counts and merges the per-caption top-k lists.  Both give the ranking of the
+ * dense matrix exactly.  Image i owns captions group*i .. group*i + group-1.
+ * ------------------------------------------------------------------------------- */
+typedef struct alad_mrsw_retrieval_args {
+  const void* words;             /* packed caption rows [n_word_rows, Kp] (alad_pack_tokens), device          */
+  int64_t n_word_rows;
+  const int32_t* row_cap;        /* device [ceil(n_word_rows/256)*256]: caption of every packed row, -1 padding */
+  const void* regions;           /* packed region rows [n_region_rows, Kp], device                            */
+  int64_t n_region_rows;
+  int32_t Kp;
+  int32_t operand_format;        /* as alad_mrsw_fwd_args: 0 = bf16 rows, 1 = fp32 rows read as TF32           */
+  const int32_t* nr;             /* HOST [Ni]: packed region rows of every image                              */
+  const uint8_t* clamp;          /* HOST [Ni] or NULL: image has masked region slots                          */
+  const int64_t* cap_row;        /* HOST [Nc + 1]: first packed word row of every caption, cap_row[Nc] = n_word_rows */
+  int32_t Ni, Nc, group, k, block_images;
+  float* S;                      /* optional [Ni, ldS]                                                        */
+  int64_t ldS;
+  int32_t* rank_i2t;             /* [Ni]  position of the image's best ground-truth caption                   */
+  int32_t* top1;                 /* [Ni]  arg-max caption                                                     */
+  int32_t* rank_t2i;             /* [Nc]  images ahead of the caption's ground-truth image                    */
+  float* topk_score;             /* [Nc, k]                                                                   */
+  int32_t* topk_idx;             /* [Nc, k] image indices, -1 = fewer than k images                           */
+  void* workspace;               /* alad_mrsw_retrieval_workspace_bytes, 256-byte aligned                     */
+  int64_t workspace_bytes;
+} alad_mrsw_retrieval_args;
+int64_t alad_mrsw_retrieval_workspace_bytes(int32_t Ni, int32_t Nc, int32_t k, int32_t block_images, int32_t with_S);
+int alad_mrsw_retrieval(const alad_mrsw_retrieval_args* a, void* stream);
+
 /* merge P sorted candidate lists per caption (after the all-gather across shards). */
 int alad_topk_merge(const float* cand_score, const int32_t* cand_idx, int32_t P, int32_t Nc, int32_t k,
                     float* out_score, int32_t* out_idx, void* stream);

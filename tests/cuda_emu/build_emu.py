@@ -54,7 +54,7 @@ def build(name, tsan=False):
     return lib
 
 
-FULL_LIBRARY = ["cabi", "pack", "fused", "mrsw_bwd", "losses", "train_step", "distill", "misc_sim", "scan_pool", "rank", "pairs", "peer", "h2d"]
+FULL_LIBRARY = ["cabi", "pack", "fused", "mrsw_bwd", "losses", "train_step", "distill", "misc_sim", "scan_pool", "rank", "retrieval", "pairs", "peer", "h2d"]
 
 
 def build_library(tsan=False):

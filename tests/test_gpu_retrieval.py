@@ -194,6 +194,12 @@ def test_streaming_ranks_equal_the_dense_matrix(block, precision):
     got = retrieval.streaming_ranks(ti, tc, il, cl, Ni, img_start=0, img_step=5, precision=precision, block_images=block, k=50)
     for a, b, name in zip(got, want, ("ranks_i2t", "top1", "ranks_t2i", "top50")):
         np.testing.assert_array_equal(a, b, err_msg=name)
+    if block == 1000:           # the same native call asked to write the matrix as well: one pass, identical scores and ranking
+        got = retrieval.streaming_ranks(ti, tc, il, cl, Ni, img_start=0, img_step=5, precision=precision, block_images=block, k=50,
+                                        keep_scores=True)
+        for a, b, name in zip(got, want, ("ranks_i2t", "top1", "ranks_t2i", "top50")):
+            np.testing.assert_array_equal(a, b, err_msg=name)
+        assert torch.equal(got[4], S)
 
 
 def test_oversized_gallery_takes_the_streaming_path(monkeypatch):

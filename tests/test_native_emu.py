@@ -92,3 +92,26 @@ def test_block_mode_of_i2t_on_a_small_gallery(virtual_b200, agg):
     np.testing.assert_allclose(S, ref, rtol=1e-4, atol=1e-5)
     np.testing.assert_array_equal(ranks, O.i2t_ranks(ref)[0])
     assert evaluation._cache["key"][-2] == f"block:{agg}"
+
+
+@pytest.mark.parametrize("block,keep", [(16, False), (100, False), (100, True)])
+def test_native_streaming_retrieval_on_a_small_gallery(virtual_b200, block, keep):
+    """alad_mrsw_retrieval (the native block-by-block composition behind retrieval.streaming_ranks): ranks, top-1 and top-k
+    equal the ranking of the dense matrix -- several blocks with a ragged last one, one block, and the variant that also
+    writes the matrix.  (The GPU test of the same function runs a 333-image gallery; too slow for the emulator.)"""
+    import numpy as np
+    import torch
+    from aladin_b200 import retrieval, synth
+    Ni, k = 41, 10
+    images, captions, il, cl = synth.eval_containers(5, Ni, 24, 64, max_regions=12, max_words=14, alpha=0.3)
+    il[5 * 3:5 * 3 + 5] = [1] * 5                  # an image without regions
+    cl[7] = cl[101] = 3                            # captions without words
+    ti, tc = torch.from_numpy(images), torch.from_numpy(captions)
+    S = retrieval.AlignmentGallery(ti, tc, il, cl, n_images=Ni, img_start=0, img_step=5, precision="bf16").scores()
+    want = retrieval.rank_both_directions(S, Ni, k=k)
+    got = retrieval.streaming_ranks(ti, tc, il, cl, Ni, img_start=0, img_step=5, precision="bf16", block_images=block, k=k,
+                                    keep_scores=keep)
+    for a, b, name in zip(got, want, ("ranks_i2t", "top1", "ranks_t2i", "topk")):
+        np.testing.assert_array_equal(a, b, err_msg=name)
+    if keep:
+        assert torch.equal(got[4], S)
