@@ -102,4 +102,25 @@ def also_block(pk, quick=False):
             "what": "fp32 operands read as TF32 by the tensor core (half the bf16 rate, twice the operand bytes)"}
     # ---- config 5: two-stage retrieval
     out["config5_two_stage_coco5k"] = P2.measure(5000, 25000, 100, world=1, steps=3, warmup=2)
+    # ---- the HBM-bound kernels around the scoring kernel (north_star: "achieved HBM GB/s for the loss and top-k kernels"):
+    # ranking of a COCO-5k-sized score matrix (two reads of S) and the B x B losses, CUDA events, algorithmic bytes.
+    # Own guard: a failure here must not take the configs above with it.
+    try:
+        import hbm_probe as HP
+        rk = HP.ranking_part()
+        ls = [HP.loss_part(8192), HP.loss_part(512)]
+        hbm = pk.get("hbm_gbs")
+        out["hbm_kernels"] = {
+            "ranking_coco5k": {"ms": rk["fused_ms"], "reads_of_S": 2, "one_purpose_kernels_ms": rk["separate_ms"],
+                               "algorithmic_bytes": rk["sweep_bytes"], "GBs_algorithmic": rk["fused_GBs_algorithmic"],
+                               "frac_of_hbm_peak": rk["fused_GBs_algorithmic"] / hbm if hbm else None,
+                               "equals_one_purpose_kernels": rk["fused_equals_separate"] and rk["masked_equal"]},
+            "losses": [{"B": l["B"], "triplet_ms": l["triplet_ms"], "triplet_GBs_algorithmic": l["triplet_GBs_algorithmic"],
+                        "listnet_ms": l["listnet_ms"], "listnet_GBs_algorithmic": l["listnet_GBs_algorithmic"],
+                        "listnet_frac_of_hbm_peak": l["listnet_GBs_algorithmic"] / hbm if hbm else None,
+                        "listnet_loss_rel_err_vs_fp64": l["listnet_loss_rel_err"],
+                        "listnet_grad_err_vs_fp64": l["listnet_grad_max_err_rel_to_max"]} for l in ls],
+            "what": "CUDA-event times; algorithmic bytes = 4*Ni*Nc (one reading of S), 8*B^2 (triplet), 16*B^2 (listnet)"}
+    except Exception as e:                          # noqa: BLE001
+        out["hbm_kernels"] = {"error": f"{type(e).__name__}: {e}"}
     return out
