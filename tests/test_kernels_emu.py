@@ -230,7 +230,7 @@ def _fused(rank, S, Nc, q_rows, q_cols, k, img_off, gt, want_count):
 
 
 @pytest.mark.parametrize("Ni,Nc,q_rows,q_cols,k,img_off,mode", [(264, 60, 264, 60, 10, 0, "own")] + big(
-    (300, 204, 300, 204, 10, 0, "ties"), (264, 2052, 200, 400, 10, 3, "given"), (260, 52, 260, 52, 10, 0, "nocount"),
+    (264, 2052, 200, 400, 10, 3, "given"), (260, 52, 260, 52, 10, 0, "nocount"),
     (260, 48, 260, 48, 10, 0, "masked"), (40, 61, 40, 61, 10, 0, "own"),
     (264, 60, 0, 60, 10, 0, "own")))                    # no i2t queries (ranking.t2i_rank_topk)
 def test_rank_fused_emulated(rank, Ni, Nc, q_rows, q_cols, k, img_off, mode):
@@ -249,6 +249,17 @@ def test_rank_fused_emulated(rank, Ni, Nc, q_rows, q_cols, k, img_off, mode):
         gt = r.standard_normal(q_cols).astype(np.float32)
         gt[::3] = S[(np.arange(q_cols) // 5) % Ni, np.arange(q_cols)][::3]
     rk, top1, cnt, ts, ti = _fused(rank, S, Nc, q_rows, q_cols, k, img_off, gt if mode == "given" else None, mode != "nocount")
+    if TSAN:        # the sanitizer run is about the fused kernels' barriers: numpy is the checker, not the one-purpose kernels
+        for i in range(q_rows):
+            inds = _stable_desc(S[i])
+            pos = np.empty(Nc, np.int64)
+            pos[inds] = np.arange(Nc)
+            assert top1[i] == inds[0] and rk[i] == (pos[5 * i:5 * i + 5].min() if 5 * i < Nc else Nc)
+        for c in range(q_cols):
+            inds = _stable_desc(S[:, c])
+            assert cnt[c] == np.where(inds == c // 5)[0][0]
+            np.testing.assert_array_equal(ti[c], inds[:k])
+        return
     # the one-purpose kernels on the same block
     rk0, top10 = np.zeros(q_rows, np.int32), np.zeros(q_rows, np.int32)
     ok(rank, rank.alad_rank_rows(p(S), Nc, q_rows, Nc, 5, img_off, p(rk0), p(top10), None))
